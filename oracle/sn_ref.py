@@ -1,0 +1,184 @@
+"""CPU oracle for the SNGNN similarity-navigated aggregation path.
+
+TEST INFRASTRUCTURE ONLY.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+`cpu_baseline` / `--impl reference` legs may import this module; the product package
+`sngnn_b200/` never does (it fails loudly when its CUDA library is missing).
+
+It is a *restatement* (plain torch on CPU, functional style, autograd-capable) of
+    R: models/models.py:116-158   SNConv_plus_plus.forward / message
+    R: models/models.py:233-263   SNConv_plus.forward / message
+    R: models/models.py:322-334   SNConv.forward / message
+    R: models/models.py:76-86     layer stack (relu -> [BN] -> dropout, log_softmax)
+following SURVEY.md Appendix A.  Parity pin: `tests/golden/*.pt` are outputs of the reference's
+own unmodified `models.py` executed through `oracle/shims.py` (see `oracle/make_golden.py`);
+`tests/test_oracle_golden.py` checks this file against them.  The third-party pieces the
+reference delegates to (torch_scatter.scatter_max tie-break, PyG propagate) are restated from
+their published behaviour, so for those parts: PARITY UNPINNED (documented in DESIGN.md).
+"""
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-12  # F.normalize default eps, R: models/models.py:122
+
+
+def process_edges(edge_index, num_nodes, remove_self_loops):
+    """R: models/models.py:117-120 (add N loops at the end, then optionally drop every src==dst)."""
+    loop = torch.arange(num_nodes, dtype=edge_index.dtype)
+    ei = torch.cat([edge_index, torch.stack([loop, loop])], dim=1)
+    if remove_self_loops:
+        ei = ei[:, ei[0] != ei[1]]
+    return ei
+
+
+def edge_rank(score, dst):
+    """Rank of every edge inside its target's list under (score desc, position asc).
+
+    Equivalent to the k-round scatter_max / knock-out loop of R: models/models.py:145-154:
+    round t picks, per target, the best not-yet-picked edge, first position on ties."""
+    E = score.numel()
+    pos = torch.arange(E)
+    o1 = torch.argsort(-score.detach(), stable=True)          # score desc, position asc
+    o2 = torch.argsort(dst[o1], stable=True)                   # group by target, keep order
+    order = o1[o2]
+    d_sorted = dst[order]
+    start = torch.ones(E, dtype=torch.bool)
+    if E:
+        start[1:] = d_sorted[1:] != d_sorted[:-1]
+    first = torch.where(start, pos, torch.zeros_like(pos)).cummax(0).values
+    rank = torch.empty(E, dtype=torch.long)
+    rank[order] = pos - first
+    return rank
+
+
+def edge_select(score, dst, top_k, thr):
+    """Boolean mask of selected edges: rank < top_k and score >= thr (the descending scan stops at
+    the first score below thr, which for a sorted list is the same thing)."""
+    return (edge_rank(score, dst) < top_k) & (score.detach() >= thr)
+
+
+def sn_aggregate(h, ei, top_k=None, thr=None):
+    """out_1 of R: models/models.py:132,239,326 = PyG propagate(aggr='mean') of the messages.
+
+    top_k=None -> base SNConv (every edge weighted by its cosine, R: :331-334)."""
+    N = h.size(0)
+    src, dst = ei[0], ei[1]
+    n = F.normalize(h, p=2.0, dim=-1, eps=EPS)
+    s = (n[dst] * n[src]).sum(-1)
+    if top_k is None:
+        w = s
+    else:
+        w = torch.where(edge_select(s, dst, top_k, thr), s, torch.zeros_like(s))
+    msg = w[:, None] * h[src]
+    tot = torch.zeros(N, h.size(1), dtype=h.dtype).index_add(0, dst, msg)
+    deg = torch.zeros(N, dtype=h.dtype).index_add(0, dst, torch.ones(dst.numel(), dtype=h.dtype))
+    return tot / deg.clamp(min=1)[:, None]
+
+
+def structural_term(ei, w_weight, w_bias, num_nodes):
+    """out_0 of R: models/models.py:124-130: A @ W^T + b with A[src - min(src), dst] += 1."""
+    src, dst = ei[0], ei[1]
+    if src.numel():
+        src = src - src.min()
+    wt = w_weight.t()                                   # [N, C]
+    out0 = torch.zeros(num_nodes, wt.size(1), dtype=wt.dtype).index_add(0, src, wt[dst])
+    return out0 + w_bias
+
+
+def snconv(x, edge_index, lin_w, lin_b, bias=None):
+    """R: models/models.py:322-329."""
+    ei = process_edges(edge_index, x.size(0), False)
+    out = sn_aggregate(F.linear(x, lin_w, lin_b), ei)
+    return out if bias is None else out + bias
+
+
+def snconv_plus(x, edge_index, lin_w, lin_b, top_k, thr, remove_self_loops, bias=None):
+    """R: models/models.py:233-242."""
+    ei = process_edges(edge_index, x.size(0), remove_self_loops)
+    out = sn_aggregate(F.linear(x, lin_w, lin_b), ei, top_k, thr)
+    return out if bias is None else out + bias
+
+
+def snconv_plus_plus(x, edge_index, lin_w, lin_b, w_w, w_b, beta, top_k, thr, remove_self_loops, bias=None):
+    """R: models/models.py:116-137."""
+    N = x.size(0)
+    ei = process_edges(edge_index, N, remove_self_loops)
+    out1 = sn_aggregate(F.linear(x, lin_w, lin_b), ei, top_k, thr)
+    out0 = structural_term(ei, w_w, w_b, N)
+    out = beta * out0 + (1 - beta) * out1
+    return out if bias is None else out + bias
+
+
+def stack_forward(kind, params, x, edge_index, *, top_k=None, thr=None, remove_self_loops=True,
+                  bns=None, dropout_p=0.0, training=False):
+    """R: models/models.py:76-86 / 201-211 / 293-303.  `params` = list of per-layer dicts with keys
+    lin_w, lin_b [, w_w, w_b, beta] [, bias].  BatchNorm modules (if any) are passed in `bns`."""
+    for l, p in enumerate(params):
+        if kind == "SNGNN":
+            x = snconv(x, edge_index, p["lin_w"], p["lin_b"], p.get("bias"))
+        elif kind == "SNGNN_Plus":
+            x = snconv_plus(x, edge_index, p["lin_w"], p["lin_b"], top_k, thr, remove_self_loops, p.get("bias"))
+        else:
+            x = snconv_plus_plus(x, edge_index, p["lin_w"], p["lin_b"], p["w_w"], p["w_b"], p["beta"],
+                                 top_k, thr, remove_self_loops, p.get("bias"))
+        if l < len(params) - 1:
+            x = F.relu(x)
+            if bns is not None:
+                x = bns[l](x)
+            x = F.dropout(x, dropout_p, training)
+    return F.log_softmax(x, dim=1)
+
+
+def params_from_state_dict(sd, num_layers):
+    """state_dict keys of the reference models: lins.{l}.lin.{weight,bias}, .w.{weight,bias}, .beta, .bias."""
+    out = []
+    for l in range(num_layers):
+        p = {"lin_w": sd[f"lins.{l}.lin.weight"], "lin_b": sd[f"lins.{l}.lin.bias"]}
+        if f"lins.{l}.w.weight" in sd:
+            p.update(w_w=sd[f"lins.{l}.w.weight"], w_b=sd[f"lins.{l}.w.bias"], beta=sd[f"lins.{l}.beta"])
+        if f"lins.{l}.bias" in sd:
+            p["bias"] = sd[f"lins.{l}.bias"]
+        out.append(p)
+    return out
+
+
+# ----------------------------------------------------------------------------- all-pairs mode
+def rownorm(x):
+    return F.normalize(x, p=2.0, dim=-1, eps=EPS)
+
+
+def simknn_allpairs(x, top_k, thr, remove_self, q_lo=0, q_hi=None, block=1024, dtype=torch.float32):
+    """All-pairs similarity-kNN = "the reference selection rule on the complete graph" (SURVEY.md §0):
+    candidates of query i are all nodes j (minus i if remove_self), ranked (cos desc, j asc), at most
+    top_k, cut at the first cos < thr.  Blocking follows R: SimGFAToolbox/dense.py:17-27.
+    Returns idx [nq,k] int64 (-1 padded), sim [nq,k] (0 padded), cnt [nq]."""
+    N = x.size(0)
+    q_hi = N if q_hi is None else q_hi
+    n = rownorm(x.to(dtype))
+    k = min(top_k, N)
+    idx = torch.full((q_hi - q_lo, top_k), -1, dtype=torch.long)
+    sim = torch.zeros(q_hi - q_lo, top_k, dtype=dtype)
+    cnt = torch.zeros(q_hi - q_lo, dtype=torch.long)
+    for lo in range(q_lo, q_hi, block):
+        hi = min(lo + block, q_hi)
+        s = n[lo:hi] @ n.t()
+        if remove_self:
+            r = torch.arange(lo, hi)
+            s[r - lo, r] = float("-inf")
+        v, j = torch.sort(s, dim=1, descending=True, stable=True)
+        v, j = v[:, :k], j[:, :k]
+        ok = v >= thr
+        c = ok.long().cumprod(1).sum(1)
+        keep = torch.arange(k)[None, :] < c[:, None]
+        idx[lo - q_lo:hi - q_lo, :k] = torch.where(keep, j, torch.full_like(j, -1))
+        sim[lo - q_lo:hi - q_lo, :k] = torch.where(keep, v, torch.zeros_like(v))
+        cnt[lo - q_lo:hi - q_lo] = c
+    return idx, sim, cnt
+
+
+def knn_mean_aggregate(h, idx, sim, cnt, denom):
+    """Cosine-weighted mean over an emitted kNN list; denom [nq] (candidate count or selected count)."""
+    k = idx.size(1)
+    keep = torch.arange(k)[None, :] < cnt[:, None]
+    j = idx.clamp(min=0)
+    msg = torch.where(keep, sim, torch.zeros_like(sim))[:, :, None] * h[j]
+    return msg.sum(1) / denom.clamp(min=1).to(h.dtype)[:, None]
