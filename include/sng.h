@@ -1,0 +1,164 @@
+/*
+ * sng.h -- C ABI of libsng.so, the B200 (sm_100a) implementation of SNGNN's similarity-navigated
+ *          aggregation hot path.
+ *
+ * The reference (MinhZou/SNGNN) is pure Python; it has no FFI.  What this library replaces are the
+ * torch / torch_scatter / torch_sparse / PyG calls issued by the functions cited at each entry point
+ * ("R:" = /root/reference).  The Python binding a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (row-major, contiguous unless an `ld*`
+ *     leading dimension in ELEMENTS is given); the library never allocates and keeps no reference
+ *     after return, except work enqueued on `stream`
+ *   - `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); all calls are
+ *     asynchronous with respect to the host
+ *   - sizes are int64_t; node / edge ids on the device are int32_t (N, E < 2^31)
+ *   - return value: 0 ok, <0 error; sng_last_error() gives a thread-local message
+ *   - feature rows handed to the edge kernels must be padded to a multiple of 4 floats (16-byte rows);
+ *     padding columns must be zero (the host layer does this, sngnn_b200/functional.py)
+ */
+#ifndef SNG_H_
+#define SNG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SNG_API __attribute__((visibility("default")))
+#else
+#define SNG_API
+#endif
+
+#define SNG_OK 0
+#define SNG_ERR_ARG (-1)         /* bad argument */
+#define SNG_ERR_UNSUPPORTED (-2) /* shape not supported by this build */
+#define SNG_ERR_CUDA (-3)        /* CUDA runtime/driver error */
+#define SNG_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define SNG_MAX_TOPK 64          /* edge path: top_k <= 64; top_k <= 0 means "select every edge" */
+#define SNG_KNN_MAX_TOPK 64      /* all-pairs builder */
+
+SNG_API int sng_version(void);
+SNG_API const char* sng_last_error(void);
+/* SM count / compute capability of the current device; fails (SNG_ERR_CUDA) when there is no GPU. */
+SNG_API int sng_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * K0  row normalisation: xhat = x / max(||x||_2, 1e-12)
+ * replaces F.normalize(x, p=2, dim=-1) at R: models/models.py:122,238,325 and
+ * R: SimGFAToolbox/dense.py:15,35,67,106,139,159.
+ * Any of the three outputs may be NULL.  Output rows are zero-padded up to their leading dimension
+ * (ld_f32 >= d, ld_f16 >= d); xhat_f16 is IEEE binary16 (the tensor-core operand of K1).
+ */
+SNG_API int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx,
+                    float* xhat_f32, int64_t ld_f32,
+                    uint16_t* xhat_f16, int64_t ld_f16,
+                    float* inv_norm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  fused edge-restricted similarity / selection / mean aggregation (forward)
+ * replaces SNConv_plus(_plus).message + PyG propagate(aggr='mean')
+ *   R: models/models.py:132,139-158 (++), :239,244-263 (+), :326,331-334 (base, top_k <= 0)
+ * For every target row i with in-edge list [rowptr[i], rowptr[i+1]) of CSR-by-target (sources in `col`,
+ * kept in original edge-position order):
+ *   s_e   = <h_i/r_i , h_j/r_j>,  r = max(||h||, 1e-12)
+ *   S_i   = first min(top_k, deg) edges under (s desc, position asc), cut at the first s < thr
+ *   out[i]= (1/max(deg_i,1)) * sum_{e in S_i} s_e * h[src_e]
+ * Saved for backward (top_k > 0): sel_src [n,top_k] (source ids, rank order, -1 padded),
+ * sel_w [n,top_k] (s_e), sel_cnt [n].  With top_k <= 0 those three may be NULL.
+ */
+SNG_API int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t c, int64_t ldh,
+                          const int32_t* rowptr, const int32_t* col,
+                          int top_k, float thr,
+                          float* out, int64_t ldo,
+                          int32_t* sel_src, float* sel_w, int32_t* sel_cnt,
+                          void* stream);
+
+/* K2b backward of the above w.r.t. h (closed form of SURVEY.md §3.4).
+ * Pass 1 scatters into the two zero-initialised accumulators dval, dnrm [n, c] (float atomics);
+ * pass 2 writes dh = dval + (dnrm - n (n . dnrm)) / r.   `g` = dL/dout [n,c].
+ * top_k > 0: uses the saved selection lists (inv_denom[i] = 1/max(deg_i,1));
+ * top_k <= 0: iterates the CSR (every edge selected). */
+SNG_API int sng_edge_agg_bwd(const float* h, const float* g, int64_t n, int64_t c, int64_t ld,
+                     const int32_t* rowptr, const int32_t* col,
+                     int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_cnt,
+                     const float* inv_denom,
+                     float* dval, float* dnrm, float* dh, void* stream);
+
+/* Aggregation from a selection list only (all-pairs mode: list = emitted kNN):
+ * out[i] = inv_denom[i] * sum_{t<cnt[i]} w[i,t] * h[src[i,t]]. */
+SNG_API int sng_list_agg_fwd(const float* h, int64_t n_rows, int64_t c, int64_t ldh,
+                     int list_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_cnt,
+                     const float* inv_denom, float* out, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  CSR x dense gather-reduce ("mean-aggregation SpMM")
+ *   out[i] = rowscale[i] * sum_{e in row i} val[e] * x[col[e]]  + bias
+ * val / rowscale / bias may be NULL (1 / 1 / 0).  Replaces torch.sparse mm at R: models/models.py:130
+ * (A @ W^T), its transpose in backward, and scatter(reduce='mean') on an emitted kNN CSR.
+ */
+SNG_API int sng_spmm_fwd(const float* x, int64_t n_rows, int64_t c, int64_t ldx,
+                 const int32_t* rowptr, const int32_t* col, const float* val,
+                 const float* rowscale, const float* bias,
+                 float* out, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K4  SNGNN++ fusion: out0 = A @ Wt + b_w (gather of Wt rows over OUT-neighbours), then
+ *     out = beta*out0 + (1-beta)*out1 (+ bias).   R: models/models.py:124-136.
+ * `beta` is a device scalar (the learnable parameter).  out0 is written too (needed for dL/dbeta).
+ */
+SNG_API int sng_pp_fuse_fwd(const float* wt, int64_t n, int64_t c, int64_t ld,
+                    const int32_t* rowptr_out, const int32_t* col_out,
+                    const float* b_w, const float* beta, const float* out1, const float* bias,
+                    float* out0, float* out, void* stream);
+
+/* dbeta += sum((out0 - out1) * g); dbeta is a zero-initialised device scalar. */
+SNG_API int sng_pp_beta_grad(const float* out0, const float* out1, const float* g, int64_t numel,
+                     float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SDDMM cosine at given edges: s[e] = <xhat[a[e]], xhat[b[e]]> (xhat already normalised, FP32).
+ * replaces index_select x2 + mul + sum at R: SimGFAToolbox/dense.py:152-164 and the per-node mm of :53-58.
+ */
+SNG_API int sng_sddmm_dot(const float* xhat, int64_t n, int64_t d, int64_t ld,
+                  const int32_t* a, const int32_t* b, int64_t num_edges, float* s, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  all-pairs similarity-kNN builder (tcgen05 / TMA / TMEM), never materialising the N x N matrix.
+ *   xq_f16  [nq , ldh]  normalised query rows  (FP16, zero padded, ldh % 8 == 0, ldh >= 16*ceil(d/16), 16-byte aligned)
+ *   xall_f16[n  , ldh]  normalised database rows
+ *   query row r is global node q_offset + r (used for remove_self and for sharding by query rows)
+ * Stage 1 (tensor cores) keeps, per query row, the `cand` best FP16-scored columns (cand >= top_k + margin).
+ * Stage 2 rescores them in FP32 (xq_f32 / xall_f32, leading dim ld32 % 4 == 0, zero padded), orders them by
+ * (sim desc, index asc), applies thr / top_k and PROVES exactness: a row whose k-th exact score is not clear
+ * of the best possible score of any dropped column is flagged and recomputed by an exact FP32 scan (stage 3).
+ * Outputs: idx [nq, top_k] int32 (-1 padded), sim [nq, top_k], cnt [nq]; n_fallback (device int32) counts
+ * rows that needed stage 3.
+ * Replaces (as "the reference rule on the complete graph") the selection of
+ * R: models/models.py:145-156 and the blocked X X^T of R: SimGFAToolbox/dense.py:17-27.
+ */
+SNG_API size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, int top_k);
+SNG_API int sng_simknn_build(const uint16_t* xq_f16, const uint16_t* xall_f16, int64_t ldh,
+                     const float* xq_f32, const float* xall_f32, int64_t ld32,
+                     int64_t nq, int64_t q_offset, int64_t n, int64_t d,
+                     int top_k, float thr, int remove_self,
+                     int32_t* idx, float* sim, int32_t* cnt, int32_t* n_fallback,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stage 1 only (profiling / tests): cand_idx / cand_val [nq, nsplit, cand], cand_min [nq, nsplit] (worst kept
+ * score of a list that filled up, else -inf).  force_mb in {0,1,2} picks the rows-per-CTA variant (0 = auto),
+ * force_nsplit > 0 the number of column splits; *nsplit_out receives the value used (size the outputs for 8). */
+SNG_API int sng_simknn_stage1(const uint16_t* xq_f16, const uint16_t* xall_f16, int64_t ldh,
+                      int64_t nq, int64_t q_offset, int64_t n, int64_t d,
+                      int cand, float thr_lo, int remove_self,
+                      int32_t* cand_idx, float* cand_val, float* cand_min,
+                      int force_mb, int force_nsplit, int* nsplit_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNG_H_ */

@@ -1,0 +1,498 @@
+// Edge-restricted similarity / selection / aggregation kernels (K0, K2, K2b, K3, K4, SDDMM).
+//
+// All of these are HBM/L2-gather bound: one warp owns one target row; a group of
+// G = C/4 lanes owns one in-edge at a time and fetches its source row with ONE 128-bit load per lane, so
+// a warp step touches 32/G full rows (coalesced 16..512-byte segments).  Scores, selection and the
+// weighted reduction never leave registers / shared memory; nothing of size E is written.
+//
+// Reference call sites replaced: R: models/models.py:121-137,139-158 (++), :233-263 (+), :322-334 (base).
+#include "sng_common.cuh"
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+namespace sng {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+template <int G> struct Unroll { static constexpr int value = (G >= 4) ? 4 : G; };
+
+// ------------------------------------------------------------------------------------------ K0
+__global__ void __launch_bounds__(kThreads) rownorm_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
+                                                          float* __restrict__ xf, int ldf, __half* __restrict__ xh, int ldh,
+                                                          float* __restrict__ inv) {
+    const int lane = threadIdx.x & 31;
+    int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int kmax = max(xf ? ldf : 0, xh ? ldh : 0);
+    for (; row < n; row += stride) {
+        const float* xr = x + row * ldx;
+        float ss = 0.f;
+        for (int k = lane; k < d; k += 32) { float v = __ldg(xr + k); ss = fmaf(v, v, ss); }
+        ss = group_sum<32>(ss);
+        const float r = fmaxf(sqrtf(ss), kNormEps);
+        if (inv && lane == 0) inv[row] = 1.0f / r;
+        for (int k = lane; k < kmax; k += 32) {
+            const float v = k < d ? __ldg(xr + k) / r : 0.f;     // true division, as F.normalize does; zero padding beyond d
+            if (xf && k < ldf) xf[row * ldf + k] = v;
+            if (xh && k < ldh) xh[row * ldh + k] = __float2half_rn(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2 forward
+// Sorted (score desc, arrival order on ties) candidate list of one warp, in shared memory.
+struct TopList {
+    float* s;
+    int* j;
+    int cnt;
+    float kth;   // score of the last entry once the list is full, else -inf
+    __device__ __forceinline__ void insert(float sc, int src, int top_k, int lane) {
+        // number of entries that stay in front: those with score >= sc (earlier position wins ties)
+        int pos = 0;
+        for (int t0 = 0; t0 < cnt; t0 += 32) {
+            const int t = t0 + lane;
+            pos += __popc(__ballot_sync(0xffffffffu, t < cnt && s[t] >= sc));
+        }
+        const int ncnt = min(cnt + 1, top_k);
+        // shift [pos, ncnt-1) one slot down; top_k <= 64 => two slots per lane
+        float a0 = 0.f, a1 = 0.f; int b0 = 0, b1 = 0;
+        const int t0 = lane, t1 = lane + 32;
+        const bool m0 = t0 > pos && t0 < ncnt, m1 = t1 > pos && t1 < ncnt;
+        if (m0) { a0 = s[t0 - 1]; b0 = j[t0 - 1]; }
+        if (m1) { a1 = s[t1 - 1]; b1 = j[t1 - 1]; }
+        __syncwarp();
+        if (m0) { s[t0] = a0; j[t0] = b0; }
+        if (m1) { s[t1] = a1; j[t1] = b1; }
+        if (lane == 0) { s[pos] = sc; j[pos] = src; }
+        __syncwarp();
+        cnt = ncnt;
+        kth = (cnt == top_k) ? s[top_k - 1] : -CUDART_INF_F;
+    }
+};
+
+template <int G, bool SELECT_ALL>
+__global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
+    const float* __restrict__ h, int n, int c, int64_t ldh, const int* __restrict__ rowptr, const int* __restrict__ col,
+    int top_k, float thr, float* __restrict__ out, int64_t ldo,
+    int* __restrict__ sel_src, float* __restrict__ sel_w, int* __restrict__ sel_cnt) {
+    constexpr int EPW = 32 / G;                 // edges per warp step
+    constexpr int U = Unroll<G>::value;         // steps whose loads are issued together
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G, c4 = q * 4;
+    const bool ch_ok = c4 < c;
+    TopList L;
+    L.s = smem + (size_t)warp * 2 * max(top_k, 1);
+    L.j = reinterpret_cast<int*>(L.s + max(top_k, 1));
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < n; row += gridDim.x * kWarpsPerBlock) {
+        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        const float4 hi = ch_ok ? ldg4(h + (int64_t)row * ldh + c4) : z4;
+        const float4 ni = scale4(hi, inv_norm_of(group_sum<G>(dot4(hi, hi))));
+        float4 acc = z4;
+        L.cnt = 0; L.kth = -CUDART_INF_F;
+
+        for (int base = beg; base < end; base += 32) {
+            const int nchunk = min(32, end - base);
+            const int jl = lane < nchunk ? __ldg(col + base + lane) : -1;
+            for (int st = 0; st < nchunk; st += EPW * U) {
+                float4 v[U]; int j[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = st + u * EPW + grp;
+                    j[u] = __shfl_sync(0xffffffffu, jl, e & 31);
+                    if (e >= nchunk) j[u] = -1;
+                    v[u] = (j[u] >= 0 && ch_ok) ? ldg4(h + (int64_t)j[u] * ldh + c4) : z4;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (st + u * EPW >= nchunk) break;                       // warp-uniform
+                    const float d = group_sum<G>(dot4(ni, v[u]));
+                    const float ss = group_sum<G>(dot4(v[u], v[u]));
+                    const float sc = d * inv_norm_of(ss);
+                    if (SELECT_ALL) {
+                        if (j[u] >= 0) fma4(acc, sc, v[u]);
+                    } else {
+#pragma unroll
+                        for (int g2 = 0; g2 < EPW; ++g2) {                   // edges in position order
+                            const float sg = __shfl_sync(0xffffffffu, sc, g2 * G);
+                            const int jg = __shfl_sync(0xffffffffu, j[u], g2 * G);
+                            if (jg >= 0 && sg >= thr && (L.cnt < top_k || sg > L.kth)) L.insert(sg, jg, top_k, lane);
+                        }
+                    }
+                }
+            }
+        }
+        if (!SELECT_ALL) {
+            for (int st = 0; st < L.cnt; st += EPW) {
+                const int t = st + grp;
+                if (t < L.cnt && ch_ok) fma4(acc, L.s[t], ldg4(h + (int64_t)L.j[t] * ldh + c4));
+            }
+            for (int t = lane; t < top_k; t += 32) {
+                sel_src[(int64_t)row * top_k + t] = t < L.cnt ? L.j[t] : -1;
+                sel_w[(int64_t)row * top_k + t] = t < L.cnt ? L.s[t] : 0.f;
+            }
+            if (lane == 0) sel_cnt[row] = L.cnt;
+            __syncwarp();
+        }
+        acc.x = cross_group_sum<G>(acc.x); acc.y = cross_group_sum<G>(acc.y);
+        acc.z = cross_group_sum<G>(acc.z); acc.w = cross_group_sum<G>(acc.w);
+        if (grp == 0 && ch_ok) {
+            const float invd = 1.0f / (float)max(end - beg, 1);
+            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + c4) = scale4(acc, invd);
+        }
+    }
+}
+
+// list-only aggregation (all-pairs mode)
+template <int G>
+__global__ void __launch_bounds__(kThreads) list_agg_fwd_kernel(
+    const float* __restrict__ h, int n_rows, int c, int64_t ldh, int list_k, const int* __restrict__ sel_src,
+    const float* __restrict__ sel_w, const int* __restrict__ sel_cnt, const float* __restrict__ inv_denom,
+    float* __restrict__ out, int64_t ldo) {
+    constexpr int EPW = 32 / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G, c4 = q * 4;
+    const bool ch_ok = c4 < c;
+    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < n_rows; row += gridDim.x * kWarpsPerBlock) {
+        const int cnt = min(__ldg(sel_cnt + row), list_k);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int st = 0; st < cnt; st += EPW) {
+            const int t = st + grp;
+            if (t < cnt && ch_ok) {
+                const int j = __ldg(sel_src + (int64_t)row * list_k + t);
+                fma4(acc, __ldg(sel_w + (int64_t)row * list_k + t), ldg4(h + (int64_t)j * ldh + c4));
+            }
+        }
+        acc.x = cross_group_sum<G>(acc.x); acc.y = cross_group_sum<G>(acc.y);
+        acc.z = cross_group_sum<G>(acc.z); acc.w = cross_group_sum<G>(acc.w);
+        if (grp == 0 && ch_ok)
+            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + c4) = scale4(acc, inv_denom ? __ldg(inv_denom + row) : 1.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K2b backward
+template <int G, bool SELECT_ALL>
+__global__ void __launch_bounds__(kThreads) edge_agg_bwd_scatter_kernel(
+    const float* __restrict__ h, const float* __restrict__ g, int n, int c, int64_t ld, const int* __restrict__ rowptr,
+    const int* __restrict__ col, int top_k, const int* __restrict__ sel_src, const float* __restrict__ sel_w,
+    const int* __restrict__ sel_cnt, const float* __restrict__ inv_denom, float* __restrict__ dval, float* __restrict__ dnrm) {
+    constexpr int EPW = 32 / G;
+    constexpr int U = Unroll<G>::value;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G, c4 = q * 4;
+    const bool ch_ok = c4 < c;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < n; row += gridDim.x * kWarpsPerBlock) {
+        int beg, cnt;
+        float invd;
+        if (SELECT_ALL) {
+            beg = __ldg(rowptr + row);
+            cnt = __ldg(rowptr + row + 1) - beg;
+            invd = 1.0f / (float)max(cnt, 1);
+        } else {
+            beg = 0;
+            cnt = __ldg(sel_cnt + row);
+            invd = __ldg(inv_denom + row);
+        }
+        if (cnt == 0) continue;
+        const float4 hi = ch_ok ? ldg4(h + (int64_t)row * ld + c4) : z4;
+        const float4 ni = scale4(hi, inv_norm_of(group_sum<G>(dot4(hi, hi))));
+        const float4 gs = ch_ok ? scale4(ldg4(g + (int64_t)row * ld + c4), invd) : z4;     // g_i / deg_i
+        float4 dni = z4;
+        for (int st = 0; st < cnt; st += EPW * U) {
+            float4 v[U]; int j[U]; float w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = st + u * EPW + grp;
+                j[u] = -1; w[u] = 0.f;
+                if (t < cnt) {
+                    if (SELECT_ALL) j[u] = __ldg(col + beg + t);
+                    else { j[u] = __ldg(sel_src + (int64_t)row * top_k + t); w[u] = __ldg(sel_w + (int64_t)row * top_k + t); }
+                }
+                v[u] = (j[u] >= 0 && ch_ok) ? ldg4(h + (int64_t)j[u] * ld + c4) : z4;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (st + u * EPW >= cnt) break;
+                const float inv_rj = inv_norm_of(group_sum<G>(dot4(v[u], v[u])));
+                const float s = SELECT_ALL ? group_sum<G>(dot4(ni, v[u])) * inv_rj : w[u];
+                const float ds = group_sum<G>(dot4(v[u], gs));                 // dL/ds_e = (h_j . g_i)/deg_i
+                if (j[u] >= 0 && ch_ok) {
+                    atomicAdd(reinterpret_cast<float4*>(dval + (int64_t)j[u] * ld + c4), scale4(gs, s));
+                    atomicAdd(reinterpret_cast<float4*>(dnrm + (int64_t)j[u] * ld + c4), scale4(ni, ds));
+                    fma4(dni, ds * inv_rj, v[u]);                              // ds * n_j
+                }
+            }
+        }
+        dni.x = cross_group_sum<G>(dni.x); dni.y = cross_group_sum<G>(dni.y);
+        dni.z = cross_group_sum<G>(dni.z); dni.w = cross_group_sum<G>(dni.w);
+        if (grp == 0 && ch_ok) atomicAdd(reinterpret_cast<float4*>(dnrm + (int64_t)row * ld + c4), dni);
+    }
+}
+
+// pass 2: dh = dval + (dnrm - n (n . dnrm)) / r      (one lane-group per row)
+template <int G>
+__global__ void __launch_bounds__(kThreads) norm_bwd_finish_kernel(const float* __restrict__ h, int n, int c, int64_t ld,
+                                                                  const float* __restrict__ dval, const float* __restrict__ dnrm,
+                                                                  float* __restrict__ dh) {
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G, c4 = q * 4;
+    const bool ch_ok = c4 < c;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = (blockIdx.x * kWarpsPerBlock + warp) * RPW; r0 < n; r0 += gridDim.x * kWarpsPerBlock * RPW) {
+        const int row = r0 + grp;
+        const bool ok = row < n && ch_ok;
+        const float4 hi = ok ? ldg4(h + (int64_t)row * ld + c4) : z4;
+        const float inv_r = inv_norm_of(group_sum<G>(dot4(hi, hi)));
+        const float4 ni = scale4(hi, inv_r);
+        const float4 dn = ok ? ldg4(dnrm + (int64_t)row * ld + c4) : z4;
+        const float proj = group_sum<G>(dot4(ni, dn));
+        if (ok) {
+            const float4 dv = ldg4(dval + (int64_t)row * ld + c4);
+            float4 o;
+            o.x = dv.x + (dn.x - ni.x * proj) * inv_r; o.y = dv.y + (dn.y - ni.y * proj) * inv_r;
+            o.z = dv.z + (dn.z - ni.z * proj) * inv_r; o.w = dv.w + (dn.w - ni.w * proj) * inv_r;
+            *reinterpret_cast<float4*>(dh + (int64_t)row * ld + c4) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K3 / K4
+template <int G>
+__device__ __forceinline__ float4 gather_sum(const float* __restrict__ x, int64_t ldx, const int* __restrict__ col,
+                                             const float* __restrict__ val, int beg, int end, int c4, bool ch_ok, int grp, int lane) {
+    constexpr int EPW = 32 / G;
+    constexpr int U = Unroll<G>::value;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = z4;
+    for (int base = beg; base < end; base += 32) {
+        const int nchunk = min(32, end - base);
+        const int jl = lane < nchunk ? __ldg(col + base + lane) : -1;
+        const float wl = (val && lane < nchunk) ? __ldg(val + base + lane) : 1.f;
+        for (int st = 0; st < nchunk; st += EPW * U) {
+            float4 v[U]; float w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = st + u * EPW + grp;
+                int j = __shfl_sync(0xffffffffu, jl, e & 31);
+                w[u] = __shfl_sync(0xffffffffu, wl, e & 31);
+                if (e >= nchunk) j = -1;
+                v[u] = (j >= 0 && ch_ok) ? ldg4(x + (int64_t)j * ldx + c4) : z4;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) fma4(acc, w[u], v[u]);
+        }
+    }
+    acc.x = cross_group_sum<G>(acc.x); acc.y = cross_group_sum<G>(acc.y);
+    acc.z = cross_group_sum<G>(acc.z); acc.w = cross_group_sum<G>(acc.w);
+    return acc;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) spmm_fwd_kernel(const float* __restrict__ x, int n_rows, int c, int64_t ldx,
+                                                           const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                           const float* __restrict__ val, const float* __restrict__ rowscale,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int64_t ldo) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G, c4 = q * 4;
+    const bool ch_ok = c4 < c;
+    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < n_rows; row += gridDim.x * kWarpsPerBlock) {
+        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        float4 acc = gather_sum<G>(x, ldx, col, val, beg, end, c4, ch_ok, grp, lane);
+        if (grp == 0 && ch_ok) {
+            if (rowscale) acc = scale4(acc, __ldg(rowscale + row));
+            if (bias) { const float4 b = ldg4(bias + c4); acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w; }
+            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + c4) = acc;
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) pp_fuse_fwd_kernel(const float* __restrict__ wt, int n, int c, int64_t ld,
+                                                              const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                              const float* __restrict__ b_w, const float* __restrict__ beta_p,
+                                                              const float* __restrict__ out1, const float* __restrict__ bias,
+                                                              float* __restrict__ out0, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G, c4 = q * 4;
+    const bool ch_ok = c4 < c;
+    const float beta = __ldg(beta_p);
+    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < n; row += gridDim.x * kWarpsPerBlock) {
+        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        float4 a = gather_sum<G>(wt, ld, col, nullptr, beg, end, c4, ch_ok, grp, lane);
+        if (grp == 0 && ch_ok) {
+            const float4 b = ldg4(b_w + c4);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            const int64_t o = (int64_t)row * ld + c4;
+            *reinterpret_cast<float4*>(out0 + o) = a;
+            const float4 o1 = ldg4(out1 + o);
+            float4 r;
+            r.x = beta * a.x + (1.f - beta) * o1.x; r.y = beta * a.y + (1.f - beta) * o1.y;
+            r.z = beta * a.z + (1.f - beta) * o1.z; r.w = beta * a.w + (1.f - beta) * o1.w;
+            if (bias) { const float4 bb = ldg4(bias + c4); r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w; }
+            *reinterpret_cast<float4*>(out + o) = r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) pp_beta_grad_kernel(const float* __restrict__ out0, const float* __restrict__ out1,
+                                                          const float* __restrict__ g, int64_t numel, float* __restrict__ dbeta) {
+    float acc = 0.f;
+    const int64_t n4 = numel / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = ldg4(out0 + 4 * i), b = ldg4(out1 + 4 * i), gg = ldg4(g + 4 * i);
+        acc = fmaf(a.x - b.x, gg.x, fmaf(a.y - b.y, gg.y, fmaf(a.z - b.z, gg.z, fmaf(a.w - b.w, gg.w, acc))));
+    }
+    acc = group_sum<32>(acc);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+        v = group_sum<32>(v);
+        if (threadIdx.x == 0) atomicAdd(dbeta, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ SDDMM
+__global__ void __launch_bounds__(kThreads) sddmm_dot_kernel(const float* __restrict__ xh, int d, int64_t ld,
+                                                            const int* __restrict__ a, const int* __restrict__ b,
+                                                            int64_t ne, float* __restrict__ s) {
+    const int lane = threadIdx.x & 31;
+    int64_t e = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const bool vec = (ld % 4 == 0) && (d % 4 == 0);
+    for (; e < ne; e += (int64_t)gridDim.x * kWarpsPerBlock) {
+        const float* pa = xh + (int64_t)__ldg(a + e) * ld;
+        const float* pb = xh + (int64_t)__ldg(b + e) * ld;
+        float acc = 0.f;
+        if (vec) for (int k = lane * 4; k < d; k += 128) acc += dot4(ldg4(pa + k), ldg4(pb + k));
+        else for (int k = lane; k < d; k += 32) acc = fmaf(__ldg(pa + k), __ldg(pb + k), acc);
+        acc = group_sum<32>(acc);
+        if (lane == 0) s[e] = acc;
+    }
+}
+
+static int grid_for_rows(int64_t rows, int rows_per_block) {
+    int64_t need = (rows + rows_per_block - 1) / rows_per_block;
+    int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 1) * 8;   // 8 resident 256-thread CTAs per SM, grid-stride
+    int64_t g = need < cap ? need : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+#define SNG_DISPATCH_G(cexpr, ...)                                              \
+    switch (group_lanes(cexpr)) {                                               \
+        case 1: { constexpr int G = 1; __VA_ARGS__; } break;                    \
+        case 2: { constexpr int G = 2; __VA_ARGS__; } break;                    \
+        case 4: { constexpr int G = 4; __VA_ARGS__; } break;                    \
+        case 8: { constexpr int G = 8; __VA_ARGS__; } break;                    \
+        case 16: { constexpr int G = 16; __VA_ARGS__; } break;                  \
+        default: { constexpr int G = 32; __VA_ARGS__; } break;                  \
+    }
+
+static int check_rows(const char* fn, int64_t n, int64_t c, int64_t ld) {
+    if (n < 0 || n >= (1ll << 31)) { set_error("%s: n=%lld out of range", fn, (long long)n); return SNG_ERR_ARG; }
+    if (c <= 0 || c % 4 != 0 || ld % 4 != 0 || ld < c) { set_error("%s: c=%lld ld=%lld must be multiples of 4, ld>=c", fn, (long long)c, (long long)ld); return SNG_ERR_ARG; }
+    if (c > 128) { set_error("%s: c=%lld > 128 channels not supported by the edge kernels", fn, (long long)c); return SNG_ERR_UNSUPPORTED; }
+    return SNG_OK;
+}
+
+}  // namespace sng
+
+using namespace sng;
+
+extern "C" int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx, float* xhat_f32, int64_t ld_f32,
+                               uint16_t* xhat_f16, int64_t ld_f16, float* inv_norm, void* stream) {
+    SNG_REQUIRE(x && n >= 0 && d > 0 && ldx >= d && d < (1ll << 30), "sng_rownorm_f32: bad x/n/d/ldx");
+    SNG_REQUIRE(!xhat_f32 || (ld_f32 >= d && ld_f32 < (1ll << 30)), "sng_rownorm_f32: ld_f32 < d");
+    SNG_REQUIRE(!xhat_f16 || (ld_f16 >= d && ld_f16 < (1ll << 30)), "sng_rownorm_f32: ld_f16 < d");
+    if (n == 0) return SNG_OK;
+    rownorm_kernel<<<grid_for_rows(n, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
+        x, n, (int)d, ldx, xhat_f32, (int)ld_f32, reinterpret_cast<__half*>(xhat_f16), (int)ld_f16, inv_norm);
+    return check_launch("sng_rownorm_f32");
+}
+
+extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t c, int64_t ldh, const int32_t* rowptr, const int32_t* col,
+                                     int top_k, float thr, float* out, int64_t ldo, int32_t* sel_src, float* sel_w,
+                                     int32_t* sel_cnt, void* stream) {
+    if (int rc = check_rows("sng_edge_topk_agg_fwd", n, c, ldh)) return rc;
+    SNG_REQUIRE(h && rowptr && col && out && ldo % 4 == 0 && ldo >= c, "sng_edge_topk_agg_fwd: null pointer or bad ldo");
+    SNG_REQUIRE(top_k <= SNG_MAX_TOPK, "sng_edge_topk_agg_fwd: top_k=%d > %d", top_k, SNG_MAX_TOPK);
+    SNG_REQUIRE(top_k <= 0 || (sel_src && sel_w && sel_cnt), "sng_edge_topk_agg_fwd: selection outputs required when top_k>0");
+    SNG_REQUIRE(top_k <= 0 || thr > -1.1f, "sng_edge_topk_agg_fwd: thr must be > -1.1 (knock-out sentinel of R models.py:153)");
+    if (n == 0) return SNG_OK;
+    const int grid = grid_for_rows(n, kWarpsPerBlock);
+    const size_t smem = (size_t)kWarpsPerBlock * 2 * (top_k > 0 ? top_k : 1) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    SNG_DISPATCH_G(c,
+        if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, (int)n, (int)c, ldh, rowptr, col, top_k, thr, out, ldo, sel_src, sel_w, sel_cnt);
+        else edge_topk_agg_fwd_kernel<G, true><<<grid, kThreads, smem, st>>>(h, (int)n, (int)c, ldh, rowptr, col, 0, thr, out, ldo, nullptr, nullptr, nullptr));
+    return check_launch("sng_edge_topk_agg_fwd");
+}
+
+extern "C" int sng_list_agg_fwd(const float* h, int64_t n_rows, int64_t c, int64_t ldh, int list_k, const int32_t* sel_src,
+                                const float* sel_w, const int32_t* sel_cnt, const float* inv_denom, float* out, int64_t ldo,
+                                void* stream) {
+    if (int rc = check_rows("sng_list_agg_fwd", n_rows, c, ldh)) return rc;
+    SNG_REQUIRE(h && sel_src && sel_w && sel_cnt && out && list_k > 0 && ldo % 4 == 0 && ldo >= c, "sng_list_agg_fwd: bad arguments");
+    if (n_rows == 0) return SNG_OK;
+    const int grid = grid_for_rows(n_rows, kWarpsPerBlock);
+    SNG_DISPATCH_G(c, list_agg_fwd_kernel<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(h, (int)n_rows, (int)c, ldh, list_k, sel_src, sel_w, sel_cnt, inv_denom, out, ldo));
+    return check_launch("sng_list_agg_fwd");
+}
+
+extern "C" int sng_edge_agg_bwd(const float* h, const float* g, int64_t n, int64_t c, int64_t ld, const int32_t* rowptr,
+                                const int32_t* col, int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_cnt,
+                                const float* inv_denom, float* dval, float* dnrm, float* dh, void* stream) {
+    if (int rc = check_rows("sng_edge_agg_bwd", n, c, ld)) return rc;
+    SNG_REQUIRE(h && g && dval && dnrm && dh, "sng_edge_agg_bwd: null pointer");
+    SNG_REQUIRE(top_k > 0 ? (sel_src && sel_w && sel_cnt && inv_denom) : (rowptr && col), "sng_edge_agg_bwd: missing selection list / CSR");
+    if (n == 0) return SNG_OK;
+    const int grid = grid_for_rows(n, kWarpsPerBlock);
+    cudaStream_t st = (cudaStream_t)stream;
+    SNG_DISPATCH_G(c,
+        if (top_k > 0) edge_agg_bwd_scatter_kernel<G, false><<<grid, kThreads, 0, st>>>(h, g, (int)n, (int)c, ld, rowptr, col, top_k, sel_src, sel_w, sel_cnt, inv_denom, dval, dnrm);
+        else edge_agg_bwd_scatter_kernel<G, true><<<grid, kThreads, 0, st>>>(h, g, (int)n, (int)c, ld, rowptr, col, 0, nullptr, nullptr, nullptr, nullptr, dval, dnrm);
+        norm_bwd_finish_kernel<G><<<grid_for_rows(n, kWarpsPerBlock * (32 / G)), kThreads, 0, st>>>(h, (int)n, (int)c, ld, dval, dnrm, dh));
+    return check_launch("sng_edge_agg_bwd");
+}
+
+extern "C" int sng_spmm_fwd(const float* x, int64_t n_rows, int64_t c, int64_t ldx, const int32_t* rowptr, const int32_t* col,
+                            const float* val, const float* rowscale, const float* bias, float* out, int64_t ldo, void* stream) {
+    if (int rc = check_rows("sng_spmm_fwd", n_rows, c, ldx)) return rc;
+    SNG_REQUIRE(x && rowptr && col && out && ldo % 4 == 0 && ldo >= c, "sng_spmm_fwd: null pointer or bad ldo");
+    if (n_rows == 0) return SNG_OK;
+    const int grid = grid_for_rows(n_rows, kWarpsPerBlock);
+    SNG_DISPATCH_G(c, spmm_fwd_kernel<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, (int)n_rows, (int)c, ldx, rowptr, col, val, rowscale, bias, out, ldo));
+    return check_launch("sng_spmm_fwd");
+}
+
+extern "C" int sng_pp_fuse_fwd(const float* wt, int64_t n, int64_t c, int64_t ld, const int32_t* rowptr_out, const int32_t* col_out,
+                               const float* b_w, const float* beta, const float* out1, const float* bias, float* out0, float* out,
+                               void* stream) {
+    if (int rc = check_rows("sng_pp_fuse_fwd", n, c, ld)) return rc;
+    SNG_REQUIRE(wt && rowptr_out && col_out && b_w && beta && out1 && out0 && out, "sng_pp_fuse_fwd: null pointer");
+    if (n == 0) return SNG_OK;
+    const int grid = grid_for_rows(n, kWarpsPerBlock);
+    SNG_DISPATCH_G(c, pp_fuse_fwd_kernel<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(wt, (int)n, (int)c, ld, rowptr_out, col_out, b_w, beta, out1, bias, out0, out));
+    return check_launch("sng_pp_fuse_fwd");
+}
+
+extern "C" int sng_pp_beta_grad(const float* out0, const float* out1, const float* g, int64_t numel, float* dbeta, void* stream) {
+    SNG_REQUIRE(out0 && out1 && g && dbeta && numel >= 0 && numel % 4 == 0, "sng_pp_beta_grad: bad arguments (numel must be a multiple of 4)");
+    if (numel == 0) return SNG_OK;
+    const int grid = grid_for_rows(numel / 4, 256);
+    pp_beta_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out0, out1, g, numel, dbeta);
+    return check_launch("sng_pp_beta_grad");
+}
+
+extern "C" int sng_sddmm_dot(const float* xhat, int64_t n, int64_t d, int64_t ld, const int32_t* a, const int32_t* b,
+                             int64_t num_edges, float* s, void* stream) {
+    SNG_REQUIRE(xhat && a && b && s && n >= 0 && d > 0 && ld >= d && num_edges >= 0, "sng_sddmm_dot: bad arguments");
+    if (num_edges == 0) return SNG_OK;
+    sddmm_dot_kernel<<<grid_for_rows(num_edges, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(xhat, (int)d, ld, a, b, num_edges, s);
+    return check_launch("sng_sddmm_dot");
+}

@@ -1,0 +1,587 @@
+// K1: all-pairs similarity-kNN builder for sm_100a -- tcgen05.mma + TMEM accumulators + TMA operand
+// staging, with the threshold / top-k selection fused into the epilogue so the N x N similarity matrix
+// never exists in HBM.
+//
+// Replaces (as "the reference selection rule on the complete graph") the k-round
+// scatter_max selection of R: models/models.py:145-156 and the blocked X X^T of
+// R: SimGFAToolbox/dense.py:17-27.
+//
+// Pipeline (one CTA = MB x 128 query rows against a range of 128-column tiles of the database):
+//   warp 0      TMA producer: A (query block, all of K) once; B column tiles through an S-stage ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=128, K=16, FP16 in, FP32 acc in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4..   epilogue: thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time, 3-input max
+//               tree against the row's running threshold (the current worst kept candidate); hits go to a
+//               per-row candidate list in shared memory.  TMEM is double buffered so the epilogue of tile
+//               t overlaps the MMAs of tile t+1.
+// Stage 2 rescoring in FP32 + proof of exactness, stage 3 exact fallback: see the bottom of this file.
+//
+// Operands are FP16 (not BF16): unit-norm rows live in [-1,1] where FP16 has 3 more mantissa bits, so the
+// worst-case score error is 2^-10 instead of 2^-8 and the candidate margin needed for exact indices is 4x
+// smaller; kind::f16 runs FP16 and BF16 at the same rate.
+#include "sng_common.cuh"
+#include <cuda.h>        // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+namespace sng {
+namespace knn {
+
+constexpr int BM = 128;                 // rows per MMA = TMEM lanes
+constexpr int BN = 128;                 // database columns per tile
+constexpr int BK = 64;                  // K elements per smem tile row = 128 bytes = one swizzle span
+constexpr int kTileBytes = BM * BK * 2; // 16 KiB
+constexpr int kUmmaK = 16;
+constexpr int kNonEpiThreads = 128;
+constexpr int kMaxStages = 8;
+constexpr int kFallbackBlocks = 32;
+constexpr int kMaxCandTotal = 512;      // nsplit * cand <= this (stage-2 shared memory)
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap (error returned to the caller) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done, polls = 0;
+    unsigned long long t0 = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (++polls > 4096u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();     // 4 s
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
+// rows are 128 B apart, 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: A,B = FP16 (0), D = FP32 (1 at bit 4), both K-major, N at [17,23) as N/8, M at [24,29) as M/16
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct Stage1Params {
+    int nq, n, q_offset;          // query rows in this call, database rows, global id of query row 0
+    int kblocks, ksteps_last;     // K tiling: kblocks tiles of 64, the last one has ksteps_last MMA steps of 16
+    int stages;                   // B ring depth
+    int cand;                     // candidate slots per row (L)
+    int nsplit, tiles_total;      // column tiles are split across gridDim.y CTAs
+    float thr_lo;                 // approximate scores <= thr_lo can never be selected
+    int remove_self;
+    float* cand_val;              // [nq, nsplit, cand]
+    int* cand_idx;                // [nq, nsplit, cand]   (-1 = empty)
+    float* cand_min;              // [nq, nsplit]  worst kept approx score if the list filled up, else -inf
+};
+
+template <int MB>
+__global__ void __launch_bounds__(kNonEpiThreads + 128 * MB, 1)
+simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const Stage1Params p) {
+    constexpr int ROWS = BM * MB;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_off = 0;
+    const uint32_t b_off = a_off + (uint32_t)MB * p.kblocks * kTileBytes;
+    const uint32_t list_off = b_off + (uint32_t)p.stages * kTileBytes;
+    const uint32_t bar_off = list_off + (uint32_t)ROWS * p.cand * 8u;
+    float* list_val = reinterpret_cast<float*>(smem + list_off);
+    int* list_idx = reinterpret_cast<int*>(smem + list_off + (size_t)ROWS * p.cand * 4);
+    const uint32_t bar_full = base + bar_off;                       // [kMaxStages]
+    const uint32_t bar_empty = bar_full + 8 * kMaxStages;           // [kMaxStages]
+    const uint32_t bar_a = bar_empty + 8 * kMaxStages;              // [1]
+    const uint32_t bar_tfull = bar_a + 8;                           // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 8 * (2 * kMaxStages + 5));
+
+    const int row0 = blockIdx.x * ROWS;
+    const int t_beg = (int)(((long long)p.tiles_total * blockIdx.y) / p.nsplit);
+    const int t_end = (int)(((long long)p.tiles_total * (blockIdx.y + 1)) / p.nsplit);
+    constexpr uint32_t kTmemCols = 2 * MB * BN;                     // 256 or 512 (power of two)
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * MB); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(bar_a, (uint32_t)MB * p.kblocks * kTileBytes);
+            for (int mb = 0; mb < MB; ++mb)
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_2d(base + a_off + (uint32_t)(mb * p.kblocks + kb) * kTileBytes, &map_q, bar_a, kb * BK, row0 + mb * BM);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t_beg; t < t_end; ++t) {
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, kTileBytes);
+                    tma_load_2d(base + b_off + (uint32_t)stage * kTileBytes, &map_db, bar_full + 8 * stage, kb * BK, t * BN);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            tc_fence_after();
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = t_beg; t < t_end; ++t) {
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const int ksteps = (kb == p.kblocks - 1) ? p.ksteps_last : (BK / kUmmaK);
+                    const uint64_t bdesc = make_smem_desc(base + b_off + (uint32_t)stage * kTileBytes);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb) {
+                            const uint64_t adesc = make_smem_desc(base + a_off + (uint32_t)(mb * p.kblocks + kb) * kTileBytes);
+                            // +32 bytes per K step inside the swizzle span = +2 in the (addr >> 4) field
+                            umma_f16(tmem_base + (uint32_t)((acc * MB + mb) * BN), adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2),
+                                     kIdesc, (kb | ks) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * stage);            // frees this B stage when the MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);                   // accumulator of tile t complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue: one thread = one query row
+        const int ew = warp - 4, mb = ew >> 2, quarter = warp & 3;
+        const int r = mb * BM + quarter * 32 + lane;              // row within the CTA == TMEM lane (+128*mb)
+        const int grow = row0 + r;
+        const int self_col = p.remove_self ? (p.q_offset + grow) : -1;
+        const int L = p.cand, n = p.n;
+        float* lv = list_val + r;
+        int* li = list_idx + r;
+        int cnt = 0, minpos = 0;
+        float thr_cur = p.thr_lo;
+
+        auto insert = [&](float x, int col) {
+            if (col >= n || col == self_col) return;
+            int slot = minpos;
+            if (cnt < L) slot = cnt++;
+            lv[slot * ROWS] = x;
+            li[slot * ROWS] = col;
+            if (cnt == L) {
+                float mn = lv[0]; int mp = 0;
+                for (int s = 1; s < L; ++s) { const float y = lv[s * ROWS]; if (y < mn) { mn = y; mp = s; } }
+                thr_cur = mn; minpos = mp;
+            }
+        };
+        auto process = [&](const uint32_t (&v)[32], int col0) {
+            float m[11];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) m[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+            m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+            const float m0 = max3(m[0], m[1], m[2]), m1 = max3(m[3], m[4], m[5]), m2 = max3(m[6], m[7], m[8]);
+            const float mx = max3(max3(m0, m1, m2), m[9], m[10]);
+            if (mx > thr_cur) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = __uint_as_float(v[i]);
+                    if (x > thr_cur) insert(x, col0 + i);
+                }
+            }
+        };
+
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t va[32], vb[32];
+        for (int t = t_beg; t < t_end; ++t) {
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * MB + mb) * BN);
+            const int col0 = t * BN;
+            tmem_ld32(taddr, va);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 32, vb);
+            process(va, col0);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 64, va);
+            process(vb, col0 + 32);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 96, vb);
+            process(va, col0 + 64);
+            tmem_ld_wait();
+            // all four loads of this accumulator stage have landed: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            process(vb, col0 + 96);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (grow < p.nq) {
+            const size_t o = ((size_t)grow * p.nsplit + blockIdx.y) * L;
+            for (int s = 0; s < L; ++s) {
+                p.cand_val[o + s] = s < cnt ? lv[s * ROWS] : -CUDART_INF_F;
+                p.cand_idx[o + s] = s < cnt ? li[s * ROWS] : -1;
+            }
+            p.cand_min[(size_t)grow * p.nsplit + blockIdx.y] = (cnt == L) ? thr_cur : -CUDART_INF_F;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ exact FP32 score
+// ONE definition of the "exact" cosine used by stage 2 and stage 3: sequential fmaf over c = 0..d-1 of the
+// FP32 unit rows (d padded to a multiple of 4 with zeros, which leaves the value unchanged).
+__device__ __forceinline__ float dot_seq(const float* __restrict__ a, const float* __restrict__ b, int d4) {
+    float s = 0.f;
+    for (int k = 0; k < d4; ++k) {
+        const float4 x = ldg4(a + 4 * k), y = ldg4(b + 4 * k);
+        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+    return s;
+}
+__device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
+
+// Stage 2: one warp per query row.  Rescore the nsplit*cand candidates exactly, order them by (score desc,
+// index asc), apply thr / top_k, and prove that no dropped column could belong to the answer.
+__global__ void __launch_bounds__(256) simknn_rescore_kernel(
+    const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int nq, int m_total, int nsplit, int top_k, float thr,
+    float eps, const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const float* __restrict__ cand_min,
+    int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out, int* __restrict__ fb_rows, int* __restrict__ n_fallback) {
+    extern __shared__ float sm2[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sc = sm2 + (size_t)warp * 2 * m_total;
+    int* id = reinterpret_cast<int*>(sc + m_total);
+    for (int row = blockIdx.x * 8 + warp; row < nq; row += gridDim.x * 8) {
+        const float* a = xq + (int64_t)row * ld32;
+        int nvalid = 0;
+        for (int m0 = 0; m0 < m_total; m0 += 32) {
+            const int m = m0 + lane;
+            int j = -1; float s = -CUDART_INF_F;
+            if (m < m_total) {
+                j = __ldg(cand_idx + (size_t)row * m_total + m);
+                if (j >= 0) s = dot_seq(a, xall + (int64_t)j * ld32, d4);
+                sc[m] = s; id[m] = j;
+            }
+            nvalid += __popc(__ballot_sync(0xffffffffu, j >= 0 && s >= thr));
+        }
+        __syncwarp();
+        const int cnt = min(nvalid, top_k);
+        float kth = thr;                                            // cut value: k-th exact score, or thr if fewer than k qualify
+        for (int m0 = 0; m0 < m_total; m0 += 32) {
+            const int m = m0 + lane;
+            int rank = 0x7fffffff; float s = 0.f; int j = -1;
+            if (m < m_total) {
+                s = sc[m]; j = id[m];
+                if (j >= 0 && s >= thr) {
+                    rank = 0;
+                    for (int o = 0; o < m_total; ++o) rank += (id[o] >= 0 && better(sc[o], id[o], s, j)) ? 1 : 0;
+                }
+            }
+            if (rank < top_k) {
+                idx_out[(size_t)row * top_k + rank] = j;
+                sim_out[(size_t)row * top_k + rank] = s;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, rank == top_k - 1);
+            if (hit) kth = __shfl_sync(0xffffffffu, s, __ffs(hit) - 1);
+        }
+        for (int t = cnt + lane; t < top_k; t += 32) { idx_out[(size_t)row * top_k + t] = -1; sim_out[(size_t)row * top_k + t] = 0.f; }
+        float bound = -CUDART_INF_F;                                 // best exact score any DROPPED column may have
+        for (int s0 = lane; s0 < nsplit; s0 += 32) bound = fmaxf(bound, __ldg(cand_min + (size_t)row * nsplit + s0) + eps);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+        if (lane == 0) {
+            cnt_out[row] = cnt;
+            if (!(kth > bound)) fb_rows[atomicAdd(n_fallback, 1)] = row;
+        }
+        __syncwarp();
+    }
+}
+
+// Stage 3: exact scan for the rows stage 2 could not prove (many near-ties at the cut, e.g. duplicated or all-zero rows).
+__global__ void __launch_bounds__(256) simknn_fallback_kernel(
+    const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int n, int q_offset, int top_k, float thr,
+    int remove_self, const int* __restrict__ fb_rows, const int* __restrict__ n_fallback, float* __restrict__ scratch,
+    int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out) {
+    __shared__ float red_s[8];
+    __shared__ int red_i[8];
+    __shared__ float pick_s;
+    __shared__ int pick_i;
+    float* sc = scratch + (size_t)blockIdx.x * n;
+    const int nfb = *n_fallback;
+    for (int f = blockIdx.x; f < nfb; f += gridDim.x) {
+        const int row = fb_rows[f];
+        const float* a = xq + (int64_t)row * ld32;
+        const int self_col = remove_self ? q_offset + row : -1;
+        for (int j = threadIdx.x; j < n; j += blockDim.x)
+            sc[j] = (j == self_col) ? -CUDART_INF_F : dot_seq(a, xall + (int64_t)j * ld32, d4);
+        __syncthreads();
+        float prev_s = CUDART_INF_F; int prev_i = -1; int cnt = 0;
+        for (int t = 0; t < top_k; ++t) {
+            float bs = -CUDART_INF_F; int bi = 0x7fffffff;
+            for (int j = threadIdx.x; j < n; j += blockDim.x) {
+                const float s = sc[j];
+                const bool after = s < prev_s || (s == prev_s && j > prev_i);     // strictly after the previous pick
+                if (after && s >= thr && better(s, j, bs, bi)) { bs = s; bi = j; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+            }
+            if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = bs; red_i[threadIdx.x >> 5] = bi; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < 8; ++w) if (better(red_s[w], red_i[w], bs, bi)) { bs = red_s[w]; bi = red_i[w]; }
+                pick_s = bs; pick_i = bi;
+            }
+            __syncthreads();
+            prev_s = pick_s; prev_i = pick_i;
+            if (prev_i == 0x7fffffff) break;                      // nothing left above thr (uniform across the block)
+            if (threadIdx.x == 0) { idx_out[(size_t)row * top_k + t] = prev_i; sim_out[(size_t)row * top_k + t] = prev_s; }
+            ++cnt;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            for (int t = cnt; t < top_k; ++t) { idx_out[(size_t)row * top_k + t] = -1; sim_out[(size_t)row * top_k + t] = 0.f; }
+            cnt_out[row] = cnt;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// [rows, ld] FP16 row-major, box = 64 (K) x 128 (rows), 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t ld) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SNG_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%lld)", (int)r, (long long)rows, (long long)ld); return SNG_ERR_CUDA; }
+    return SNG_OK;
+}
+
+struct Plan {
+    int mb, stages, cand, nsplit, kblocks, ksteps_last, tiles;
+    size_t smem;
+};
+
+static size_t smem_bytes(int mb, int kblocks, int stages, int cand) {
+    return 1024 + (size_t)mb * kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)BM * mb * cand * 8 + 8 * (2 * kMaxStages + 5) + 16;
+}
+
+static int default_cand(int top_k) {
+    int c = top_k + 16;
+    if (c < 32) c = 32;
+    return (c + 7) / 8 * 8;
+}
+
+static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int cand, int force_mb) {
+    const size_t kMaxSmem = 227 * 1024;
+    const int d16 = (int)((d + 15) / 16 * 16);
+    pl->kblocks = (d16 + BK - 1) / BK;
+    pl->ksteps_last = (d16 - (pl->kblocks - 1) * BK) / kUmmaK;
+    pl->cand = cand;
+    pl->tiles = (int)((n + BN - 1) / BN);
+    pl->mb = 0;
+    for (int mb = 2; mb >= 1; --mb) {
+        if (force_mb && mb != force_mb) continue;
+        for (int st = kMaxStages; st >= 2; --st) {
+            if (st > pl->kblocks * 4 && st > 4) continue;            // deeper than useful
+            const size_t s = smem_bytes(mb, pl->kblocks, st, cand);
+            if (s <= kMaxSmem) { pl->mb = mb; pl->stages = st; pl->smem = s; break; }
+        }
+        if (pl->mb) break;
+    }
+    if (!pl->mb) { set_error("simknn: d=%lld with %d candidate slots does not fit in shared memory", (long long)d, cand); return SNG_ERR_UNSUPPORTED; }
+    // a CTA must own the SM (TMEM: 2*MB*128 columns; two co-resident MB=2 CTAs would deadlock on allocation)
+    if (pl->mb == 2 && pl->smem <= kMaxSmem / 2) pl->smem = kMaxSmem / 2 + 1024;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int64_t row_blocks = (nq + BM * pl->mb - 1) / (BM * pl->mb);
+    int ns = (int)((3ll * sms + row_blocks - 1) / row_blocks);
+    if (ns > 8) ns = 8;
+    if (ns > pl->tiles) ns = pl->tiles;
+    if (ns * cand > kMaxCandTotal) ns = kMaxCandTotal / cand;
+    if (ns < 1) ns = 1;
+    pl->nsplit = ns;
+    return SNG_OK;
+}
+
+static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n,
+                         float thr_lo, int remove_self, float* cand_val, int* cand_idx, float* cand_min, cudaStream_t st) {
+    CUtensorMap mq, mdb;
+    if (int rc = make_map(&mq, xq, nq, ldb)) return rc;
+    if (int rc = make_map(&mdb, xall, n, ldb)) return rc;
+    Stage1Params p;
+    p.nq = (int)nq; p.n = (int)n; p.q_offset = (int)q_offset;
+    p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = pl.cand;
+    p.nsplit = pl.nsplit; p.tiles_total = pl.tiles; p.thr_lo = thr_lo; p.remove_self = remove_self;
+    p.cand_val = cand_val; p.cand_idx = cand_idx; p.cand_min = cand_min;
+    dim3 grid((unsigned)((nq + BM * pl.mb - 1) / (BM * pl.mb)), (unsigned)pl.nsplit);
+    cudaError_t e;
+    if (pl.mb == 2) {
+        e = cudaFuncSetAttribute(simknn_stage1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e == cudaSuccess) simknn_stage1_kernel<2><<<grid, kNonEpiThreads + 256, pl.smem, st>>>(mq, mdb, p);
+    } else {
+        e = cudaFuncSetAttribute(simknn_stage1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e == cudaSuccess) simknn_stage1_kernel<1><<<grid, kNonEpiThreads + 128, pl.smem, st>>>(mq, mdb, p);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("simknn stage 1: cudaFuncSetAttribute(%zu B smem): %s", pl.smem, cudaGetErrorString(e)); return SNG_ERR_CUDA; }
+    return check_launch("simknn stage 1");
+}
+
+static int check_common(const char* fn, const void* xq, const void* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n, int64_t d) {
+    if (!xq || !xall) { set_error("%s: null operand", fn); return SNG_ERR_ARG; }
+    if (nq <= 0 || n <= 0 || d <= 0 || q_offset < 0 || n >= (1ll << 31) || nq >= (1ll << 31)) { set_error("%s: bad nq/n/d/q_offset", fn); return SNG_ERR_ARG; }
+    if (ldb % 8 != 0 || ldb < (d + 15) / 16 * 16) { set_error("%s: ldb=%lld must be a multiple of 8 and >= d rounded up to 16", fn, (long long)ldb); return SNG_ERR_ARG; }
+    if (((uintptr_t)xq | (uintptr_t)xall) & 15) { set_error("%s: FP16 operands must be 16-byte aligned", fn); return SNG_ERR_ARG; }
+    if (d > 1024) { set_error("%s: d=%lld > 1024 not supported", fn, (long long)d); return SNG_ERR_UNSUPPORTED; }
+    return SNG_OK;
+}
+
+// worst-case |fp16-tensor-core score - exact FP32 score| for unit rows: 2 * 2^-11 (operand rounding) + accumulation slack
+constexpr float kScoreEps = 0.0009765625f + 1.2e-4f;
+
+}  // namespace knn
+}  // namespace sng
+
+using namespace sng;
+using namespace sng::knn;
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, int top_k) {
+    if (nq <= 0 || n <= 0 || d <= 0 || top_k <= 0 || top_k > SNG_KNN_MAX_TOPK) return 0;
+    Plan pl;
+    if (make_plan(&pl, nq, n, d, default_cand(top_k), 0)) return 0;
+    const size_t slots = (size_t)nq * pl.nsplit * pl.cand;
+    return align256(slots * 4) * 2 + align256((size_t)nq * 8 * 4) + align256((size_t)nq * 4) + align256((size_t)kFallbackBlocks * n * 4) + 1024;
+}
+
+extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n, int64_t d,
+                                 int cand, float thr_lo, int remove_self, int32_t* cand_idx, float* cand_val, float* cand_min,
+                                 int force_mb, int force_nsplit, int* nsplit_out, void* stream) {
+    if (int rc = check_common("sng_simknn_stage1", xq, xall, ldb, nq, q_offset, n, d)) return rc;
+    SNG_REQUIRE(cand >= 8 && cand <= 128 && cand_idx && cand_val && cand_min, "sng_simknn_stage1: bad cand / outputs");
+    Plan pl;
+    if (int rc = make_plan(&pl, nq, n, d, cand, force_mb)) return rc;
+    if (force_nsplit > 0) pl.nsplit = force_nsplit < pl.tiles ? force_nsplit : pl.tiles;
+    if (nsplit_out) *nsplit_out = pl.nsplit;
+    return launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min, (cudaStream_t)stream);
+}
+
+extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_t ldb, const float* xq32, const float* xall32, int64_t ld32,
+                                int64_t nq, int64_t q_offset, int64_t n, int64_t d, int top_k, float thr, int remove_self,
+                                int32_t* idx, float* sim, int32_t* cnt, int32_t* n_fallback, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    if (int rc = check_common("sng_simknn_build", xq, xall, ldb, nq, q_offset, n, d)) return rc;
+    SNG_REQUIRE(xq32 && xall32 && ld32 % 4 == 0 && ld32 >= d, "sng_simknn_build: FP32 rows must be padded to a multiple of 4 floats (ld32=%lld)", (long long)ld32);
+    SNG_REQUIRE(top_k >= 1 && top_k <= SNG_KNN_MAX_TOPK, "sng_simknn_build: top_k=%d out of [1,%d]", top_k, SNG_KNN_MAX_TOPK);
+    SNG_REQUIRE(idx && sim && cnt && n_fallback && workspace, "sng_simknn_build: null output / workspace");
+    if (workspace_bytes < sng_simknn_workspace_bytes(nq, n, d, top_k)) { set_error("sng_simknn_build: workspace too small (%zu < %zu)", workspace_bytes, sng_simknn_workspace_bytes(nq, n, d, top_k)); return SNG_ERR_WORKSPACE; }
+    Plan pl;
+    if (int rc = make_plan(&pl, nq, n, d, default_cand(top_k), 0)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m_total = pl.nsplit * pl.cand;
+    uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float* cand_val = reinterpret_cast<float*>(w); w += align256((size_t)nq * m_total * 4);
+    int* cand_idx = reinterpret_cast<int*>(w); w += align256((size_t)nq * m_total * 4);
+    float* cand_min = reinterpret_cast<float*>(w); w += align256((size_t)nq * 8 * 4);
+    int* fb_rows = reinterpret_cast<int*>(w); w += align256((size_t)nq * 4);
+    float* scratch = reinterpret_cast<float*>(w);
+    if (cudaMemsetAsync(n_fallback, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
+    // approximate scores below thr - eps can never reach thr exactly
+    const float thr_lo = thr - 1.01f * kScoreEps;
+    if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min, st)) return rc;
+    const int d4 = (int)((d + 3) / 4);
+    {
+        const int blocks = (int)((nq + 7) / 8 < (int64_t)sm_count() * 8 ? (nq + 7) / 8 : (int64_t)sm_count() * 8);
+        simknn_rescore_kernel<<<blocks > 0 ? blocks : 1, 256, (size_t)8 * 2 * m_total * 4, st>>>(
+            xq32, xall32, ld32, d4, (int)nq, m_total, pl.nsplit, top_k, thr, kScoreEps, cand_val, cand_idx, cand_min, idx, sim, cnt, fb_rows, n_fallback);
+        if (int rc = check_launch("simknn stage 2")) return rc;
+    }
+    simknn_fallback_kernel<<<kFallbackBlocks, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb_rows,
+                                                           n_fallback, scratch, idx, sim, cnt);
+    return check_launch("simknn stage 3");
+}

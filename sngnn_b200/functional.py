@@ -1,0 +1,186 @@
+"""Autograd functions over the C-ABI kernels (include/sng.h).  torch is used for memory, streams and the
+dense `lin` GEMM only; every sparse / selection / aggregation step is a libsng.so call.
+
+Channel padding: the edge kernels want 16-byte feature rows, so the layer output width C is padded to
+Cp = 4*ceil(C/4) by zero-padding the `lin` weights (zero columns change neither norms nor dot products).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _C
+
+
+def padded_channels(c):
+    return (c + 3) // 4 * 4
+
+
+def linear_padded(x, weight, bias, cp):
+    """h = x @ W^T + b with the output width zero-padded to `cp` (R: models/models.py:121,237,324)."""
+    c = weight.size(0)
+    if cp != c:
+        weight = F.pad(weight, (0, 0, 0, cp - c))
+        bias = None if bias is None else F.pad(bias, (0, cp - c))
+    return F.linear(x, weight, bias)
+
+
+def _check_h(h):
+    _C.require_cuda(h)
+    if h.dtype != torch.float32 or h.dim() != 2 or h.size(1) % 4 != 0:
+        raise RuntimeError("expected a float32 [N, 4m] tensor")
+    return h.contiguous()
+
+
+class EdgeTopkAgg(torch.autograd.Function):
+    """out_1 of R: models/models.py:132 / :239 / :326 -- K2 forward, K2b backward."""
+
+    @staticmethod
+    def forward(ctx, h, graph, top_k, thr):
+        h = _check_h(h)
+        n, c = h.shape
+        if n != graph.n:
+            raise RuntimeError(f"h has {n} rows but the graph has {graph.n} nodes")
+        out = torch.empty_like(h)
+        k = int(top_k) if top_k is not None else 0
+        if k > 0:
+            sel_src = torch.empty(n, k, dtype=torch.int32, device=h.device)
+            sel_w = torch.empty(n, k, dtype=torch.float32, device=h.device)
+            sel_cnt = torch.empty(n, dtype=torch.int32, device=h.device)
+        else:
+            sel_src = sel_w = sel_cnt = None
+        _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h), n, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
+                                                float(thr if thr is not None else 0.0), _C.ptr(out), c,
+                                                _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.stream()),
+                 "sng_edge_topk_agg_fwd")
+        ctx.graph, ctx.k = graph, k
+        ctx.save_for_backward(h, sel_src, sel_w, sel_cnt)
+        ctx.mark_non_differentiable(*[t for t in (sel_src, sel_w, sel_cnt) if t is not None])
+        if k > 0:
+            return out, sel_src, sel_w, sel_cnt
+        return out, None, None, None
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        h, sel_src, sel_w, sel_cnt = ctx.saved_tensors
+        graph, k = ctx.graph, ctx.k
+        n, c = h.shape
+        g = g.contiguous()
+        dval = torch.zeros_like(h)
+        dnrm = torch.zeros_like(h)
+        dh = torch.empty_like(h)
+        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(g), n, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
+                                           _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(graph.inv_deg),
+                                           _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
+                 "sng_edge_agg_bwd")
+        return dh, None, None, None
+
+
+def edge_topk_agg(h, graph, top_k=None, thr=None, return_selection=False):
+    out, sel_src, sel_w, sel_cnt = EdgeTopkAgg.apply(h, graph, top_k, thr)
+    if return_selection:
+        return out, (sel_src, sel_w, sel_cnt)
+    return out
+
+
+class ListAgg(torch.autograd.Function):
+    """Mean aggregation over an explicit neighbour list (all-pairs mode): forward sng_list_agg_fwd, backward K2b."""
+
+    @staticmethod
+    def forward(ctx, h, idx, sim, cnt, inv_denom):
+        h = _check_h(h)
+        n, c = h.shape
+        out = torch.empty(idx.size(0), c, dtype=h.dtype, device=h.device)
+        _C.check(_C.lib().sng_list_agg_fwd(_C.ptr(h), idx.size(0), c, c, idx.size(1), _C.ptr(idx), _C.ptr(sim), _C.ptr(cnt),
+                                           _C.ptr(inv_denom), _C.ptr(out), c, _C.stream()), "sng_list_agg_fwd")
+        ctx.save_for_backward(h, idx, sim, cnt, inv_denom)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, idx, sim, cnt, inv_denom = ctx.saved_tensors
+        n, c = h.shape
+        if idx.size(0) != n:
+            raise RuntimeError("backward through a row-sharded list aggregation is not supported")
+        g = g.contiguous()
+        dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
+        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(g), n, c, c, None, None, idx.size(1), _C.ptr(idx), _C.ptr(sim),
+                                           _C.ptr(cnt), _C.ptr(inv_denom), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
+                 "sng_edge_agg_bwd")
+        return dh, None, None, None, None
+
+
+def spmm(x, rowptr, col, n_rows, val=None, rowscale=None, bias=None):
+    """K3: out[i] = rowscale[i] * sum_e val[e] x[col[e]] + bias (no autograd; used inside backward passes)."""
+    x = _check_h(x)
+    c = x.size(1)
+    out = torch.empty(n_rows, c, dtype=x.dtype, device=x.device)
+    _C.check(_C.lib().sng_spmm_fwd(_C.ptr(x), n_rows, c, c, _C.ptr(rowptr), _C.ptr(col), _C.ptr(val), _C.ptr(rowscale),
+                                   _C.ptr(bias), _C.ptr(out), c, _C.stream()), "sng_spmm_fwd")
+    return out
+
+
+class PPFuse(torch.autograd.Function):
+    """out = beta*(A @ W^T + b_w) + (1-beta)*out_1 (+bias)  --  R: models/models.py:124-136 (K4)."""
+
+    @staticmethod
+    def forward(ctx, out1, w_weight, w_bias, beta, bias, graph):
+        out1 = _check_h(out1)
+        n, cp = out1.shape
+        c = w_weight.size(0)
+        if w_weight.size(1) != n:
+            raise RuntimeError(f"w.weight is [{c},{w_weight.size(1)}] but the graph has {n} nodes "
+                               "(R builds w = Linear(num_nodes, out_channels), models.py:95)")
+        wt = F.pad(w_weight.detach(), (0, 0, 0, cp - c)).t().contiguous()        # [N, Cp]
+        bw = F.pad(w_bias.detach(), (0, cp - c)).contiguous()
+        bb = None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous()
+        out0 = torch.empty_like(out1)
+        out = torch.empty_like(out1)
+        _C.check(_C.lib().sng_pp_fuse_fwd(_C.ptr(wt), n, cp, cp, _C.ptr(graph.rowptr_out), _C.ptr(graph.col_out), _C.ptr(bw),
+                                          _C.ptr(beta), _C.ptr(out1), _C.ptr(bb), _C.ptr(out0), _C.ptr(out), _C.stream()),
+                 "sng_pp_fuse_fwd")
+        ctx.graph, ctx.c, ctx.has_bias = graph, c, bias is not None
+        ctx.save_for_backward(out0, out1, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out0, out1, beta = ctx.saved_tensors
+        graph, c = ctx.graph, ctx.c
+        n, cp = out1.shape
+        g = g.contiguous()
+        dbeta = torch.zeros(1, dtype=torch.float32, device=g.device)
+        _C.check(_C.lib().sng_pp_beta_grad(_C.ptr(out0), _C.ptr(out1), _C.ptr(g), g.numel(), _C.ptr(dbeta), _C.stream()),
+                 "sng_pp_beta_grad")
+        g0 = g * beta
+        dout1 = g - g0
+        # dL/dW^T = A^T g0: row t gathers g0 over the (shifted) sources of t's in-edges
+        dwt = spmm(g0, graph.rowptr_in, graph.col_in_shift, n)
+        dw = dwt[:, :c].t()
+        db_w = g0.sum(0)[:c]
+        dbias = g.sum(0)[:c] if ctx.has_bias else None
+        return dout1, dw, db_w, dbeta, dbias, None
+
+
+def rownorm(x, want_f32=True, want_f16=False, f16_ld=None, want_inv=False):
+    """K0: F.normalize(x, p=2, dim=-1) (R: models/models.py:122).  Returns (xhat_f32, xhat_f16, inv_norm)."""
+    _C.require_cuda(x)
+    x = x.contiguous().float()
+    n, d = x.shape
+    xf = torch.empty_like(x) if want_f32 else None
+    ldh = f16_ld or (d + 15) // 16 * 16
+    xh = torch.empty(n, ldh, dtype=torch.float16, device=x.device) if want_f16 else None
+    inv = torch.empty(n, dtype=torch.float32, device=x.device) if want_inv else None
+    _C.check(_C.lib().sng_rownorm_f32(_C.ptr(x), n, d, d, _C.ptr(xf), d, _C.ptr(xh), ldh, _C.ptr(inv), _C.stream()),
+             "sng_rownorm_f32")
+    return xf, xh, inv
+
+
+def sddmm_dot(xhat, a, b):
+    """s[e] = <xhat[a[e]], xhat[b[e]]> (R: SimGFAToolbox/dense.py:160-162)."""
+    _C.require_cuda(xhat, a, b)
+    xhat = xhat.contiguous()
+    a = a.to(torch.int32).contiguous()
+    b = b.to(torch.int32).contiguous()
+    s = torch.empty(a.numel(), dtype=torch.float32, device=xhat.device)
+    _C.check(_C.lib().sng_sddmm_dot(_C.ptr(xhat), xhat.size(0), xhat.size(1), xhat.size(1), _C.ptr(a), _C.ptr(b), a.numel(),
+                                    _C.ptr(s), _C.stream()), "sng_sddmm_dot")
+    return s

@@ -1,0 +1,103 @@
+"""All-pairs similarity-kNN builder (host side of K0 + K1, include/sng.h).
+
+`build_knn` = "the reference selection rule on the complete graph" (SURVEY.md §0): for query node i the
+candidates are all nodes j (minus i when remove_self), ranked by (cosine desc, j asc), at most top_k, cut at
+the first cosine < thr -- i.e. R: models/models.py:145-156 applied to every pair, with the all-pairs cosine of
+R: SimGFAToolbox/dense.py:17-27 computed on the tensor cores and never written to HBM.
+
+Row sharding: `q_lo:q_hi` selects the query rows this call (this rank) owns; the database is always all of x.
+"""
+import torch
+
+from . import _C
+from . import functional as SF
+
+
+def _pad_to(v, m):
+    return (v + m - 1) // m * m
+
+
+def normalize_operands(x):
+    """K0: returns (xhat_f32 [N, ld32], xhat_f16 [N, ldh]) zero padded to ld32 = 4*ceil(d/4), ldh = 16*ceil(d/16)."""
+    _C.require_cuda(x)
+    x = x.contiguous().float()
+    n, d = x.shape
+    ld32, ldh = _pad_to(d, 4), _pad_to(d, 16)
+    xf = torch.empty(n, ld32, dtype=torch.float32, device=x.device)
+    xh = torch.empty(n, ldh, dtype=torch.float16, device=x.device)
+    _C.check(_C.lib().sng_rownorm_f32(_C.ptr(x), n, d, d, _C.ptr(xf), ld32, _C.ptr(xh), ldh, None, _C.stream()), "sng_rownorm_f32")
+    return xf, xh
+
+
+def build_knn_normalized(xf, xh, d, top_k, thr, remove_self=True, q_lo=0, q_hi=None, return_fallback=False):
+    """K1 on already normalised operands (what a rank calls after the all-gather of x-hat)."""
+    n = xf.size(0)
+    q_hi = n if q_hi is None else q_hi
+    nq = q_hi - q_lo
+    if nq <= 0:
+        raise ValueError("empty query range")
+    dev = xf.device
+    idx = torch.empty(nq, top_k, dtype=torch.int32, device=dev)
+    sim = torch.empty(nq, top_k, dtype=torch.float32, device=dev)
+    cnt = torch.empty(nq, dtype=torch.int32, device=dev)
+    nfb = torch.zeros(1, dtype=torch.int32, device=dev)
+    wbytes = _C.lib().sng_simknn_workspace_bytes(nq, n, d, top_k)
+    if wbytes == 0:
+        raise RuntimeError(f"sng_simknn_workspace_bytes rejected nq={nq} n={n} d={d} top_k={top_k}: {_C.last_error()}")
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    _C.check(_C.lib().sng_simknn_build(_C.ptr(xh[q_lo:]), _C.ptr(xh), xh.size(1), _C.ptr(xf[q_lo:]), _C.ptr(xf), xf.size(1),
+                                       nq, q_lo, n, d, int(top_k), float(thr), int(bool(remove_self)),
+                                       _C.ptr(idx), _C.ptr(sim), _C.ptr(cnt), _C.ptr(nfb), _C.ptr(ws), wbytes, _C.stream()),
+             "sng_simknn_build")
+    if return_fallback:
+        return idx, sim, cnt, nfb
+    return idx, sim, cnt
+
+
+def build_knn(x, top_k, thr=-1.0, remove_self=True, q_lo=0, q_hi=None, return_fallback=False):
+    """idx [nq, top_k] int32 (-1 padded, rank order), sim [nq, top_k] float32, cnt [nq] int32."""
+    xf, xh = normalize_operands(x)
+    return build_knn_normalized(xf, xh, x.size(1), top_k, thr, remove_self, q_lo, q_hi, return_fallback)
+
+
+def knn_to_csr(idx, cnt):
+    """CSR neighbour lists (rowptr int32 [nq+1], col int32 [nnz]) + gather index into the flattened [nq*k] lists."""
+    nq, k = idx.shape
+    rowptr = torch.zeros(nq + 1, dtype=torch.int64, device=idx.device)
+    torch.cumsum(cnt.long(), 0, out=rowptr[1:])
+    keep = torch.arange(k, device=idx.device)[None, :] < cnt[:, None]
+    flat = keep.reshape(-1).nonzero().flatten()
+    return rowptr.to(torch.int32), idx.reshape(-1)[flat].contiguous(), flat
+
+
+def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_mb=0, force_nsplit=0):
+    """Tensor-core stage only (tests / profiling): FP16-scored candidate lists [N, nsplit, cand]."""
+    import ctypes
+    xf, xh = normalize_operands(x)
+    n, d = x.shape
+    dev = x.device
+    ci = torch.empty(n, 8, cand, dtype=torch.int32, device=dev)
+    cv = torch.empty(n, 8, cand, dtype=torch.float32, device=dev)
+    cm = torch.empty(n, 8, dtype=torch.float32, device=dev)
+    ns = ctypes.c_int(0)
+    _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh), _C.ptr(xh), xh.size(1), n, 0, n, d, cand, float(thr_lo), int(remove_self),
+                                        _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), force_mb, force_nsplit, ctypes.byref(ns), _C.stream()),
+             "sng_simknn_stage1")
+    s = ns.value
+    flat_i = ci.reshape(-1)[: n * s * cand].reshape(n, s, cand)
+    flat_v = cv.reshape(-1)[: n * s * cand].reshape(n, s, cand)
+    flat_m = cm.reshape(-1)[: n * s].reshape(n, s)
+    return flat_i, flat_v, flat_m, xf, xh
+
+
+def allpairs_topk_agg(h, top_k, thr, remove_self, denominator="candidates"):
+    """All-pairs candidate mode of SNConv_plus(_plus): kNN on the layer's own h (similarity is on lin(x),
+    SURVEY.md D4), then the cosine-weighted mean.  `h` is the padded [N, Cp] hidden matrix."""
+    n = h.size(0)
+    idx, sim, cnt = build_knn(h.detach(), top_k, thr, remove_self)
+    if denominator == "candidates":
+        cand = float(n - 1 if remove_self else n)
+        inv = torch.full((n,), 1.0 / max(cand, 1.0), dtype=torch.float32, device=h.device)
+    else:
+        inv = cnt.clamp(min=1).float().reciprocal()
+    return SF.ListAgg.apply(h, idx, sim, cnt, inv)

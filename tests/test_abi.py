@@ -1,0 +1,92 @@
+"""The C-ABI library loads without a GPU and exports exactly what include/sng.h declares; host-side logic
+(graph preparation, argument validation) runs on CPU.  No compute kernels are launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "sng.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sng_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sngnn_b200 import _C
+    lib = _C.lib()
+    names = _header_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sng.h but not exported by libsng.so"
+    assert sorted(_C.SIGNATURES) == names, "sngnn_b200/_C.py SIGNATURES out of sync with include/sng.h"
+    assert lib.sng_version() >= 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_no_gpu_is_a_loud_error_not_a_fallback():
+    from sngnn_b200 import _C, functional as SF, graph as G
+    a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = _C.lib().sng_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    assert rc == -3 and "device" in _C.last_error().lower()
+    g = G.prepare(torch.tensor([[0, 1], [1, 0]]), 2, True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        SF.edge_topk_agg(torch.randn(2, 4), g, 1, 0.0)
+
+
+def test_argument_validation_without_device():
+    from sngnn_b200 import _C
+    L = _C.lib()
+    assert L.sng_rownorm_f32(None, 4, 4, 4, None, 4, None, 4, None, None) == -1
+    assert "sng_rownorm_f32" in _C.last_error()
+    assert L.sng_simknn_workspace_bytes(0, 10, 4, 1) == 0
+    assert L.sng_simknn_workspace_bytes(1000, 1000, 65, 10) > 1000 * 32 * 8
+
+
+def test_graph_prepare_matches_reference_edge_processing():
+    from sngnn_b200 import graph as G, synth
+    from oracle import sn_ref
+    n = 50
+    ei = synth.make_graph(n, 300, seed=9, hub_offset=2.0)
+    ei = torch.cat([ei, torch.tensor([[3, 3], [3, 7]])], dim=1)        # an original self loop and a duplicate-able edge
+    for rsl in (True, False):
+        g = G.prepare(ei, n, rsl, structural=True)
+        pe = sn_ref.process_edges(ei, n, rsl)
+        assert torch.equal(G.process_edges(ei, n, rsl), pe)
+        # CSR by target keeps original positions
+        for i in range(n):
+            want = pe[0][pe[1] == i]
+            got = g.col_in[g.rowptr_in[i]:g.rowptr_in[i + 1]].long()
+            assert torch.equal(got, want)
+        deg = torch.bincount(pe[1], minlength=n).clamp(min=1).float()
+        assert torch.allclose(g.inv_deg, 1 / deg)
+        m = int(pe[0].min())
+        assert g.src_shift == m
+        for i in range(n):
+            want = sorted(pe[1][pe[0] - m == i].tolist())
+            got = sorted(g.col_out[g.rowptr_out[i]:g.rowptr_out[i + 1]].tolist())
+            assert got == want
+        assert G.prepare(ei, n, rsl, structural=True) is g                # cache hit
+    sl = g.row_slice(10, 30)
+    assert sl.n == 20 and int(sl.rowptr_in[0]) == 0 and sl.col_in.numel() == int(g.rowptr_in[30] - g.rowptr_in[10])
+
+
+def test_module_surface_matches_reference_signatures():
+    import inspect
+    import sngnn_b200.models as M
+    sig = lambda f: [p for p in inspect.signature(f).parameters if p != "self"]
+    assert sig(M.SNGNN.__init__) == ["in_channels", "hidden_channels", "out_channels", "num_layers", "bn"]
+    assert sig(M.SNGNN_Plus.__init__)[:10] == ["in_channels", "hidden_channels", "out_channels", "num_nodes", "num_layers", "top_k",
+                                               "thr", "is_remove_self_loops", "droput_rate", "bn"]
+    assert sig(M.SNGNN_Plus_Plus.__init__)[:11] == ["in_channels", "hidden_channels", "out_channels", "num_nodes", "num_layers",
+                                                    "top_k", "thr", "init_beta", "is_remove_self_loops", "droput_rate", "bn"]
+    assert sig(M.SNConv_plus_plus.__init__)[:9] == ["in_channels", "out_channels", "num_nodes", "top_k", "thr", "init_beta",
+                                                    "is_remove_self_loops", "bias", "aggr"]
+    m = M.SNGNN_Plus_Plus(8, 4, 3, 20, 2, init_beta=0.25)
+    assert float(m.lins[0].beta) == 0.25 and m.lins[0].w.weight.shape == (4, 20)
+    assert sorted(k for k in m.state_dict()) == sorted(
+        [f"lins.{l}.{n}" for l in (0, 1) for n in ("beta", "lin.weight", "lin.bias", "w.weight", "w.bias")])

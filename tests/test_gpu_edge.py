@@ -1,0 +1,155 @@
+"""GPU parity of the edge-restricted path (K0, K2, K2b, K3, K4) through the C-ABI, against the CPU oracle and
+the golden vectors of the reference.  Tolerances: indices exact (FP64-band rule), values 1e-5 relative."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, golden_inputs
+from parity import compare_lists
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _models():
+    import sngnn_b200.models as M
+    return M
+
+
+def _build(M, run, x, y):
+    cfg, kind = run["cfg"], run["kind"]
+    N, Fd = x.shape
+    C = int(y.max()) + 1
+    if kind == "SNGNN":
+        m = M.SNGNN(Fd, cfg["hidden"], C, cfg["layers"], bn=cfg.get("bn", False))
+        m.dropout = torch.nn.Dropout(0.0)
+    elif kind == "SNGNN_Plus":
+        m = M.SNGNN_Plus(Fd, cfg["hidden"], C, N, cfg["layers"], cfg["top_k"], cfg["thr"], cfg["rsl"], 0.0, bn=cfg.get("bn", False))
+    else:
+        m = M.SNGNN_Plus_Plus(Fd, cfg["hidden"], C, N, cfg["layers"], cfg["top_k"], cfg["thr"], cfg["beta"], cfg["rsl"], 0.0,
+                              bn=cfg.get("bn", False))
+    m.load_state_dict(run["state_dict"])
+    return m.to(DEV).train()
+
+
+@pytest.mark.parametrize("fname", ["models_tiny.pt", "models_small.pt", "models_chameleon.pt"])
+def test_models_match_reference_golden(fname):
+    from sngnn_b200.synth import GraphData
+    M = _models()
+    g = load_golden(fname)
+    x, ei, y = golden_inputs(g)
+    data = GraphData(x, ei).to(DEV)
+    yd = y.to(DEV)
+    mask = (torch.arange(x.size(0)) % 2 == 0).to(DEV)
+    worst = 0.0
+    for run in g["runs"]:
+        m = _build(M, run, x, y)
+        out = m(data)
+        loss = F.nll_loss(out[mask], yd[mask])
+        loss.backward()
+        tag = f"{fname} {run['kind']} {run['cfg']}"
+        torch.testing.assert_close(out.detach().cpu(), run["logp"], rtol=1e-5, atol=2e-6, msg=lambda s: f"{tag}: {s}")
+        torch.testing.assert_close(loss.detach().cpu(), run["loss"], rtol=1e-5, atol=1e-6, msg=lambda s: f"{tag} loss: {s}")
+        for k, p in m.named_parameters():
+            ref = run["grads"][k]
+            scale = ref.abs().max().item() + 1e-12
+            err = (p.grad.detach().cpu() - ref).abs().max().item() / scale
+            worst = max(worst, err)
+            assert err < 1e-4, f"{tag} grad {k}: rel-to-max err {err:.3e}"
+    print(f"{fname}: worst grad error relative to max {worst:.2e}")
+
+
+@pytest.mark.parametrize("n,e,c,k,thr,rsl", [(5000, 60000, 32, 10, 0.0, True), (5000, 60000, 5, 3, 0.3, False),
+                                              (20000, 400000, 64, 10, -0.5, True), (3000, 30000, 2, 64, -1.0, True),
+                                              (4000, 50000, 128, 7, 0.2, True)])
+def test_edge_selection_and_aggregate_vs_oracle(n, e, c, k, thr, rsl):
+    """sel lists exact vs the oracle's rank rule; out_1 within 1e-5; dh via K2b vs autograd of the oracle."""
+    from oracle import sn_ref
+    from sngnn_b200 import synth, graph as G, functional as SF
+    torch.manual_seed(n + c)
+    ei = synth.make_graph(n, e, seed=n, symmetric=True, hub_offset=3.0)
+    h = torch.randn(n, c)
+    h[7] = h[3]; h[11] = 0                                   # duplicate + zero row
+    cp = SF.padded_channels(c)
+    hp = F.pad(h, (0, cp - c)).to(DEV).requires_grad_(True)
+    g = G.prepare(ei.to(DEV), n, rsl)
+    out, (sel_src, sel_w, sel_cnt) = SF.edge_topk_agg(hp, g, k, thr, return_selection=True)
+    w = torch.randn(n, cp, device=DEV)
+    (out * w).sum().backward()
+
+    # oracle (FP32 for values, FP64 for the index band rule)
+    h64 = h.double().requires_grad_(True)
+    pe = sn_ref.process_edges(ei, n, rsl)
+    out_ref = sn_ref.sn_aggregate(h64, pe, k, thr)
+    (out_ref * w[:, :c].cpu().double()).sum().backward()
+    torch.testing.assert_close(out[:, :c].detach().cpu().double(), out_ref.detach(), rtol=1e-5, atol=1e-6)
+    scale = h64.grad.abs().max()
+    assert ((hp.grad[:, :c].cpu().double() - h64.grad).abs().max() / scale) < 2e-5
+    assert hp.grad[:, c:].abs().max().item() == 0 if cp > c else True
+
+    # selection lists
+    n64 = F.normalize(h.double(), dim=-1, eps=1e-12)
+    s64 = (n64[pe[1]] * n64[pe[0]]).sum(-1)
+    rank = sn_ref.edge_rank(s64, pe[1])
+    selm = (rank < k) & (s64 >= thr)
+    idx_ref = torch.full((n, k), -1, dtype=torch.long)
+    idx_ref[pe[1][selm], rank[selm]] = pe[0][selm]
+    cnt_ref = torch.zeros(n, dtype=torch.long).index_add(0, pe[1][selm], torch.ones(int(selm.sum()), dtype=torch.long))
+    res = compare_lists(sel_src, sel_cnt, idx_ref, cnt_ref, lambda r, j: (n64[r] * n64[j]).sum(-1), thr)
+    print(res)
+    assert res["out_of_band"] == 0, res
+    assert res["exact"] >= 0.999 * n
+
+
+def test_base_snconv_select_all_vs_oracle():
+    from oracle import sn_ref
+    from sngnn_b200 import synth, graph as G, functional as SF
+    n, c = 6000, 12
+    ei = synth.make_graph(n, 50000, seed=5, symmetric=False, hub_offset=3.0)
+    h = torch.randn(n, c)
+    hp = h.to(DEV).requires_grad_(True)
+    g = G.prepare(ei.to(DEV), n, False)
+    out = SF.edge_topk_agg(hp, g, None, None)
+    w = torch.randn(n, c, device=DEV)
+    (out * w).sum().backward()
+    h64 = h.double().requires_grad_(True)
+    ref = sn_ref.sn_aggregate(h64, sn_ref.process_edges(ei, n, False))
+    (ref * w.cpu().double()).sum().backward()
+    torch.testing.assert_close(out.detach().cpu().double(), ref.detach(), rtol=1e-5, atol=1e-6)
+    assert ((hp.grad.cpu().double() - h64.grad).abs().max() / h64.grad.abs().max()) < 2e-5
+
+
+def test_rownorm_spmm_sddmm():
+    from sngnn_b200 import functional as SF, synth, graph as G
+    torch.manual_seed(0)
+    x = torch.randn(3000, 65, device=DEV)
+    x[5] = 0
+    xf, xh, inv = SF.rownorm(x, want_f32=True, want_f16=True, f16_ld=80, want_inv=True)
+    ref = F.normalize(x, dim=-1)
+    torch.testing.assert_close(xf, ref, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(xh[:, :65].float(), ref, rtol=1e-3, atol=1e-4)
+    assert xh[:, 65:].abs().max().item() == 0
+    torch.testing.assert_close(inv, 1.0 / x.norm(dim=1).clamp(min=1e-12), rtol=1e-5, atol=0)
+    n, c = 4000, 32
+    ei = synth.make_graph(n, 40000, seed=3).to(DEV)
+    g = G.prepare(ei, n, True, structural=True)
+    X = torch.randn(n, c, device=DEV)
+    out = SF.spmm(X, g.rowptr_in, g.col_in, n)
+    pe = G.process_edges(ei, n, True)
+    ref = torch.zeros(n, c, device=DEV, dtype=torch.float64).index_add(0, pe[1], X.double()[pe[0]])
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+    a, b = pe[0][:1000], pe[1][:1000]
+    s = SF.sddmm_dot(F.normalize(X, dim=-1), a, b)
+    nx = F.normalize(X.double(), dim=-1)
+    torch.testing.assert_close(s.double(), (nx[a] * nx[b]).sum(-1), rtol=1e-5, atol=1e-6)
+
+
+def test_errors_are_loud():
+    from sngnn_b200 import functional as SF, graph as G, _C
+    ei = torch.tensor([[0, 1], [1, 0]], device=DEV)
+    g = G.prepare(ei, 2, True)
+    with pytest.raises(RuntimeError):
+        SF.edge_topk_agg(torch.randn(2, 4), g, 1, 0.0)                  # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        SF.edge_topk_agg(torch.randn(2, 4, device=DEV), g, 65, 0.0)     # top_k > SNG_MAX_TOPK
+    assert "top_k" in _C.last_error()
