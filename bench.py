@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark of the similarity-navigated aggregation hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (torchrun launches N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+One step = one all-pairs similarity-kNN build (K0 normalise -> [all-gather of x-hat at N>1] -> K1 tensor-core
+stage + FP32 rescore + exact fallback) of the pokec-shaped synthetic feature matrix (1,632,803 x 65, top_k=10),
+query rows sharded across ranks (strong scaling: the graph is fixed).
+`value` = ordered pairs / s = N*N / max-over-ranks device time, inputs resident in HBM.
+`e2e`   = the same through the public API from pinned HOST features to HOST neighbour lists.
+Also reported (same run, separately timed, not part of `value`): the SNGNN++ epoch on the pokec-shaped graph
+(30.6 M edges) and the fused mean-aggregation kernels' GB/s; `roofline` is for the tensor-core kernel.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "simknn_build_gpairs_per_s"
+UNIT = "Gpairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pokec", help="shape name from sngnn_b200.synth.SHAPES")
+    ap.add_argument("--top_k", type=int, default=10)
+    ap.add_argument("--thr", type=float, default=0.0)
+    ap.add_argument("--features", default="clustered", choices=["clustered", "normal"])
+    ap.add_argument("--skip-epoch", action="store_true", help="only the kNN build (used under ncu)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=2048, help="query-row slab of the CPU baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_knn_sample(x, rows, top_k, thr, block=1000):
+    """The reference's CPU path for this metric: blocked x-hat @ x-hat^T in 1000-row blocks
+    (R: SimGFAToolbox/dense.py:17-27) + the selection rule, as restated in oracle/sn_ref.py."""
+    from oracle import sn_ref
+    t0 = time.perf_counter()
+    sn_ref.simknn_allpairs(x, top_k, thr, True, 0, rows, block=block)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sngnn_b200 import synth
+    N, Fd, E, C = synth.SHAPES[args.workload]
+    x = synth.make_features(N, Fd, args.features, seed=0, zscore=(args.workload == "pokec"))
+    rows = min(args.cpu_rows // 4 if args.cpu_rows >= 2048 else args.cpu_rows, N)      # bounded sample per step
+    for _ in range(args.warmup):
+        cpu_knn_sample(x, min(rows, 256), args.top_k, args.thr)
+    ts = [cpu_knn_sample(x, rows, args.top_k, args.thr) for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    val = rows * N / t / 1e9
+    sample = f"{rows} query rows x all {N} columns per step (blocked torch.mm + stable sort, float32)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}-shape all-pairs kNN build N={N} d={Fd} top_k={args.top_k} thr={args.thr}",
+                       "features": args.features, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def timed(fn, steps, warmup, sync_all=None):
+    for _ in range(warmup):
+        fn()
+    if sync_all:
+        sync_all()
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps          # ms per call
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from sngnn_b200 import _C, simknn, synth
+    import sngnn_b200.models as M
+    import sngnn_b200.functional as SF
+    from sngnn_b200 import graph as G
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _C.lib()                                     # fail loudly if libsng.so is missing
+    pk = peaks()
+
+    N, Fd, E, C = synth.SHAPES[args.workload]
+    k, thr = args.top_k, args.thr
+    x = synth.make_features(N, Fd, args.features, seed=0, device=dev, zscore=(args.workload == "pokec"))
+    R = (N + world - 1) // world                  # rows per rank (the last rank may own fewer)
+    lo, hi = min(N, rank * R), min(N, (rank + 1) * R)
+    nq = hi - lo
+    ld32, ldh = simknn._pad_to(Fd, 4), simknn._pad_to(Fd, 16)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- resident-input step: normalise own rows, all-gather x-hat, build own rows ------------------------
+    xf_all = torch.zeros(world * R, ld32, dtype=torch.float32, device=dev)
+    xh_all = torch.zeros(world * R, ldh, dtype=torch.float16, device=dev)
+    xf_pad = torch.zeros(R, ld32, dtype=torch.float32, device=dev)
+    xh_pad = torch.zeros(R, ldh, dtype=torch.float16, device=dev)
+
+    def normalise_and_gather(x_shard):
+        xf, xh = simknn.normalize_operands(x_shard)
+        if world == 1:
+            return xf, xh
+        xf_pad[:nq].copy_(xf)
+        xh_pad[:nq].copy_(xh)
+        dist.all_gather_into_tensor(xf_all, xf_pad)          # NCCL over NVLink; x-hat is the only exchanged data
+        dist.all_gather_into_tensor(xh_all, xh_pad)
+        return xf_all[:N], xh_all[:N]
+
+    out = {}
+
+    def step_resident():
+        xf, xh = normalise_and_gather(x[lo:hi])
+        out["r"] = simknn.build_knn_normalized(xf, xh, Fd, k, thr, True, lo, hi, return_fallback=True)
+
+    # ---- end-to-end step: pinned host features -> device -> ... -> host neighbour lists -------------------
+    x_host = x[lo:hi].cpu().pin_memory()
+    idx_host = torch.empty(nq, k, dtype=torch.int32).pin_memory()
+    sim_host = torch.empty(nq, k, dtype=torch.float32).pin_memory()
+    cnt_host = torch.empty(nq, dtype=torch.int32).pin_memory()
+    x_stage = torch.empty_like(x[lo:hi])
+
+    def step_e2e():
+        x_stage.copy_(x_host, non_blocking=True)
+        xf, xh = normalise_and_gather(x_stage)
+        idx, sim, cnt = simknn.build_knn_normalized(xf, xh, Fd, k, thr, True, lo, hi)
+        idx_host.copy_(idx, non_blocking=True)
+        sim_host.copy_(sim, non_blocking=True)
+        cnt_host.copy_(cnt, non_blocking=True)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ms = timed(step_resident, args.steps, args.warmup, barrier)
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup - 2), barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    idx, sim, cnt, nfb = out["r"]
+    n_fallback = int(nfb)
+
+    # ---- the dominant kernel alone (roofline): tensor-core stage on this rank's rows -----------------------
+    xf, xh = normalise_and_gather(x[lo:hi])
+    import ctypes
+    cand = 32 if k <= 16 else (k + 16 + 7) // 8 * 8
+    ci = torch.empty(nq * 8 * cand, dtype=torch.int32, device=dev)
+    cv = torch.empty(nq * 8 * cand, dtype=torch.float32, device=dev)
+    cm = torch.empty(nq * 8, dtype=torch.float32, device=dev)
+    ns = ctypes.c_int(0)
+    thr_lo = thr - 1.01 * (2.0 ** -10 + 1.2e-4)
+
+    def stage1_only():
+        _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh[lo:]), _C.ptr(xh), ldh, nq, lo, N, Fd, cand, thr_lo, 1, _C.ptr(ci), _C.ptr(cv),
+                                            _C.ptr(cm), 0, 0, ctypes.byref(ns), _C.stream()), "sng_simknn_stage1")
+
+    ms_k1 = timed(stage1_only, max(2, args.steps // 2), 1)
+    flops = 2.0 * nq * N * Fd
+    achieved_tf = flops / (ms_k1 * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"stage1:{args.workload}:{world}")
+    roofline = {"bound": "tensor", "kernel": "simknn_stage1_kernel", "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": achieved_tf / pk["tf_sust"], "traffic": traffic, "peak_source": pk["src"] + " (sustained bf16/fp16 dense)",
+                "kernel_ms": ms_k1, "algorithmic_flops_per_launch": flops, "share_of_step": ms_k1 / ms}
+
+    # ---- SNGNN++ epoch + aggregation kernels on the pokec-shaped graph (rank 0 reports; replicas at N>1) ------
+    extras = {}
+    if not args.skip_epoch:
+        torch.cuda.empty_cache()
+        ei = synth.make_graph(N, E, seed=1, device=dev, symmetric=True)
+        y = synth.make_labels(N, C, seed=2, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g = G.prepare(ei, N, True, structural=True)
+        torch.cuda.synchronize()
+        prep_ms = (time.perf_counter() - t0) * 1e3
+        Ep = g.num_edges
+        hid = 32
+        torch.manual_seed(2)
+        model = M.SNGNN_Plus_Plus(Fd, hid, C, N, 2, k, thr, 0.5, 1, 0.5).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=5e-4)
+        data = synth.GraphData(x, ei)
+        import torch.nn.functional as F
+
+        def epoch():                                          # R: train.py:136-138 = train step + val + test forwards
+            model.train()
+            opt.zero_grad()
+            loss = F.nll_loss(model(data), y)
+            loss.backward()
+            opt.step()
+            model.eval()
+            with torch.no_grad():
+                model(data)
+                model(data)
+
+        def fwd_only():
+            model.eval()
+            with torch.no_grad():
+                model(data)
+
+        ep_ms = timed(epoch, 5, 2)
+        fw_ms = timed(fwd_only, 5, 1)
+        # fused aggregation kernels alone, C = 32
+        h = torch.randn(N, hid, device=dev)
+        gg = torch.randn(N, hid, device=dev)
+        sel = {}
+
+        def k2_fwd():
+            sel["o"] = SF.EdgeTopkAgg.apply(h, g, k, thr)
+
+        k2_ms = timed(k2_fwd, 10, 3)
+        _, ss, sw, sc = sel["o"]
+        dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
+
+        def k2_bwd():
+            dval.zero_(); dnrm.zero_()
+            _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(gg), N, hid, hid, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss),
+                                               _C.ptr(sw), _C.ptr(sc), _C.ptr(g.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh),
+                                               _C.stream()), "sng_edge_agg_bwd")
+
+        k2b_ms = timed(k2_bwd, 10, 3)
+        nsel = int(sc.sum())
+        bytes_fwd = Ep * (4 * hid + 4) + N * (8 * hid + 8) + 8 * N * k
+        bytes_bwd = nsel * (3 * 4 * hid + 16) + 3 * N * 4 * hid + 2 * N * 4 * hid   # + the two accumulator memsets
+        extras = {"epoch_ms": ep_ms, "forward_ms": fw_ms, "graph_prep_ms": prep_ms,
+                  "epoch_config": f"SNGNN_Plus_Plus 2 layers hidden {hid} top_k={k} thr={thr} init_beta=0.5 on {args.workload}-shape graph "
+                                  f"({Ep} edges after loop processing); epoch = fwd+loss+bwd+Adam + 2 eval forwards (R train.py:136-138)",
+                  "agg": {"fwd_ms": k2_ms, "fwd_gbs": bytes_fwd / (k2_ms * 1e-3) / 1e9, "fwd_frac_hbm": bytes_fwd / (k2_ms * 1e-3) / 1e9 / pk["hbm"],
+                          "bwd_ms": k2b_ms, "bwd_gbs": bytes_bwd / (k2b_ms * 1e-3) / 1e9, "bwd_frac_hbm": bytes_bwd / (k2b_ms * 1e-3) / 1e9 / pk["hbm"],
+                          "algorithmic_bytes_fwd": bytes_fwd, "algorithmic_bytes_bwd": bytes_bwd, "selected_edges": nsel, "channels": hid}}
+
+    # ---- parity gate on a sample of rows + CPU baseline (rank 0) ---------------------------------------------
+    parity, cpu = None, None
+    if rank == 0:
+        from oracle import sn_ref
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from parity import compare_lists
+        xc = x.cpu()
+        rows = 256
+        n64 = sn_ref.rownorm(xc.double())
+        iref, sref, cref = sn_ref.simknn_allpairs(xc.double(), k, thr, True, 0, rows, block=128, dtype=torch.float64)
+        parity = compare_lists(idx[:rows], cnt[:rows], iref, cref, lambda r, j: (n64[r] * n64[j]).sum(-1), thr)
+        parity["rows_checked"] = rows
+        parity["fallback_rows"] = n_fallback
+        if not args.skip_cpu:
+            cpu_rows = min(args.cpu_rows, N)
+            cpu_knn_sample(xc, 128, k, thr)
+            tc = cpu_knn_sample(xc, cpu_rows, k, thr)
+            cpu = {"value": cpu_rows * N / tc / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{cpu_rows} query rows x all {N} columns, blocked torch.mm (1000-row blocks) + stable sort, float32, {tc:.1f} s"}
+
+    if rank == 0:
+        pairs = float(N) * float(N)
+        h2d = x_host.numel() * 4
+        d2h = idx_host.numel() * 4 + sim_host.numel() * 4 + cnt_host.numel() * 4
+        line = {"metric": METRIC, "value": pairs / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 tensor-core scores + f32 exact rescore", "data": "synthetic",
+                "config": {"workload": f"{args.workload}-shape all-pairs similarity-kNN build: N={N} d={Fd} top_k={k} thr={thr} remove_self=1, "
+                                       f"query rows sharded over {world} GPU(s)",
+                           "features": args.features, "l2": "inputs larger than L2 (x-hat f16 %.0f MB, f32 %.0f MB)" % (N * ldh * 2 / 1e6, N * ld32 * 4 / 1e6),
+                           "parallelism": f"row-shard x{world}" + (" + NCCL all-gather of x-hat" if world > 1 else "")},
+                "e2e": {"value": pairs / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                "gpu_launches": 4 * args.steps, "kernels_per_step": ["rownorm_kernel", "simknn_stage1_kernel", "simknn_rescore_kernel", "simknn_fallback_kernel"],
+                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

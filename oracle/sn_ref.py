@@ -149,29 +149,43 @@ def rownorm(x):
 def simknn_allpairs(x, top_k, thr, remove_self, q_lo=0, q_hi=None, block=1024, dtype=torch.float32):
     """All-pairs similarity-kNN = "the reference selection rule on the complete graph" (SURVEY.md §0):
     candidates of query i are all nodes j (minus i if remove_self), ranked (cos desc, j asc), at most
-    top_k, cut at the first cos < thr.  Blocking follows R: SimGFAToolbox/dense.py:17-27.
+    top_k, cut at the first cos < thr.  Blocking follows R: SimGFAToolbox/dense.py:17-27 (blocked mm); the
+    per-row selection uses topk for the cut value and an exact (value desc, index asc) ordering of everything
+    at or above it, so ties are broken by index exactly like the iterated scatter_max of R: models.py:145-154.
     Returns idx [nq,k] int64 (-1 padded), sim [nq,k] (0 padded), cnt [nq]."""
     N = x.size(0)
     q_hi = N if q_hi is None else q_hi
     n = rownorm(x.to(dtype))
-    k = min(top_k, N)
-    idx = torch.full((q_hi - q_lo, top_k), -1, dtype=torch.long)
-    sim = torch.zeros(q_hi - q_lo, top_k, dtype=dtype)
-    cnt = torch.zeros(q_hi - q_lo, dtype=torch.long)
+    nq = q_hi - q_lo
+    idx = torch.full((nq, top_k), -1, dtype=torch.long)
+    sim = torch.zeros(nq, top_k, dtype=dtype)
+    cnt = torch.zeros(nq, dtype=torch.long)
+    kk = min(top_k, N)
     for lo in range(q_lo, q_hi, block):
         hi = min(lo + block, q_hi)
         s = n[lo:hi] @ n.t()
         if remove_self:
             r = torch.arange(lo, hi)
             s[r - lo, r] = float("-inf")
-        v, j = torch.sort(s, dim=1, descending=True, stable=True)
-        v, j = v[:, :k], j[:, :k]
-        ok = v >= thr
-        c = ok.long().cumprod(1).sum(1)
-        keep = torch.arange(k)[None, :] < c[:, None]
-        idx[lo - q_lo:hi - q_lo, :k] = torch.where(keep, j, torch.full_like(j, -1))
-        sim[lo - q_lo:hi - q_lo, :k] = torch.where(keep, v, torch.zeros_like(v))
-        cnt[lo - q_lo:hi - q_lo] = c
+        cut = torch.topk(s, kk, dim=1).values[:, -1:]
+        cut = torch.maximum(cut, torch.full_like(cut, thr))
+        rows, cols = ((s >= cut) & (s > float("-inf"))).nonzero(as_tuple=True)       # row-major: cols ascending per row
+        vals = s[rows, cols]
+        o1 = torch.argsort(-vals, stable=True)
+        o2 = torch.argsort(rows[o1], stable=True)
+        order = o1[o2]
+        rows, cols, vals = rows[order], cols[order], vals[order]
+        pos = torch.arange(rows.numel())
+        start = torch.ones(rows.numel(), dtype=torch.bool)
+        if rows.numel():
+            start[1:] = rows[1:] != rows[:-1]
+        first = torch.where(start, pos, torch.zeros_like(pos)).cummax(0).values
+        rank = pos - first
+        keep = rank < top_k
+        rows, cols, vals, rank = rows[keep], cols[keep], vals[keep], rank[keep]
+        idx[rows + (lo - q_lo), rank] = cols
+        sim[rows + (lo - q_lo), rank] = vals
+        cnt[lo - q_lo:hi - q_lo] = torch.bincount(rows, minlength=hi - lo)
     return idx, sim, cnt
 
 
