@@ -223,10 +223,10 @@ def run_ours(args):
     # ---- the dominant kernel alone (roofline): tensor-core stage on this rank's rows -----------------------
     xf, xh = normalise_and_gather(x[lo:hi])
     import ctypes
-    cand = 32 if k <= 16 else (k + 16 + 7) // 8 * 8
-    ci = torch.empty(nq * 8 * cand, dtype=torch.int32, device=dev)
-    cv = torch.empty(nq * 8 * cand, dtype=torch.float32, device=dev)
-    cm = torch.empty(nq * 8, dtype=torch.float32, device=dev)
+    cand = simknn.default_cand(k)
+    ci = torch.empty(nq * 512, dtype=torch.int32, device=dev)      # lists * cand <= 512 slots per row
+    cv = torch.empty(nq * 512, dtype=torch.float32, device=dev)
+    cm = torch.empty(nq * 64, dtype=torch.float32, device=dev)
     ns = ctypes.c_int(0)
     thr_lo = thr - 1.01 * (2.0 ** -10 + 1.2e-4)
 

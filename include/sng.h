@@ -149,14 +149,15 @@ SNG_API int sng_simknn_build(const uint16_t* xq_f16, const uint16_t* xall_f16, i
                      int32_t* idx, float* sim, int32_t* cnt, int32_t* n_fallback,
                      void* workspace, size_t workspace_bytes, void* stream);
 
-/* Stage 1 only (profiling / tests): cand_idx / cand_val [nq, nsplit, cand], cand_min [nq, nsplit] (worst kept
- * score of a list that filled up, else -inf).  force_mb in {0,1,2} picks the rows-per-CTA variant (0 = auto),
- * force_nsplit > 0 the number of column splits; *nsplit_out receives the value used (size the outputs for 8). */
+/* Stage 1 only (profiling / tests): cand_idx / cand_val [nq, lists, cand], cand_min [nq, lists] (upper bound of every
+ * score that list dropped, -inf if it dropped nothing above thr_lo); lists = column splits x epilogue warps per TMEM
+ * lane quarter.  force_ew in {0,1,2,4} picks the epilogue width (0 = auto), force_nsplit > 0 the number of column
+ * splits; *lists_out receives lists (size the outputs for lists * cand <= 512 slots per row). */
 SNG_API int sng_simknn_stage1(const uint16_t* xq_f16, const uint16_t* xall_f16, int64_t ldh,
                       int64_t nq, int64_t q_offset, int64_t n, int64_t d,
                       int cand, float thr_lo, int remove_self,
                       int32_t* cand_idx, float* cand_val, float* cand_min,
-                      int force_mb, int force_nsplit, int* nsplit_out, void* stream);
+                      int force_ew, int force_nsplit, int* lists_out, void* stream);
 
 #ifdef __cplusplus
 }

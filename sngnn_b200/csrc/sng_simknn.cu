@@ -23,31 +23,44 @@
 #include <cuda.h>        // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time
 #include <cuda_fp16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace sng {
 namespace knn {
 
-constexpr int BM = 128;                 // rows per MMA = TMEM lanes
-constexpr int BN = 128;                 // database columns per tile
+constexpr int BM = 128;                 // query rows per CTA = TMEM lanes (a CTA pair owns 256 rows)
+constexpr int BN = 256;                 // database columns per pair tile = UMMA N
 constexpr int BK = 64;                  // K elements per smem tile row = 128 bytes = one swizzle span
-constexpr int kTileBytes = BM * BK * 2; // 16 KiB
+constexpr int kTileBytes = 128 * BK * 2;// 16 KiB: one K block of 128 rows (A block, or this CTA's half of a B tile)
 constexpr int kUmmaK = 16;
 constexpr int kNonEpiThreads = 128;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 10;
 constexpr int kFallbackBlocks = 32;
-constexpr int kMaxCandTotal = 512;      // nsplit * cand <= this (stage-2 shared memory)
+constexpr int kMaxCandTotal = 512;      // lists per row * cand <= this (stage-2 shared memory)
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(bar), "r"(cta) : "memory");
 }
 // Bounded wait: a protocol bug must trap (error returned to the caller) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -65,18 +78,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+// TMA load issued by either CTA of the pair into its OWN shared memory; the bytes are credited to the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_leader), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+// D[tmem] (+)= A[smem] * B[smem]^T over the CTA pair: M = 256 (128 rows per CTA), N = 256 (128 B rows per CTA), K = 16
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// arrive (once all previously issued MMAs have retired) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -94,139 +111,170 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
+// v[i] for a warp-uniform runtime i, without local memory: 31 selects
+__device__ __forceinline__ float select32(const uint32_t (&v)[32], int i) {
+    uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (i & 1) ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (i & 2) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = (i & 4) ? b[2 * j + 1] : b[2 * j];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) d[j] = (i & 8) ? c[2 * j + 1] : c[2 * j];
+    return __uint_as_float((i & 16) ? d[1] : d[0]);
+}
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (sm_100 "version 1"):
 // rows are 128 B apart, 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: A,B = FP16 (0), D = FP32 (1 at bit 4), both K-major, N at [17,23) as N/8, M at [24,29) as M/16
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: A,B = FP16 (0), D = FP32 (1 at bit 4), both K-major, N/8 at [17,23), M/16 at [24,29); M = 256 spans the pair
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 struct Stage1Params {
     int nq, n, q_offset;          // query rows in this call, database rows, global id of query row 0
     int kblocks, ksteps_last;     // K tiling: kblocks tiles of 64, the last one has ksteps_last MMA steps of 16
-    int stages;                   // B ring depth
-    int cand;                     // candidate slots per row (L)
-    int nsplit, tiles_total;      // column tiles are split across gridDim.y CTAs
+    int stages;                   // B ring depth (K blocks)
+    int cand;                     // candidate slots per list (L)
+    int nsplit, tiles_total;      // 256-column tiles are split across gridDim.y cluster columns
     float thr_lo;                 // approximate scores <= thr_lo can never be selected
     int remove_self;
-    float* cand_val;              // [nq, nsplit, cand]
-    int* cand_idx;                // [nq, nsplit, cand]   (-1 = empty)
-    float* cand_min;              // [nq, nsplit]  worst kept approx score if the list filled up, else -inf
+    float* cand_val;              // [nq, nsplit*EW, cand]
+    int* cand_idx;                // [nq, nsplit*EW, cand]   (-1 = empty)
+    float* cand_min;              // [nq, nsplit*EW]  worst kept approx score if the list filled up, else -inf
 };
 
-template <int MB>
-__global__ void __launch_bounds__(kNonEpiThreads + 128 * MB, 1)
+// EW = epilogue warps per TMEM lane quarter; every epilogue thread owns one query row x (256/EW) columns of each tile
+// and its own candidate list; the EW threads of a row share one pruning threshold.
+template <int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 128 * EW, 1)
 simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const Stage1Params p) {
-    constexpr int ROWS = BM * MB;
+    constexpr int CPT = BN / EW;                                  // columns per thread per tile
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                      // 0 = leader (issues the MMAs)
     const uint32_t a_off = 0;
-    const uint32_t b_off = a_off + (uint32_t)MB * p.kblocks * kTileBytes;
+    const uint32_t b_off = a_off + (uint32_t)p.kblocks * kTileBytes;
     const uint32_t list_off = b_off + (uint32_t)p.stages * kTileBytes;
-    const uint32_t bar_off = list_off + (uint32_t)ROWS * p.cand * 8u;
+    const uint32_t thr_off = list_off + (uint32_t)EW * p.cand * BM * 8u;
+    const uint32_t bar_off = thr_off + BM * 4u;
     float* list_val = reinterpret_cast<float*>(smem + list_off);
-    int* list_idx = reinterpret_cast<int*>(smem + list_off + (size_t)ROWS * p.cand * 4);
-    const uint32_t bar_full = base + bar_off;                       // [kMaxStages]
-    const uint32_t bar_empty = bar_full + 8 * kMaxStages;           // [kMaxStages]
-    const uint32_t bar_a = bar_empty + 8 * kMaxStages;              // [1]
-    const uint32_t bar_tfull = bar_a + 8;                           // [2]
-    const uint32_t bar_tempty = bar_tfull + 16;                     // [2]
+    int* list_idx = reinterpret_cast<int*>(smem + list_off + (size_t)EW * p.cand * BM * 4);
+    volatile float* row_thr = reinterpret_cast<volatile float*>(smem + thr_off);
+    const uint32_t bar_full = base + bar_off;                       // [kMaxStages]  leader only: B K-block landed in both CTAs
+    const uint32_t bar_empty = bar_full + 8 * kMaxStages;           // [kMaxStages]  per CTA: MMAs that read the stage retired
+    const uint32_t bar_a = bar_empty + 8 * kMaxStages;              // [1]           leader only: both A blocks landed
+    const uint32_t bar_tfull = bar_a + 8;                           // [2]           per CTA: accumulator stage complete
+    const uint32_t bar_tempty = bar_tfull + 16;                     // [2]           leader only: both CTAs drained the stage
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 8 * (2 * kMaxStages + 5));
 
-    const int row0 = blockIdx.x * ROWS;
+    const int row0 = (int)blockIdx.x * BM;                          // blockIdx.x = 2 * pair + rank
     const int t_beg = (int)(((long long)p.tiles_total * blockIdx.y) / p.nsplit);
     const int t_end = (int)(((long long)p.tiles_total * (blockIdx.y + 1)) / p.nsplit);
-    constexpr uint32_t kTmemCols = 2 * MB * BN;                     // 256 or 512 (power of two)
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_a, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * MB); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_a, 2);
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 2 * 4 * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else if (warp == 3) {
+        for (int i = lane; i < BM; i += 32) row_thr[i] = p.thr_lo;
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    if (*tmem_slot != 0u) __trap();            // the CTA owns the SM, so all 512 columns start at 0; addresses below assume it
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            mbar_expect_tx(bar_a, (uint32_t)MB * p.kblocks * kTileBytes);
-            for (int mb = 0; mb < MB; ++mb)
-                for (int kb = 0; kb < p.kblocks; ++kb)
-                    tma_load_2d(base + a_off + (uint32_t)(mb * p.kblocks + kb) * kTileBytes, &map_q, bar_a, kb * BK, row0 + mb * BM);
-            int stage = 0; uint32_t phase = 0;
-            for (int t = t_beg; t < t_end; ++t) {
-                for (int kb = 0; kb < p.kblocks; ++kb) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, kTileBytes);
-                    tma_load_2d(base + b_off + (uint32_t)stage * kTileBytes, &map_db, bar_full + 8 * stage, kb * BK, t * BN);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        // ------------------------------------------------------------------ TMA producer (both CTAs, whole warp, one lane issues)
+        const bool issuer = elect_one();
+        const uint32_t bar_a_leader = bar_a & kPeerMask;
+        if (issuer) {
+            for (int kb = 0; kb < p.kblocks; ++kb)
+                tma_load_2d_pair(base + a_off + (uint32_t)kb * kTileBytes, &map_q, bar_a_leader, kb * BK, row0);
+            if (rank == 0) mbar_expect_tx(bar_a, 2u * (uint32_t)p.kblocks * kTileBytes);
+            else mbar_arrive_cluster(bar_a, 0);
+        }
+        int stage = 0; uint32_t phase = 0;
+        for (int t = t_beg; t < t_end; ++t) {
+            const int brow = t * BN + (int)rank * 128;              // this CTA stages its half of the tile's database rows
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                if (issuer) {
+                    tma_load_2d_pair(base + b_off + (uint32_t)stage * kTileBytes, &map_db, (bar_full + 8 * stage) & kPeerMask, kb * BK, brow);
+                    if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * kTileBytes);
+                    else mbar_arrive_cluster(bar_full + 8 * stage, 0);
                 }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp runs the loop, one lane issues)
+        if (rank == 0) {
+            const bool issuer = elect_one();
             mbar_wait(bar_a, 0);
             tc_fence_after();
+            const uint64_t adesc0 = make_smem_desc(base + a_off);
+            const uint64_t bdesc0 = make_smem_desc(base + b_off);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = t_beg; t < t_end; ++t) {
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
+                const uint32_t tmem_d = (uint32_t)(acc * BN);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const int ksteps = (kb == p.kblocks - 1) ? p.ksteps_last : (BK / kUmmaK);
-                    const uint64_t bdesc = make_smem_desc(base + b_off + (uint32_t)stage * kTileBytes);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-#pragma unroll
-                        for (int mb = 0; mb < MB; ++mb) {
-                            const uint64_t adesc = make_smem_desc(base + a_off + (uint32_t)(mb * p.kblocks + kb) * kTileBytes);
-                            // +32 bytes per K step inside the swizzle span = +2 in the (addr >> 4) field
-                            umma_f16(tmem_base + (uint32_t)((acc * MB + mb) * BN), adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2),
-                                     kIdesc, (kb | ks) != 0 ? 1u : 0u);
-                        }
+                    // descriptors count 16-byte units: one 16 KiB tile = 1024 units, one K step (32 B) = 2 units
+                    const uint64_t adesc = adesc0 + (uint64_t)(kb * (kTileBytes >> 4));
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kTileBytes >> 4));
+                    if (issuer) {
+                        for (int ks = 0; ks < ksteps; ++ks)
+                            umma_f16_pair(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), kIdesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_commit_pair(bar_empty + 8 * stage);        // frees this B stage in both CTAs when the MMAs retire
+                        if (kb == p.kblocks - 1) umma_commit_pair(bar_tfull + 8 * acc);   // accumulator of tile t complete (both CTAs)
                     }
-                    umma_commit(bar_empty + 8 * stage);            // frees this B stage when the MMAs retire
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * acc);                   // accumulator of tile t complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue: one thread = one query row
-        const int ew = warp - 4, mb = ew >> 2, quarter = warp & 3;
-        const int r = mb * BM + quarter * 32 + lane;              // row within the CTA == TMEM lane (+128*mb)
+        // ------------------------------------------------------------------ epilogue: thread = one query row x CPT columns per tile
+        const int quarter = warp & 3, slice = (warp - 4) >> 2;
+        const int r = quarter * 32 + lane;                        // row within the CTA == TMEM lane
         const int grow = row0 + r;
         const int self_col = p.remove_self ? (p.q_offset + grow) : -1;
         const int L = p.cand, n = p.n;
-        float* lv = list_val + r;
-        int* li = list_idx + r;
+        float* lv = list_val + (size_t)slice * L * BM + r;         // slot s at lv[s * BM]
+        int* li = list_idx + (size_t)slice * L * BM + r;
         int cnt = 0, minpos = 0;
-        float thr_cur = p.thr_lo;
+        float thr_cur = p.thr_lo;                                  // max(own list minimum once full, shared row threshold)
 
         auto insert = [&](float x, int col) {
             if (col >= n || col == self_col) return;
             int slot = minpos;
             if (cnt < L) slot = cnt++;
-            lv[slot * ROWS] = x;
-            li[slot * ROWS] = col;
+            lv[slot * BM] = x;
+            li[slot * BM] = col;
             if (cnt == L) {
                 float mn = lv[0]; int mp = 0;
-                for (int s = 1; s < L; ++s) { const float y = lv[s * ROWS]; if (y < mn) { mn = y; mp = s; } }
-                thr_cur = mn; minpos = mp;
+#pragma unroll 4
+                for (int s = 1; s < L; ++s) { const float y = lv[s * BM]; if (y < mn) { mn = y; mp = s; } }
+                minpos = mp;
+                if (mn > thr_cur) thr_cur = mn;
+                if (mn > row_thr[r]) row_thr[r] = mn;              // benign race: any list minimum is a valid row threshold
             }
         };
         auto process = [&](const uint32_t (&v)[32], int col0) {
@@ -236,10 +284,15 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
             const float m0 = max3(m[0], m[1], m[2]), m1 = max3(m[3], m[4], m[5]), m2 = max3(m[6], m[7], m[8]);
             const float mx = max3(max3(m0, m1, m2), m[9], m[10]);
-            if (mx > thr_cur) {
+            if (__any_sync(0xffffffffu, mx > thr_cur)) {           // rare, warp-uniform slow path (kept compact: one copy of insert)
+                uint32_t mask = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = __uint_as_float(v[i]);
+                for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) > thr_cur ? 1u : 0u) << i;
+                uint32_t todo = __reduce_or_sync(0xffffffffu, mask);
+                while (todo) {
+                    const int i = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const float x = select32(v, i);
                     if (x > thr_cur) insert(x, col0 + i);
                 }
             }
@@ -250,40 +303,45 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int t = t_beg; t < t_end; ++t) {
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * MB + mb) * BN);
-            const int col0 = t * BN;
+            thr_cur = fmaxf(thr_cur, row_thr[r]);
+            const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * CPT);
+            const int col0 = t * BN + slice * CPT;
             tmem_ld32(taddr, va);
-            tmem_ld_wait();
-            tmem_ld32(taddr + 32, vb);
-            process(va, col0);
-            tmem_ld_wait();
-            tmem_ld32(taddr + 64, va);
-            process(vb, col0 + 32);
-            tmem_ld_wait();
-            tmem_ld32(taddr + 96, vb);
-            process(va, col0 + 64);
-            tmem_ld_wait();
-            // all four loads of this accumulator stage have landed: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-            process(vb, col0 + 96);
+#pragma unroll
+            for (int c = 0; c < CPT / 32; c += 2) {
+                tmem_ld_wait();
+                tmem_ld32(taddr + (c + 1) * 32, vb);
+                process(va, col0 + c * 32);
+                tmem_ld_wait();
+                if (c + 2 < CPT / 32) tmem_ld32(taddr + (c + 2) * 32, va);
+                else {
+                    // every load of this accumulator stage has landed: hand the stage back to the leader's MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                }
+                process(vb, col0 + (c + 1) * 32);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (grow < p.nq) {
-            const size_t o = ((size_t)grow * p.nsplit + blockIdx.y) * L;
+            const int lists = p.nsplit * EW, li_id = (int)blockIdx.y * EW + slice;
+            const size_t o = ((size_t)grow * lists + li_id) * L;
             for (int s = 0; s < L; ++s) {
-                p.cand_val[o + s] = s < cnt ? lv[s * ROWS] : -CUDART_INF_F;
-                p.cand_idx[o + s] = s < cnt ? li[s * ROWS] : -1;
+                p.cand_val[o + s] = s < cnt ? lv[s * BM] : -CUDART_INF_F;
+                p.cand_idx[o + s] = s < cnt ? li[s * BM] : -1;
             }
-            p.cand_min[(size_t)grow * p.nsplit + blockIdx.y] = (cnt == L) ? thr_cur : -CUDART_INF_F;
+            float mn = -CUDART_INF_F;                               // bound on everything this thread ever dropped
+            if (cnt == L) { mn = lv[0]; for (int s = 1; s < L; ++s) mn = fminf(mn, lv[s * BM]); }
+            p.cand_min[(size_t)grow * lists + li_id] = fmaxf(mn, thr_cur > p.thr_lo ? thr_cur : -CUDART_INF_F);
         }
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                        // neither CTA may exit (or free TMEM) while the other can still signal / write it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(0u) : "memory");
     }
 }
 
@@ -443,49 +501,72 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
 }
 
 struct Plan {
-    int mb, stages, cand, nsplit, kblocks, ksteps_last, tiles;
+    int ew, stages, cand, nsplit, kblocks, ksteps_last, tiles;
     size_t smem;
+    int lists() const { return nsplit * ew; }
 };
 
-static size_t smem_bytes(int mb, int kblocks, int stages, int cand) {
-    return 1024 + (size_t)mb * kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)BM * mb * cand * 8 + 8 * (2 * kMaxStages + 5) + 16;
+static size_t smem_bytes(int ew, int kblocks, int stages, int cand) {
+    return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)ew * cand * BM * 8 + BM * 4 + 8 * (2 * kMaxStages + 5) + 16;
 }
 
+// candidate slots per list: the k best must survive with a margin for the FP16 score error (verified in stage 2)
 static int default_cand(int top_k) {
-    int c = top_k + 16;
-    if (c < 32) c = 32;
+    const char* e = getenv("SNG_KNN_MARGIN");
+    int c = top_k + (e ? atoi(e) : 6);
+    if (c < 16) c = 16;
     return (c + 7) / 8 * 8;
 }
 
-static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int cand, int force_mb) {
+static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int cand, int force_ew) {
     const size_t kMaxSmem = 227 * 1024;
+    if (!force_ew) {                     // tuning override for experiments: SNG_KNN_EW in {1,2,4}
+        const char* e = getenv("SNG_KNN_EW");
+        if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4') && e[1] == 0) force_ew = e[0] - '0';
+    }
     const int d16 = (int)((d + 15) / 16 * 16);
     pl->kblocks = (d16 + BK - 1) / BK;
     pl->ksteps_last = (d16 - (pl->kblocks - 1) * BK) / kUmmaK;
     pl->cand = cand;
     pl->tiles = (int)((n + BN - 1) / BN);
-    pl->mb = 0;
-    for (int mb = 2; mb >= 1; --mb) {
-        if (force_mb && mb != force_mb) continue;
-        for (int st = kMaxStages; st >= 2; --st) {
-            if (st > pl->kblocks * 4 && st > 4) continue;            // deeper than useful
-            const size_t s = smem_bytes(mb, pl->kblocks, st, cand);
-            if (s <= kMaxSmem) { pl->mb = mb; pl->stages = st; pl->smem = s; break; }
+    pl->ew = 0;
+    // small K: the epilogue (TMEM reads) paces the kernel -> 16 epilogue warps; large K: the MMAs do -> fewer, deeper B ring
+    const int ew_pref = d16 <= 128 ? 4 : (d16 <= 320 ? 2 : 1);
+    for (int ew = ew_pref; ew >= 1 && !pl->ew; ew >>= 1) {
+        if (force_ew && ew != force_ew) continue;
+        if (ew * cand > kMaxCandTotal) continue;
+        const int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
+        for (int st = want; st >= 3; --st) {
+            const size_t sz = smem_bytes(ew, pl->kblocks, st, cand);
+            if (sz <= kMaxSmem) { pl->ew = ew; pl->stages = st; pl->smem = sz; break; }
         }
-        if (pl->mb) break;
     }
-    if (!pl->mb) { set_error("simknn: d=%lld with %d candidate slots does not fit in shared memory", (long long)d, cand); return SNG_ERR_UNSUPPORTED; }
-    // a CTA must own the SM (TMEM: 2*MB*128 columns; two co-resident MB=2 CTAs would deadlock on allocation)
-    if (pl->mb == 2 && pl->smem <= kMaxSmem / 2) pl->smem = kMaxSmem / 2 + 1024;
+    if (force_ew && !pl->ew) {      // the forced value may exceed the preferred one
+        for (int st = kMaxStages; st >= 2 && !pl->ew; --st) {
+            const size_t sz = smem_bytes(force_ew, pl->kblocks, st, cand);
+            if (force_ew * cand <= kMaxCandTotal && sz <= kMaxSmem) { pl->ew = force_ew; pl->stages = st; pl->smem = sz; }
+        }
+    }
+    if (!pl->ew) { set_error("simknn: d=%lld with %d candidate slots does not fit in shared memory", (long long)d, cand); return SNG_ERR_UNSUPPORTED; }
+    // the pair kernel allocates all 512 TMEM columns: a CTA must own its SM, so never request less than half the shared memory
+    if (pl->smem <= kMaxSmem / 2) pl->smem = kMaxSmem / 2 + 1024;
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    const int64_t row_blocks = (nq + BM * pl->mb - 1) / (BM * pl->mb);
-    int ns = (int)((3ll * sms + row_blocks - 1) / row_blocks);
+    const int64_t ctas = 2 * ((nq + 2 * BM - 1) / (2 * BM));
+    int ns = (int)((3ll * sms + ctas - 1) / ctas);
     if (ns > 8) ns = 8;
     if (ns > pl->tiles) ns = pl->tiles;
-    if (ns * cand > kMaxCandTotal) ns = kMaxCandTotal / cand;
+    while (ns > 1 && ns * pl->ew * cand > kMaxCandTotal) --ns;
     if (ns < 1) ns = 1;
     pl->nsplit = ns;
     return SNG_OK;
+}
+
+template <int EW>
+static cudaError_t launch_ew(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mdb, const Stage1Params& p) {
+    cudaError_t e = cudaFuncSetAttribute(simknn_stage1_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    simknn_stage1_kernel<EW><<<grid, kNonEpiThreads + 128 * EW, smem, st>>>(mq, mdb, p);
+    return cudaSuccess;
 }
 
 static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n,
@@ -498,15 +579,10 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
     p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = pl.cand;
     p.nsplit = pl.nsplit; p.tiles_total = pl.tiles; p.thr_lo = thr_lo; p.remove_self = remove_self;
     p.cand_val = cand_val; p.cand_idx = cand_idx; p.cand_min = cand_min;
-    dim3 grid((unsigned)((nq + BM * pl.mb - 1) / (BM * pl.mb)), (unsigned)pl.nsplit);
-    cudaError_t e;
-    if (pl.mb == 2) {
-        e = cudaFuncSetAttribute(simknn_stage1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-        if (e == cudaSuccess) simknn_stage1_kernel<2><<<grid, kNonEpiThreads + 256, pl.smem, st>>>(mq, mdb, p);
-    } else {
-        e = cudaFuncSetAttribute(simknn_stage1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-        if (e == cudaSuccess) simknn_stage1_kernel<1><<<grid, kNonEpiThreads + 128, pl.smem, st>>>(mq, mdb, p);
-    }
+    dim3 grid((unsigned)(2 * ((nq + 2 * BM - 1) / (2 * BM))), (unsigned)pl.nsplit);      // x: CTA pairs (cluster of 2), y: column splits
+    cudaError_t e = pl.ew == 4 ? launch_ew<4>(grid, pl.smem, st, mq, mdb, p)
+                  : pl.ew == 2 ? launch_ew<2>(grid, pl.smem, st, mq, mdb, p)
+                               : launch_ew<1>(grid, pl.smem, st, mq, mdb, p);
     if (e != cudaSuccess) { cudaGetLastError(); set_error("simknn stage 1: cudaFuncSetAttribute(%zu B smem): %s", pl.smem, cudaGetErrorString(e)); return SNG_ERR_CUDA; }
     return check_launch("simknn stage 1");
 }
@@ -535,19 +611,21 @@ extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, i
     if (nq <= 0 || n <= 0 || d <= 0 || top_k <= 0 || top_k > SNG_KNN_MAX_TOPK) return 0;
     Plan pl;
     if (make_plan(&pl, nq, n, d, default_cand(top_k), 0)) return 0;
-    const size_t slots = (size_t)nq * pl.nsplit * pl.cand;
-    return align256(slots * 4) * 2 + align256((size_t)nq * 8 * 4) + align256((size_t)nq * 4) + align256((size_t)kFallbackBlocks * n * 4) + 1024;
+    const size_t slots = (size_t)nq * pl.lists() * pl.cand;
+    return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + align256((size_t)kFallbackBlocks * n * 4) + 1024;
 }
 
 extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n, int64_t d,
                                  int cand, float thr_lo, int remove_self, int32_t* cand_idx, float* cand_val, float* cand_min,
-                                 int force_mb, int force_nsplit, int* nsplit_out, void* stream) {
+                                 int force_ew, int force_nsplit, int* lists_out, void* stream) {
     if (int rc = check_common("sng_simknn_stage1", xq, xall, ldb, nq, q_offset, n, d)) return rc;
     SNG_REQUIRE(cand >= 8 && cand <= 128 && cand_idx && cand_val && cand_min, "sng_simknn_stage1: bad cand / outputs");
+    SNG_REQUIRE(force_ew == 0 || force_ew == 1 || force_ew == 2 || force_ew == 4, "sng_simknn_stage1: force_ew must be 0, 1, 2 or 4");
     Plan pl;
-    if (int rc = make_plan(&pl, nq, n, d, cand, force_mb)) return rc;
+    if (int rc = make_plan(&pl, nq, n, d, cand, force_ew)) return rc;
     if (force_nsplit > 0) pl.nsplit = force_nsplit < pl.tiles ? force_nsplit : pl.tiles;
-    if (nsplit_out) *nsplit_out = pl.nsplit;
+    SNG_REQUIRE(pl.lists() * cand <= kMaxCandTotal, "sng_simknn_stage1: nsplit*ew*cand = %d exceeds %d", pl.lists() * cand, kMaxCandTotal);
+    if (lists_out) *lists_out = pl.lists();
     return launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min, (cudaStream_t)stream);
 }
 
@@ -563,11 +641,11 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     Plan pl;
     if (int rc = make_plan(&pl, nq, n, d, default_cand(top_k), 0)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int m_total = pl.nsplit * pl.cand;
+    const int m_total = pl.lists() * pl.cand;
     uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float* cand_val = reinterpret_cast<float*>(w); w += align256((size_t)nq * m_total * 4);
     int* cand_idx = reinterpret_cast<int*>(w); w += align256((size_t)nq * m_total * 4);
-    float* cand_min = reinterpret_cast<float*>(w); w += align256((size_t)nq * 8 * 4);
+    float* cand_min = reinterpret_cast<float*>(w); w += align256((size_t)nq * pl.lists() * 4);
     int* fb_rows = reinterpret_cast<int*>(w); w += align256((size_t)nq * 4);
     float* scratch = reinterpret_cast<float*>(w);
     if (cudaMemsetAsync(n_fallback, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
@@ -578,7 +656,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     {
         const int blocks = (int)((nq + 7) / 8 < (int64_t)sm_count() * 8 ? (nq + 7) / 8 : (int64_t)sm_count() * 8);
         simknn_rescore_kernel<<<blocks > 0 ? blocks : 1, 256, (size_t)8 * 2 * m_total * 4, st>>>(
-            xq32, xall32, ld32, d4, (int)nq, m_total, pl.nsplit, top_k, thr, kScoreEps, cand_val, cand_idx, cand_min, idx, sim, cnt, fb_rows, n_fallback);
+            xq32, xall32, ld32, d4, (int)nq, m_total, pl.lists(), top_k, thr, kScoreEps, cand_val, cand_idx, cand_min, idx, sim, cnt, fb_rows, n_fallback);
         if (int rc = check_launch("simknn stage 2")) return rc;
     }
     simknn_fallback_kernel<<<kFallbackBlocks, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb_rows,

@@ -70,24 +70,28 @@ def knn_to_csr(idx, cnt):
     return rowptr.to(torch.int32), idx.reshape(-1)[flat].contiguous(), flat
 
 
-def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_mb=0, force_nsplit=0):
-    """Tensor-core stage only (tests / profiling): FP16-scored candidate lists [N, nsplit, cand]."""
+def default_cand(top_k):
+    """Candidate slots per list used by sng_simknn_build (mirrors csrc/sng_simknn.cu: default_cand)."""
+    import os
+    return max(16, (top_k + int(os.environ.get("SNG_KNN_MARGIN", "6")) + 7) // 8 * 8)
+
+
+def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_nsplit=0):
+    """Tensor-core stage only (tests / profiling): FP16-scored candidate lists [N, lists, cand] + per-list drop bounds."""
     import ctypes
     xf, xh = normalize_operands(x)
     n, d = x.shape
     dev = x.device
-    ci = torch.empty(n, 8, cand, dtype=torch.int32, device=dev)
-    cv = torch.empty(n, 8, cand, dtype=torch.float32, device=dev)
-    cm = torch.empty(n, 8, dtype=torch.float32, device=dev)
-    ns = ctypes.c_int(0)
+    slots = 512                                              # lists * cand never exceeds this (kMaxCandTotal)
+    ci = torch.empty(n * slots, dtype=torch.int32, device=dev)
+    cv = torch.empty(n * slots, dtype=torch.float32, device=dev)
+    cm = torch.empty(n * 64, dtype=torch.float32, device=dev)
+    nl = ctypes.c_int(0)
     _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh), _C.ptr(xh), xh.size(1), n, 0, n, d, cand, float(thr_lo), int(remove_self),
-                                        _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), force_mb, force_nsplit, ctypes.byref(ns), _C.stream()),
+                                        _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), force_ew, force_nsplit, ctypes.byref(nl), _C.stream()),
              "sng_simknn_stage1")
-    s = ns.value
-    flat_i = ci.reshape(-1)[: n * s * cand].reshape(n, s, cand)
-    flat_v = cv.reshape(-1)[: n * s * cand].reshape(n, s, cand)
-    flat_m = cm.reshape(-1)[: n * s].reshape(n, s)
-    return flat_i, flat_v, flat_m, xf, xh
+    s = nl.value
+    return ci[: n * s * cand].reshape(n, s, cand), cv[: n * s * cand].reshape(n, s, cand), cm[: n * s].reshape(n, s), xf, xh
 
 
 def allpairs_topk_agg(h, top_k, thr, remove_self, denominator="candidates"):
