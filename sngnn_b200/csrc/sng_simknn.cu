@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
 // Stage 3: exact scan for the rows stage 2 could not prove (many near-ties at the cut, e.g. duplicated or all-zero rows).
 __global__ void __launch_bounds__(256) simknn_fallback_kernel(
     const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int n, int q_offset, int top_k, float thr,
-    int remove_self, const int* __restrict__ fb_rows, const int* __restrict__ n_fallback, float* __restrict__ scratch,
+    int remove_self, const int* __restrict__ fb_rows, const int* __restrict__ n_fallback, int f_start, float* __restrict__ scratch,
     int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out) {
     __shared__ float red_s[8];
     __shared__ int red_i[8];
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(256) simknn_fallback_kernel(
     __shared__ int pick_i;
     float* sc = scratch + (size_t)blockIdx.x * n;
     const int nfb = *n_fallback;
-    for (int f = blockIdx.x; f < nfb; f += gridDim.x) {
+    for (int f = f_start + blockIdx.x; f < nfb; f += gridDim.x) {
         const int row = fb_rows[f];
         const float* a = xq + (int64_t)row * ld32;
         const int self_col = remove_self ? q_offset + row : -1;
@@ -458,6 +458,108 @@ __global__ void __launch_bounds__(256) simknn_fallback_kernel(
             if (threadIdx.x == 0) { idx_out[(size_t)row * top_k + t] = prev_i; sim_out[(size_t)row * top_k + t] = prev_s; }
             ++cnt;
             __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            for (int t = cnt; t < top_k; ++t) { idx_out[(size_t)row * top_k + t] = -1; sim_out[(size_t)row * top_k + t] = 0.f; }
+            cnt_out[row] = cnt;
+        }
+        __syncthreads();
+    }
+}
+
+// Stage 3 (parallel form): work item = (flagged row f, chunk of kChunk columns).  Scan: exact scores of the chunk in
+// shared memory, then top_k rounds of block argmax under (score desc, index asc) -> partial[f][chunk][top_k].
+// Merge: one block per flagged row reduces its n_chunks * top_k partial entries the same way.  Exact, tie-correct,
+// and parallel over columns, so a handful of flagged rows costs microseconds instead of a serial N-long scan.
+constexpr int kChunk = 8192;
+constexpr int kFbWaveRows = 4096;       // flagged rows handled per (scan, merge) wave
+constexpr int kFbWaves = 4;             // rows beyond kFbWaves * kFbWaveRows go to the serial kernel below
+
+struct Pick { float s; int i; };
+__device__ __forceinline__ Pick block_argmax(float bs, int bi, float* red_s, int* red_i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = bs; red_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    bs = red_s[0]; bi = red_i[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) if (better(red_s[w], red_i[w], bs, bi)) { bs = red_s[w]; bi = red_i[w]; }
+    __syncthreads();
+    return Pick{bs, bi};
+}
+
+__global__ void __launch_bounds__(256) simknn_fb_scan_kernel(
+    const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int n, int q_offset, int top_k, float thr,
+    int remove_self, const int* __restrict__ fb_rows, const int* __restrict__ n_fallback, int wave, int n_chunks,
+    float* __restrict__ part_s, int* __restrict__ part_i) {
+    __shared__ float sc[kChunk];
+    __shared__ float red_s[8];
+    __shared__ int red_i[8];
+    const int f_lo = wave * kFbWaveRows;
+    const int f_hi = min(*n_fallback, f_lo + kFbWaveRows);
+    const long long items = (long long)max(f_hi - f_lo, 0) * n_chunks;
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int fl = (int)(it / n_chunks), ch = (int)(it % n_chunks);
+        const int row = fb_rows[f_lo + fl];
+        const float* a = xq + (int64_t)row * ld32;
+        const int self_col = remove_self ? q_offset + row : -1;
+        const int c0 = ch * kChunk, cn = min(kChunk, n - c0);
+        for (int j = threadIdx.x; j < cn; j += blockDim.x)
+            sc[j] = (c0 + j == self_col) ? -CUDART_INF_F : dot_seq(a, xall + (int64_t)(c0 + j) * ld32, d4);
+        __syncthreads();
+        float prev_s = CUDART_INF_F; int prev_i = -1;
+        const size_t o = ((size_t)fl * n_chunks + ch) * top_k;
+        for (int t = 0; t < top_k; ++t) {
+            float bs = -CUDART_INF_F; int bi = 0x7fffffff;
+            for (int j = threadIdx.x; j < cn; j += blockDim.x) {
+                const float s = sc[j];
+                const int gi = c0 + j;
+                const bool after = s < prev_s || (s == prev_s && gi > prev_i);
+                if (after && s >= thr && better(s, gi, bs, bi)) { bs = s; bi = gi; }
+            }
+            const Pick pk = block_argmax(bs, bi, red_s, red_i);
+            prev_s = pk.s; prev_i = pk.i;
+            if (threadIdx.x == 0) { part_s[o + t] = pk.s; part_i[o + t] = pk.i == 0x7fffffff ? -1 : pk.i; }
+            if (pk.i == 0x7fffffff) {                                  // chunk exhausted: pad the remaining slots
+                for (int u = t + 1 + threadIdx.x; u < top_k; u += blockDim.x) { part_s[o + u] = -CUDART_INF_F; part_i[o + u] = -1; }
+                break;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) simknn_fb_merge_kernel(
+    const int* __restrict__ fb_rows, const int* __restrict__ n_fallback, int wave, int n_chunks, int top_k,
+    const float* __restrict__ part_s, const int* __restrict__ part_i, int* __restrict__ idx_out, float* __restrict__ sim_out,
+    int* __restrict__ cnt_out) {
+    __shared__ float red_s[8];
+    __shared__ int red_i[8];
+    const int f_lo = wave * kFbWaveRows;
+    const int f_hi = min(*n_fallback, f_lo + kFbWaveRows);
+    const int m = n_chunks * top_k;
+    for (int fl = blockIdx.x; fl < f_hi - f_lo; fl += gridDim.x) {
+        const int row = fb_rows[f_lo + fl];
+        const float* ps = part_s + (size_t)fl * m;
+        const int* pi = part_i + (size_t)fl * m;
+        float prev_s = CUDART_INF_F; int prev_i = -1; int cnt = 0;
+        for (int t = 0; t < top_k; ++t) {
+            float bs = -CUDART_INF_F; int bi = 0x7fffffff;
+            for (int j = threadIdx.x; j < m; j += blockDim.x) {
+                const int gi = pi[j];
+                if (gi < 0) continue;
+                const float s = ps[j];
+                const bool after = s < prev_s || (s == prev_s && gi > prev_i);
+                if (after && better(s, gi, bs, bi)) { bs = s; bi = gi; }
+            }
+            const Pick pk = block_argmax(bs, bi, red_s, red_i);
+            if (pk.i == 0x7fffffff) break;
+            prev_s = pk.s; prev_i = pk.i;
+            if (threadIdx.x == 0) { idx_out[(size_t)row * top_k + t] = pk.i; sim_out[(size_t)row * top_k + t] = pk.s; }
+            ++cnt;
         }
         if (threadIdx.x == 0) {
             for (int t = cnt; t < top_k; ++t) { idx_out[(size_t)row * top_k + t] = -1; sim_out[(size_t)row * top_k + t] = 0.f; }
@@ -512,10 +614,11 @@ static size_t smem_bytes(int ew, int kblocks, int stages, int cand) {
 
 // candidate slots per list: the k best must survive with a margin for the FP16 score error (verified in stage 2)
 static int default_cand(int top_k) {
-    const char* e = getenv("SNG_KNN_MARGIN");
-    int c = top_k + (e ? atoi(e) : 6);
-    if (c < 16) c = 16;
-    return (c + 7) / 8 * 8;
+    const char* e = getenv("SNG_KNN_CAND");          // tuning override for experiments
+    if (e && atoi(e) >= top_k && atoi(e) <= 128) return atoi(e);
+    int c = top_k + 4;
+    if (c < 14) c = 14;
+    return (c + 1) / 2 * 2;
 }
 
 static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int cand, int force_ew) {
@@ -612,7 +715,9 @@ extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, i
     Plan pl;
     if (make_plan(&pl, nq, n, d, default_cand(top_k), 0)) return 0;
     const size_t slots = (size_t)nq * pl.lists() * pl.cand;
-    return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + align256((size_t)kFallbackBlocks * n * 4) + 1024;
+    const size_t part = (size_t)kFbWaveRows * ((n + kChunk - 1) / kChunk) * top_k;
+    return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + align256((size_t)kFallbackBlocks * n * 4) +
+           2 * align256(part * 4) + 1024;
 }
 
 extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n, int64_t d,
@@ -647,7 +752,11 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     int* cand_idx = reinterpret_cast<int*>(w); w += align256((size_t)nq * m_total * 4);
     float* cand_min = reinterpret_cast<float*>(w); w += align256((size_t)nq * pl.lists() * 4);
     int* fb_rows = reinterpret_cast<int*>(w); w += align256((size_t)nq * 4);
-    float* scratch = reinterpret_cast<float*>(w);
+    float* scratch = reinterpret_cast<float*>(w); w += align256((size_t)kFallbackBlocks * n * 4);
+    const int n_chunks = (int)((n + kChunk - 1) / kChunk);
+    const size_t part = (size_t)kFbWaveRows * n_chunks * top_k;
+    float* part_s = reinterpret_cast<float*>(w); w += align256(part * 4);
+    int* part_i = reinterpret_cast<int*>(w);
     if (cudaMemsetAsync(n_fallback, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
     // approximate scores below thr - eps can never reach thr exactly
     const float thr_lo = thr - 1.01f * kScoreEps;
@@ -659,7 +768,13 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
             xq32, xall32, ld32, d4, (int)nq, m_total, pl.lists(), top_k, thr, kScoreEps, cand_val, cand_idx, cand_min, idx, sim, cnt, fb_rows, n_fallback);
         if (int rc = check_launch("simknn stage 2")) return rc;
     }
+    const int fb_grid = (sm_count() > 0 ? sm_count() : 148) * 4;
+    for (int wave = 0; wave < kFbWaves; ++wave) {
+        simknn_fb_scan_kernel<<<fb_grid, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb_rows, n_fallback,
+                                                      wave, n_chunks, part_s, part_i);
+        simknn_fb_merge_kernel<<<fb_grid, 256, 0, st>>>(fb_rows, n_fallback, wave, n_chunks, top_k, part_s, part_i, idx, sim, cnt);
+    }
     simknn_fallback_kernel<<<kFallbackBlocks, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb_rows,
-                                                           n_fallback, scratch, idx, sim, cnt);
+                                                           n_fallback, kFbWaves * kFbWaveRows, scratch, idx, sim, cnt);
     return check_launch("simknn stage 3");
 }

@@ -73,7 +73,9 @@ def knn_to_csr(idx, cnt):
 def default_cand(top_k):
     """Candidate slots per list used by sng_simknn_build (mirrors csrc/sng_simknn.cu: default_cand)."""
     import os
-    return max(16, (top_k + int(os.environ.get("SNG_KNN_MARGIN", "6")) + 7) // 8 * 8)
+    if os.environ.get("SNG_KNN_CAND"):
+        return int(os.environ["SNG_KNN_CAND"])
+    return (max(14, top_k + 4) + 1) // 2 * 2
 
 
 def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_nsplit=0):

@@ -72,6 +72,24 @@ def test_build_matches_oracle(n, d, k, thr, rs, kind):
     assert (sim.cpu().double()[same] - sim_ref[same]).abs().max() < 2e-6 if same.any() else True
 
 
+@pytest.mark.parametrize("n,d", [(1500, 40), (20000, 24)])
+def test_massive_ties_go_through_exact_fallback(n, d):
+    """Sparse 0/1 features: most scores tie (many at exactly 0), so stage 2 cannot prove most rows and the exact
+    stage-3 scans (parallel waves + serial remainder) must reproduce the index tie-break."""
+    from sngnn_b200 import simknn
+    g = torch.Generator().manual_seed(n)
+    x = (torch.rand(n, d, generator=g) < 0.03).float()       # ~half the rows are all-zero: every score ties at 0
+    k, thr = 10, -1.0
+    idx, sim, cnt, nfb = simknn.build_knn(x.to(DEV), k, thr, True, return_fallback=True)
+    torch.cuda.synchronize()
+    idx_ref, sim_ref, cnt_ref = _oracle(x, k, thr, True)
+    res = compare_lists(idx, cnt, idx_ref, cnt_ref, _score64(x), thr)
+    print(f"ties n={n}: {res} fallback_rows={int(nfb)}")
+    assert int(nfb) > n // 4
+    assert res["out_of_band"] == 0, res
+    assert check_tie_order(idx, sim, cnt)
+
+
 def test_build_row_sharded_equals_full():
     from sngnn_b200 import simknn
     n, d, k = 3000, 65, 10
