@@ -223,7 +223,7 @@ def run_ours(args):
     # ---- the dominant kernel alone (roofline): tensor-core stage on this rank's rows -----------------------
     xf, xh = normalise_and_gather(x[lo:hi])
     import ctypes
-    cand = simknn.default_cand(k)
+    ew, cand = simknn.default_cand(k, Fd)
     ci = torch.empty(nq * 512, dtype=torch.int32, device=dev)      # lists * cand <= 512 slots per row
     cv = torch.empty(nq * 512, dtype=torch.float32, device=dev)
     cm = torch.empty(nq * 64, dtype=torch.float32, device=dev)
@@ -232,7 +232,7 @@ def run_ours(args):
 
     def stage1_only():
         _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh[lo:]), _C.ptr(xh), ldh, nq, lo, N, Fd, cand, thr_lo, 1, _C.ptr(ci), _C.ptr(cv),
-                                            _C.ptr(cm), 0, 0, ctypes.byref(ns), _C.stream()), "sng_simknn_stage1")
+                                            _C.ptr(cm), ew, 0, ctypes.byref(ns), _C.stream()), "sng_simknn_stage1")
 
     ms_k1 = timed(stage1_only, max(2, args.steps // 2), 1)
     flops = 2.0 * nq * N * Fd

@@ -259,24 +259,27 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int L = p.cand, n = p.n;
         float* lv = list_val + (size_t)slice * L * BM + r;         // slot s at lv[s * BM]
         int* li = list_idx + (size_t)slice * L * BM + r;
-        int cnt = 0, minpos = 0;
+        int cnt = 0;
         float thr_cur = p.thr_lo;                                  // max(own list minimum once full, shared row threshold)
 
+        int minpos = 0;
         auto insert = [&](float x, int col) {
             if (col >= n || col == self_col) return;
             int slot = minpos;
             if (cnt < L) slot = cnt++;
             lv[slot * BM] = x;
             li[slot * BM] = col;
-            if (cnt == L) {
+            if (cnt == L) {                                          // list full: its minimum becomes this thread's threshold
                 float mn = lv[0]; int mp = 0;
 #pragma unroll 4
-                for (int s = 1; s < L; ++s) { const float y = lv[s * BM]; if (y < mn) { mn = y; mp = s; } }
+                for (int s2 = 1; s2 < L; ++s2) { const float y = lv[s2 * BM]; if (y < mn) { mn = y; mp = s2; } }
                 minpos = mp;
                 if (mn > thr_cur) thr_cur = mn;
-                if (mn > row_thr[r]) row_thr[r] = mn;              // benign race: any list minimum is a valid row threshold
+                if (mn > row_thr[r]) row_thr[r] = mn;              // shared with the row's other threads (any value is safe, see below)
             }
         };
+        // Pruning thresholds are heuristics: ANY threshold is safe because every thread reports the largest threshold it
+        // ever pruned with (cand_min) and stage 2 only accepts a row whose k-th exact score clears all of them.
         auto process = [&](const uint32_t (&v)[32], int col0) {
             float m[11];
 #pragma unroll
@@ -306,21 +309,33 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             thr_cur = fmaxf(thr_cur, row_thr[r]);
             const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * CPT);
             const int col0 = t * BN + slice * CPT;
-            tmem_ld32(taddr, va);
+            if (CPT == 64) {
+                // both loads in flight at once; the accumulator stage goes back to the MMA warp before any processing
+                tmem_ld32(taddr, va);
+                tmem_ld32(taddr + 32, vb);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                process(va, col0);
+                process(vb, col0 + 32);
+            } else {
+                tmem_ld32(taddr, va);
 #pragma unroll
-            for (int c = 0; c < CPT / 32; c += 2) {
-                tmem_ld_wait();
-                tmem_ld32(taddr + (c + 1) * 32, vb);
-                process(va, col0 + c * 32);
-                tmem_ld_wait();
-                if (c + 2 < CPT / 32) tmem_ld32(taddr + (c + 2) * 32, va);
-                else {
-                    // every load of this accumulator stage has landed: hand the stage back to the leader's MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                for (int c = 0; c < CPT / 32; c += 2) {
+                    tmem_ld_wait();
+                    tmem_ld32(taddr + (c + 1) * 32, vb);
+                    process(va, col0 + c * 32);
+                    tmem_ld_wait();
+                    if (c + 2 < CPT / 32) tmem_ld32(taddr + (c + 2) * 32, va);
+                    else {
+                        // every load of this accumulator stage has landed: hand the stage back to the leader's MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                    }
+                    process(vb, col0 + (c + 1) * 32);
                 }
-                process(vb, col0 + (c + 1) * 32);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -331,9 +346,8 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 p.cand_val[o + s] = s < cnt ? lv[s * BM] : -CUDART_INF_F;
                 p.cand_idx[o + s] = s < cnt ? li[s * BM] : -1;
             }
-            float mn = -CUDART_INF_F;                               // bound on everything this thread ever dropped
-            if (cnt == L) { mn = lv[0]; for (int s = 1; s < L; ++s) mn = fminf(mn, lv[s * BM]); }
-            p.cand_min[(size_t)grow * lists + li_id] = fmaxf(mn, thr_cur > p.thr_lo ? thr_cur : -CUDART_INF_F);
+            // bound on everything this thread ever dropped: the largest threshold it pruned with (its own evictions included)
+            p.cand_min[(size_t)grow * lists + li_id] = thr_cur > p.thr_lo ? thr_cur : -CUDART_INF_F;
         }
     }
     tc_fence_before();
@@ -411,59 +425,6 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
             if (!(kth > bound)) fb_rows[atomicAdd(n_fallback, 1)] = row;
         }
         __syncwarp();
-    }
-}
-
-// Stage 3: exact scan for the rows stage 2 could not prove (many near-ties at the cut, e.g. duplicated or all-zero rows).
-__global__ void __launch_bounds__(256) simknn_fallback_kernel(
-    const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int n, int q_offset, int top_k, float thr,
-    int remove_self, const int* __restrict__ fb_rows, const int* __restrict__ n_fallback, int f_start, float* __restrict__ scratch,
-    int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out) {
-    __shared__ float red_s[8];
-    __shared__ int red_i[8];
-    __shared__ float pick_s;
-    __shared__ int pick_i;
-    float* sc = scratch + (size_t)blockIdx.x * n;
-    const int nfb = *n_fallback;
-    for (int f = f_start + blockIdx.x; f < nfb; f += gridDim.x) {
-        const int row = fb_rows[f];
-        const float* a = xq + (int64_t)row * ld32;
-        const int self_col = remove_self ? q_offset + row : -1;
-        for (int j = threadIdx.x; j < n; j += blockDim.x)
-            sc[j] = (j == self_col) ? -CUDART_INF_F : dot_seq(a, xall + (int64_t)j * ld32, d4);
-        __syncthreads();
-        float prev_s = CUDART_INF_F; int prev_i = -1; int cnt = 0;
-        for (int t = 0; t < top_k; ++t) {
-            float bs = -CUDART_INF_F; int bi = 0x7fffffff;
-            for (int j = threadIdx.x; j < n; j += blockDim.x) {
-                const float s = sc[j];
-                const bool after = s < prev_s || (s == prev_s && j > prev_i);     // strictly after the previous pick
-                if (after && s >= thr && better(s, j, bs, bi)) { bs = s; bi = j; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (better(os, oi, bs, bi)) { bs = os; bi = oi; }
-            }
-            if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = bs; red_i[threadIdx.x >> 5] = bi; }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int w = 1; w < 8; ++w) if (better(red_s[w], red_i[w], bs, bi)) { bs = red_s[w]; bi = red_i[w]; }
-                pick_s = bs; pick_i = bi;
-            }
-            __syncthreads();
-            prev_s = pick_s; prev_i = pick_i;
-            if (prev_i == 0x7fffffff) break;                      // nothing left above thr (uniform across the block)
-            if (threadIdx.x == 0) { idx_out[(size_t)row * top_k + t] = prev_i; sim_out[(size_t)row * top_k + t] = prev_s; }
-            ++cnt;
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) {
-            for (int t = cnt; t < top_k; ++t) { idx_out[(size_t)row * top_k + t] = -1; sim_out[(size_t)row * top_k + t] = 0.f; }
-            cnt_out[row] = cnt;
-        }
-        __syncthreads();
     }
 }
 
@@ -569,6 +530,67 @@ __global__ void __launch_bounds__(256) simknn_fb_merge_kernel(
     }
 }
 
+// Stage 3 (throughput form) for flagged rows beyond the parallel waves: one block streams all chunks of one row and keeps
+// the running top_k (sorted by (score desc, index asc)) in shared memory.  Chunks arrive in increasing column order, so a
+// chunk whose best score does not strictly beat the current k-th entry cannot change the answer and is skipped.
+__global__ void __launch_bounds__(256) simknn_fb_stream_kernel(
+    const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int n, int q_offset, int top_k, float thr,
+    int remove_self, const int* __restrict__ fb_rows, const int* __restrict__ n_fallback, int f_start,
+    int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out) {
+    __shared__ float sc[kChunk];
+    __shared__ float red_s[8];
+    __shared__ int red_i[8];
+    __shared__ float best_s[SNG_KNN_MAX_TOPK];
+    __shared__ int best_i[SNG_KNN_MAX_TOPK];
+    __shared__ int best_n;
+    const int nfb = *n_fallback;
+    for (int f = f_start + blockIdx.x; f < nfb; f += gridDim.x) {
+        const int row = fb_rows[f];
+        const float* a = xq + (int64_t)row * ld32;
+        const int self_col = remove_self ? q_offset + row : -1;
+        if (threadIdx.x == 0) best_n = 0;
+        __syncthreads();
+        for (int c0 = 0; c0 < n; c0 += kChunk) {
+            const int cn = min(kChunk, n - c0);
+            for (int j = threadIdx.x; j < cn; j += blockDim.x)
+                sc[j] = (c0 + j == self_col) ? -CUDART_INF_F : dot_seq(a, xall + (int64_t)(c0 + j) * ld32, d4);
+            __syncthreads();
+            float prev_s = CUDART_INF_F; int prev_i = -1;
+            for (int t = 0; t < top_k; ++t) {
+                const int bn = best_n;
+                const float kth = bn == top_k ? best_s[top_k - 1] : -CUDART_INF_F;
+                float bs = -CUDART_INF_F; int bi = 0x7fffffff;
+                for (int j = threadIdx.x; j < cn; j += blockDim.x) {
+                    const float sv = sc[j];
+                    const int gi = c0 + j;
+                    const bool after = sv < prev_s || (sv == prev_s && gi > prev_i);
+                    if (after && sv >= thr && sv > kth && better(sv, gi, bs, bi)) { bs = sv; bi = gi; }
+                }
+                const Pick pk = block_argmax(bs, bi, red_s, red_i);
+                if (pk.i == 0x7fffffff) break;                          // nothing left in this chunk that beats the k-th entry
+                prev_s = pk.s; prev_i = pk.i;
+                if (threadIdx.x == 0) {                                   // sorted insert (new columns lose ties: larger index)
+                    int pos = bn < top_k ? bn : top_k - 1;
+                    while (pos > 0 && best_s[pos - 1] < pk.s) { best_s[pos] = best_s[pos - 1]; best_i[pos] = best_i[pos - 1]; --pos; }
+                    best_s[pos] = pk.s; best_i[pos] = pk.i;
+                    if (bn < top_k) best_n = bn + 1;
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int bn = best_n;
+            for (int t = 0; t < top_k; ++t) {
+                idx_out[(size_t)row * top_k + t] = t < bn ? best_i[t] : -1;
+                sim_out[(size_t)row * top_k + t] = t < bn ? best_s[t] : 0.f;
+            }
+            cnt_out[row] = bn;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -612,45 +634,49 @@ static size_t smem_bytes(int ew, int kblocks, int stages, int cand) {
     return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)ew * cand * BM * 8 + BM * 4 + 8 * (2 * kMaxStages + 5) + 16;
 }
 
-// candidate slots per list: the k best must survive with a margin for the FP16 score error (verified in stage 2)
-static int default_cand(int top_k) {
-    const char* e = getenv("SNG_KNN_CAND");          // tuning override for experiments
-    if (e && atoi(e) >= top_k && atoi(e) <= 128) return atoi(e);
-    int c = top_k + 4;
+static int env_int(const char* name, int lo, int hi) {       // tuning overrides for experiments
+    const char* e = getenv(name);
+    if (!e) return 0;
+    const int v = atoi(e);
+    return (v >= lo && v <= hi) ? v : 0;
+}
+
+// Candidate slots per list.  Every list keeps its best `cand` FP16 scores; stage 2 proves a row only if its k-th exact
+// score clears every list's drop bound by the FP16 error, so cand - top_k is the number of near-cut columns one column
+// slice may hold before the row has to go to the exact scan.
+static int cand_for(int top_k, int ew) {
+    const int o = env_int("SNG_KNN_CAND", top_k, 128);
+    if (o) return o;
+    int c = top_k + (ew >= 4 ? 4 : (ew == 2 ? 10 : 16));
     if (c < 14) c = 14;
     return (c + 1) / 2 * 2;
 }
 
-static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int cand, int force_ew) {
+// top_k > 0: derive cand from top_k;  top_k == 0: use the explicit `cand` (stage-1 test entry point)
+static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int cand, int force_ew) {
     const size_t kMaxSmem = 227 * 1024;
-    if (!force_ew) {                     // tuning override for experiments: SNG_KNN_EW in {1,2,4}
-        const char* e = getenv("SNG_KNN_EW");
-        if (e && (e[0] == '1' || e[0] == '2' || e[0] == '4') && e[1] == 0) force_ew = e[0] - '0';
-    }
+    if (!force_ew) force_ew = env_int("SNG_KNN_EW", 1, 4) == 3 ? 0 : env_int("SNG_KNN_EW", 1, 4);
     const int d16 = (int)((d + 15) / 16 * 16);
     pl->kblocks = (d16 + BK - 1) / BK;
     pl->ksteps_last = (d16 - (pl->kblocks - 1) * BK) / kUmmaK;
-    pl->cand = cand;
     pl->tiles = (int)((n + BN - 1) / BN);
     pl->ew = 0;
     // small K: the epilogue (TMEM reads) paces the kernel -> 16 epilogue warps; large K: the MMAs do -> fewer, deeper B ring
     const int ew_pref = d16 <= 128 ? 4 : (d16 <= 320 ? 2 : 1);
-    for (int ew = ew_pref; ew >= 1 && !pl->ew; ew >>= 1) {
-        if (force_ew && ew != force_ew) continue;
-        if (ew * cand > kMaxCandTotal) continue;
-        const int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
-        for (int st = want; st >= 3; --st) {
-            const size_t sz = smem_bytes(ew, pl->kblocks, st, cand);
-            if (sz <= kMaxSmem) { pl->ew = ew; pl->stages = st; pl->smem = sz; break; }
+    for (int pass = 0; pass < 2 && !pl->ew; ++pass) {
+        for (int ew = force_ew ? force_ew : ew_pref; ew >= 1 && !pl->ew; ew >>= 1) {
+            const int c = top_k > 0 ? cand_for(top_k, ew) : cand;
+            if (ew * c <= kMaxCandTotal) {
+                const int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
+                for (int st = want; st >= (pass ? 2 : 3); --st) {
+                    const size_t sz = smem_bytes(ew, pl->kblocks, st, c);
+                    if (sz <= kMaxSmem) { pl->ew = ew; pl->stages = st; pl->smem = sz; pl->cand = c; break; }
+                }
+            }
+            if (force_ew) break;
         }
     }
-    if (force_ew && !pl->ew) {      // the forced value may exceed the preferred one
-        for (int st = kMaxStages; st >= 2 && !pl->ew; --st) {
-            const size_t sz = smem_bytes(force_ew, pl->kblocks, st, cand);
-            if (force_ew * cand <= kMaxCandTotal && sz <= kMaxSmem) { pl->ew = force_ew; pl->stages = st; pl->smem = sz; }
-        }
-    }
-    if (!pl->ew) { set_error("simknn: d=%lld with %d candidate slots does not fit in shared memory", (long long)d, cand); return SNG_ERR_UNSUPPORTED; }
+    if (!pl->ew) { set_error("simknn: d=%lld top_k=%d does not fit in shared memory", (long long)d, top_k); return SNG_ERR_UNSUPPORTED; }
     // the pair kernel allocates all 512 TMEM columns: a CTA must own its SM, so never request less than half the shared memory
     if (pl->smem <= kMaxSmem / 2) pl->smem = kMaxSmem / 2 + 1024;
     const int sms = sm_count() > 0 ? sm_count() : 148;
@@ -658,7 +684,7 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int cand, int f
     int ns = (int)((3ll * sms + ctas - 1) / ctas);
     if (ns > 8) ns = 8;
     if (ns > pl->tiles) ns = pl->tiles;
-    while (ns > 1 && ns * pl->ew * cand > kMaxCandTotal) --ns;
+    while (ns > 1 && ns * pl->ew * pl->cand > kMaxCandTotal) --ns;
     if (ns < 1) ns = 1;
     pl->nsplit = ns;
     return SNG_OK;
@@ -713,11 +739,10 @@ static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, int top_k) {
     if (nq <= 0 || n <= 0 || d <= 0 || top_k <= 0 || top_k > SNG_KNN_MAX_TOPK) return 0;
     Plan pl;
-    if (make_plan(&pl, nq, n, d, default_cand(top_k), 0)) return 0;
+    if (make_plan(&pl, nq, n, d, top_k, 0, 0)) return 0;
     const size_t slots = (size_t)nq * pl.lists() * pl.cand;
     const size_t part = (size_t)kFbWaveRows * ((n + kChunk - 1) / kChunk) * top_k;
-    return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + align256((size_t)kFallbackBlocks * n * 4) +
-           2 * align256(part * 4) + 1024;
+    return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + 2 * align256(part * 4) + 1024;
 }
 
 extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n, int64_t d,
@@ -727,7 +752,7 @@ extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64
     SNG_REQUIRE(cand >= 8 && cand <= 128 && cand_idx && cand_val && cand_min, "sng_simknn_stage1: bad cand / outputs");
     SNG_REQUIRE(force_ew == 0 || force_ew == 1 || force_ew == 2 || force_ew == 4, "sng_simknn_stage1: force_ew must be 0, 1, 2 or 4");
     Plan pl;
-    if (int rc = make_plan(&pl, nq, n, d, cand, force_ew)) return rc;
+    if (int rc = make_plan(&pl, nq, n, d, 0, cand, force_ew)) return rc;
     if (force_nsplit > 0) pl.nsplit = force_nsplit < pl.tiles ? force_nsplit : pl.tiles;
     SNG_REQUIRE(pl.lists() * cand <= kMaxCandTotal, "sng_simknn_stage1: nsplit*ew*cand = %d exceeds %d", pl.lists() * cand, kMaxCandTotal);
     if (lists_out) *lists_out = pl.lists();
@@ -744,7 +769,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     SNG_REQUIRE(idx && sim && cnt && n_fallback && workspace, "sng_simknn_build: null output / workspace");
     if (workspace_bytes < sng_simknn_workspace_bytes(nq, n, d, top_k)) { set_error("sng_simknn_build: workspace too small (%zu < %zu)", workspace_bytes, sng_simknn_workspace_bytes(nq, n, d, top_k)); return SNG_ERR_WORKSPACE; }
     Plan pl;
-    if (int rc = make_plan(&pl, nq, n, d, default_cand(top_k), 0)) return rc;
+    if (int rc = make_plan(&pl, nq, n, d, top_k, 0, 0)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int m_total = pl.lists() * pl.cand;
     uint8_t* w = reinterpret_cast<uint8_t*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -752,7 +777,6 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     int* cand_idx = reinterpret_cast<int*>(w); w += align256((size_t)nq * m_total * 4);
     float* cand_min = reinterpret_cast<float*>(w); w += align256((size_t)nq * pl.lists() * 4);
     int* fb_rows = reinterpret_cast<int*>(w); w += align256((size_t)nq * 4);
-    float* scratch = reinterpret_cast<float*>(w); w += align256((size_t)kFallbackBlocks * n * 4);
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
     const size_t part = (size_t)kFbWaveRows * n_chunks * top_k;
     float* part_s = reinterpret_cast<float*>(w); w += align256(part * 4);
@@ -774,7 +798,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
                                                       wave, n_chunks, part_s, part_i);
         simknn_fb_merge_kernel<<<fb_grid, 256, 0, st>>>(fb_rows, n_fallback, wave, n_chunks, top_k, part_s, part_i, idx, sim, cnt);
     }
-    simknn_fallback_kernel<<<kFallbackBlocks, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb_rows,
-                                                           n_fallback, kFbWaves * kFbWaveRows, scratch, idx, sim, cnt);
+    simknn_fb_stream_kernel<<<fb_grid, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb_rows,
+                                                    n_fallback, kFbWaves * kFbWaveRows, idx, sim, cnt);
     return check_launch("simknn stage 3");
 }

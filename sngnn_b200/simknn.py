@@ -70,12 +70,14 @@ def knn_to_csr(idx, cnt):
     return rowptr.to(torch.int32), idx.reshape(-1)[flat].contiguous(), flat
 
 
-def default_cand(top_k):
-    """Candidate slots per list used by sng_simknn_build (mirrors csrc/sng_simknn.cu: default_cand)."""
+def default_cand(top_k, d):
+    """(epilogue warps per lane quarter, candidate slots per list) that sng_simknn_build picks for (top_k, d);
+    mirrors make_plan / cand_for in csrc/sng_simknn.cu (used to reproduce its stage-1 launch for profiling)."""
     import os
-    if os.environ.get("SNG_KNN_CAND"):
-        return int(os.environ["SNG_KNN_CAND"])
-    return (max(14, top_k + 4) + 1) // 2 * 2
+    d16 = _pad_to(d, 16)
+    ew = int(os.environ.get("SNG_KNN_EW", 0)) or (4 if d16 <= 128 else (2 if d16 <= 320 else 1))
+    cand = int(os.environ.get("SNG_KNN_CAND", 0)) or (max(top_k + {4: 4, 2: 10, 1: 16}[ew], 14) + 1) // 2 * 2
+    return ew, cand
 
 
 def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_nsplit=0):
