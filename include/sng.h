@@ -70,8 +70,10 @@ SNG_API int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx,
  *   out[i]= (1/max(deg_i,1)) * sum_{e in S_i} s_e * h[src_e]
  * Saved for backward (top_k > 0): sel_src [n,top_k] (source ids, rank order, -1 padded),
  * sel_w [n,top_k] (s_e), sel_cnt [n].  With top_k <= 0 those three may be NULL.
+ * Row sharding: the call covers target rows [row_offset, row_offset + n) of `h` (which holds ALL nodes, because
+ * sources are arbitrary); rowptr / out / sel_* are local to the shard, `col` holds global source ids.
  */
-SNG_API int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t c, int64_t ldh,
+SNG_API int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
                           const int32_t* rowptr, const int32_t* col,
                           int top_k, float thr,
                           float* out, int64_t ldo,

@@ -44,7 +44,8 @@ __device__ __forceinline__ float cross_group_sum(float v) {
     for (int o = 16; o >= G; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ float inv_norm_of(float ss) { return 1.0f / fmaxf(sqrtf(ss), kNormEps); }
+// 1 / max(||x||, 1e-12) from the squared norm (one MUFU.RSQ; 2 ulp, far inside the 1e-5 contract)
+__device__ __forceinline__ float inv_norm_of(float ss) { return rsqrtf(fmaxf(ss, kNormEps * kNormEps)); }
 
 // lanes-per-row group size for a padded channel count c (multiple of 4): smallest power of two >= c/4
 inline int group_lanes(int64_t c) {

@@ -73,7 +73,7 @@ struct TopList {
 
 template <int G, bool SELECT_ALL>
 __global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
-    const float* __restrict__ h, int n, int c, int64_t ldh, const int* __restrict__ rowptr, const int* __restrict__ col,
+    const float* __restrict__ h, int n, int row_offset, int c, int64_t ldh, const int* __restrict__ rowptr, const int* __restrict__ col,
     int top_k, float thr, float* __restrict__ out, int64_t ldo,
     int* __restrict__ sel_src, float* __restrict__ sel_w, int* __restrict__ sel_cnt) {
     constexpr int EPW = 32 / G;                 // edges per warp step
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
 
     for (int row = blockIdx.x * kWarpsPerBlock + warp; row < n; row += gridDim.x * kWarpsPerBlock) {
         const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-        const float4 hi = ch_ok ? ldg4(h + (int64_t)row * ldh + c4) : z4;
+        const float4 hi = ch_ok ? ldg4(h + (int64_t)(row_offset + row) * ldh + c4) : z4;     // target row's own features
         const float4 ni = scale4(hi, inv_norm_of(group_sum<G>(dot4(hi, hi))));
         float4 acc = z4;
         L.cnt = 0; L.kth = -CUDART_INF_F;
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
         for (int base = beg; base < end; base += 32) {
             const int nchunk = min(32, end - base);
             const int jl = lane < nchunk ? __ldg(col + base + lane) : -1;
+            float my_s = -CUDART_INF_F;                          // score of edge base+lane (lane == position inside the chunk)
             for (int st = 0; st < nchunk; st += EPW * U) {
                 float4 v[U]; int j[U];
 #pragma unroll
@@ -115,12 +116,37 @@ __global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
                     if (SELECT_ALL) {
                         if (j[u] >= 0) fma4(acc, sc, v[u]);
                     } else {
-#pragma unroll
-                        for (int g2 = 0; g2 < EPW; ++g2) {                   // edges in position order
-                            const float sg = __shfl_sync(0xffffffffu, sc, g2 * G);
-                            const int jg = __shfl_sync(0xffffffffu, j[u], g2 * G);
-                            if (jg >= 0 && sg >= thr && (L.cnt < top_k || sg > L.kth)) L.insert(sg, jg, top_k, lane);
-                        }
+                        // hand the score of (step, group) to the lane that owns that edge position
+                        const float t = __shfl_sync(0xffffffffu, sc, (lane % EPW) * G);
+                        if (lane / EPW == st / EPW + u) my_s = t;
+                    }
+                }
+            }
+            if (!SELECT_ALL) {
+                const bool valid = jl >= 0 && my_s >= thr;
+                if (L.cnt == 0) {
+                    // empty list (normally the row's first and only chunk): rank all candidates of the chunk at once
+                    unsigned m = __ballot_sync(0xffffffffu, valid);
+                    const int nv = __popc(m);
+                    int rank = 0;
+                    while (m) {
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float os = __shfl_sync(0xffffffffu, my_s, l);
+                        rank += (os > my_s || (os == my_s && l < lane)) ? 1 : 0;
+                    }
+                    if (valid && rank < top_k) { L.s[rank] = my_s; L.j[rank] = jl; }
+                    __syncwarp();
+                    L.cnt = min(nv, top_k);
+                    L.kth = (L.cnt == top_k) ? L.s[top_k - 1] : -CUDART_INF_F;
+                } else {
+                    unsigned m = __ballot_sync(0xffffffffu, valid && (L.cnt < top_k || my_s > L.kth));
+                    while (m) {                                              // ascending lane == ascending edge position
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float sg = __shfl_sync(0xffffffffu, my_s, l);
+                        const int jg = __shfl_sync(0xffffffffu, jl, l);
+                        if (L.cnt < top_k || sg > L.kth) L.insert(sg, jg, top_k, lane);
                     }
                 }
             }
@@ -415,11 +441,12 @@ extern "C" int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx
     return check_launch("sng_rownorm_f32");
 }
 
-extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t c, int64_t ldh, const int32_t* rowptr, const int32_t* col,
-                                     int top_k, float thr, float* out, int64_t ldo, int32_t* sel_src, float* sel_w,
+extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t row_offset, int64_t c, int64_t ldh, const int32_t* rowptr,
+                                     const int32_t* col, int top_k, float thr, float* out, int64_t ldo, int32_t* sel_src, float* sel_w,
                                      int32_t* sel_cnt, void* stream) {
     if (int rc = check_rows("sng_edge_topk_agg_fwd", n, c, ldh)) return rc;
     SNG_REQUIRE(h && rowptr && col && out && ldo % 4 == 0 && ldo >= c, "sng_edge_topk_agg_fwd: null pointer or bad ldo");
+    SNG_REQUIRE(row_offset >= 0 && row_offset + n < (1ll << 31), "sng_edge_topk_agg_fwd: bad row_offset");
     SNG_REQUIRE(top_k <= SNG_MAX_TOPK, "sng_edge_topk_agg_fwd: top_k=%d > %d", top_k, SNG_MAX_TOPK);
     SNG_REQUIRE(top_k <= 0 || (sel_src && sel_w && sel_cnt), "sng_edge_topk_agg_fwd: selection outputs required when top_k>0");
     SNG_REQUIRE(top_k <= 0 || thr > -1.1f, "sng_edge_topk_agg_fwd: thr must be > -1.1 (knock-out sentinel of R models.py:153)");
@@ -428,8 +455,8 @@ extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t c, int64
     const size_t smem = (size_t)kWarpsPerBlock * 2 * (top_k > 0 ? top_k : 1) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     SNG_DISPATCH_G(c,
-        if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, (int)n, (int)c, ldh, rowptr, col, top_k, thr, out, ldo, sel_src, sel_w, sel_cnt);
-        else edge_topk_agg_fwd_kernel<G, true><<<grid, kThreads, smem, st>>>(h, (int)n, (int)c, ldh, rowptr, col, 0, thr, out, ldo, nullptr, nullptr, nullptr));
+        if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, (int)n, (int)row_offset, (int)c, ldh, rowptr, col, top_k, thr, out, ldo, sel_src, sel_w, sel_cnt);
+        else edge_topk_agg_fwd_kernel<G, true><<<grid, kThreads, smem, st>>>(h, (int)n, (int)row_offset, (int)c, ldh, rowptr, col, 0, thr, out, ldo, nullptr, nullptr, nullptr));
     return check_launch("sng_edge_topk_agg_fwd");
 }
 

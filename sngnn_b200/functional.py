@@ -47,7 +47,7 @@ class EdgeTopkAgg(torch.autograd.Function):
             sel_cnt = torch.empty(n, dtype=torch.int32, device=h.device)
         else:
             sel_src = sel_w = sel_cnt = None
-        _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h), n, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
+        _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h), n, 0, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
                                                 float(thr if thr is not None else 0.0), _C.ptr(out), c,
                                                 _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.stream()),
                  "sng_edge_topk_agg_fwd")
@@ -72,6 +72,23 @@ class EdgeTopkAgg(torch.autograd.Function):
                                            _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
                  "sng_edge_agg_bwd")
         return dh, None, None, None
+
+
+def edge_topk_agg_rows(h_all, shard, row_offset, top_k=None, thr=None):
+    """Forward-only K2 on a row shard: targets [row_offset, row_offset + shard.n) of `h_all` (all nodes, e.g. after an
+    all-gather), `shard` = PreparedGraph.row_slice(lo, hi).  Returns (out [shard.n, C], sel_src, sel_w, sel_cnt)."""
+    h_all = _check_h(h_all)
+    c = h_all.size(1)
+    n = shard.n
+    k = int(top_k) if top_k is not None else 0
+    out = torch.empty(n, c, dtype=h_all.dtype, device=h_all.device)
+    sel_src = torch.empty(n, max(k, 1), dtype=torch.int32, device=h_all.device) if k > 0 else None
+    sel_w = torch.empty(n, max(k, 1), dtype=torch.float32, device=h_all.device) if k > 0 else None
+    sel_cnt = torch.empty(n, dtype=torch.int32, device=h_all.device) if k > 0 else None
+    _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h_all), n, int(row_offset), c, c, _C.ptr(shard.rowptr_in), _C.ptr(shard.col_in), k,
+                                            float(thr if thr is not None else 0.0), _C.ptr(out), c,
+                                            _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.stream()), "sng_edge_topk_agg_fwd")
+    return out, sel_src, sel_w, sel_cnt
 
 
 def edge_topk_agg(h, graph, top_k=None, thr=None, return_selection=False):
