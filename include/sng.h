@@ -130,6 +130,18 @@ SNG_API int sng_sddmm_dot(const float* xhat, int64_t n, int64_t d, int64_t ld,
                   const int32_t* a, const int32_t* b, int64_t num_edges, float* s, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Toolbox helpers (Sim-GFA metrics that are not neighbour selection).
+ * sng_allpairs_dense_f32: out[n,n] = xhat xhat^T in FP32, for the *_small metrics that RETURN the N x N values
+ *   (R: SimGFAToolbox/dense.py:138-149).
+ * sng_class_sums_f64: sums[c, :] += sum_{i: y[i]==c} xhat[i, :] and counts[c] += |class c| (both zero-initialised,
+ *   FP64); y may be NULL when num_classes == 1.  Every "sum over all pairs" metric is <S_a, S_b>
+ *   (R: SimGFAToolbox/dense.py:9-30, 104-130, 167-179 materialise N x N blocks for the same sums).
+ */
+SNG_API int sng_allpairs_dense_f32(const float* xhat, int64_t n, int64_t d, int64_t ld, float* out, void* stream);
+SNG_API int sng_class_sums_f64(const float* xhat, const int32_t* y, int64_t n, int64_t d, int64_t ld, int num_classes,
+                       double* sums, double* counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K1  all-pairs similarity-kNN builder (tcgen05 / TMA / TMEM), never materialising the N x N matrix.
  *   xq_f16  [nq , ldh]  normalised query rows  (FP16, zero padded, ldh % 8 == 0, ldh >= 16*ceil(d/16), 16-byte aligned)
  *   xall_f16[n  , ldh]  normalised database rows

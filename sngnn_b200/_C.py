@@ -25,6 +25,8 @@ SIGNATURES = {
     "sng_pp_fuse_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sng_pp_beta_grad": (_I32, [_P, _P, _P, _I64, _P, _P]),
     "sng_sddmm_dot": (_I32, [_P, _I64, _I64, _I64, _P, _P, _I64, _P, _P]),
+    "sng_allpairs_dense_f32": (_I32, [_P, _I64, _I64, _I64, _P, _P]),
+    "sng_class_sums_f64": (_I32, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P]),
     "sng_simknn_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),
     "sng_simknn_build": (_I32, [_P, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, _I32, _F32, _I32,
                                 _P, _P, _P, _P, _P, _SZ, _P]),

@@ -523,3 +523,87 @@ extern "C" int sng_sddmm_dot(const float* xhat, int64_t n, int64_t d, int64_t ld
     sddmm_dot_kernel<<<grid_for_rows(num_edges, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(xhat, (int)d, ld, a, b, num_edges, s);
     return check_launch("sng_sddmm_dot");
 }
+
+// ------------------------------------------------------------------------------------------ toolbox helpers
+// Dense all-pairs cosine S = Xhat Xhat^T in FP32 for the toolbox's *_small variants, which RETURN the N x N values
+// (R: SimGFAToolbox/dense.py:138-149).  64x64 output tile per CTA, 16-wide K slices through shared memory, 4x4 micro-tile
+// per thread.  Only meant for matrices that are materialised anyway; the kNN builder never forms S.
+namespace sng {
+__global__ void __launch_bounds__(256) allpairs_dense_kernel(const float* __restrict__ xh, int n, int d, int64_t ld, float* __restrict__ out) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < d; k0 += 16) {
+        for (int t = threadIdx.x; t < 64 * 16; t += 256) {
+            const int r = t >> 4, k = t & 15;
+            As[k][r] = (i0 + r < n && k0 + k < d) ? __ldg(xh + (int64_t)(i0 + r) * ld + k0 + k) : 0.f;
+            Bs[k][r] = (j0 + r < n && k0 + k < d) ? __ldg(xh + (int64_t)(j0 + r) * ld + k0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = As[k][ty * 4 + u]; b[u] = Bs[k][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
+            if (i < n && j < n) out[(int64_t)i * n + j] = acc[u][v];
+        }
+}
+
+// Per-class sums of unit rows, S[c] = sum_{i: y_i = c} xhat_i  (FP64 accumulation): the closed form behind every
+// "sum of all pairwise similarities" metric, sum_{i in a, j in b} <xhat_i, xhat_j> = <S_a, S_b>
+// (R: SimGFAToolbox/dense.py:9-30, 104-130, 167-179 compute the same sums by materialising N x N blocks).
+__global__ void __launch_bounds__(256) class_sum_kernel(const float* __restrict__ xh, const int* __restrict__ y, int64_t n, int d, int64_t ld,
+                                                       int num_classes, double* __restrict__ sums, double* __restrict__ counts) {
+    // grid.x tiles rows, grid.y tiles columns (256 per block): each thread owns one column for a slab of rows
+    const int col = blockIdx.y * 256 + threadIdx.x;
+    const int64_t rows_per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per, r1 = min(n, r0 + rows_per);
+    const bool counter = counts && blockIdx.y == 0 && threadIdx.x == 0;
+    int cur = -1;
+    double acc = 0.0, run = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+        int c = y ? __ldg(y + r) : 0;
+        if (c < 0 || c >= num_classes) c = -1;                         // rows with an out-of-range label are ignored
+        if (c != cur) {
+            if (cur >= 0 && col < d) atomicAdd(sums + (int64_t)cur * d + col, acc);
+            if (cur >= 0 && counter) atomicAdd(counts + cur, run);
+            cur = c; acc = 0.0; run = 0.0;
+        }
+        if (c >= 0 && col < d) acc += (double)__ldg(xh + r * ld + col);
+        run += 1.0;
+    }
+    if (cur >= 0 && col < d) atomicAdd(sums + (int64_t)cur * d + col, acc);
+    if (cur >= 0 && counter) atomicAdd(counts + cur, run);
+}
+}  // namespace sng
+
+extern "C" int sng_allpairs_dense_f32(const float* xhat, int64_t n, int64_t d, int64_t ld, float* out, void* stream) {
+    SNG_REQUIRE(xhat && out && n > 0 && d > 0 && ld >= d && n < 65536 * 64ll, "sng_allpairs_dense_f32: bad arguments");
+    dim3 grid((unsigned)((n + 63) / 64), (unsigned)((n + 63) / 64));
+    sng::allpairs_dense_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xhat, (int)n, (int)d, ld, out);
+    return check_launch("sng_allpairs_dense_f32");
+}
+
+extern "C" int sng_class_sums_f64(const float* xhat, const int32_t* y, int64_t n, int64_t d, int64_t ld, int num_classes, double* sums,
+                                  double* counts, void* stream) {
+    SNG_REQUIRE(xhat && sums && n >= 0 && d > 0 && ld >= d && num_classes >= 1 && (y || num_classes == 1), "sng_class_sums_f64: bad arguments");
+    if (n == 0) return SNG_OK;
+    const int gx = (int)(n < 4096 ? (n + 63) / 64 : 2048);
+    dim3 grid((unsigned)(gx > 0 ? gx : 1), (unsigned)((d + 255) / 256));
+    sng::class_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xhat, y, n, (int)d, ld, num_classes, sums, counts);
+    return check_launch("sng_class_sums_f64");
+}

@@ -1,0 +1,71 @@
+"""GPU toolbox (sngnn_b200.toolbox) against the golden outputs of the reference's own dense.py / sparse.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, rtol=1e-4, atol=1e-5):
+    torch.testing.assert_close(torch.as_tensor(a).float().cpu(), torch.as_tensor(b).float().cpu(), rtol=rtol, atol=atol)
+
+
+def test_dense_metrics_match_reference_golden():
+    import sngnn_b200.toolbox as T
+    g = load_golden("toolbox.pt")
+    x, ei, y = g["x"], g["edge_index"].long(), g["y"]
+    _close(T.node_similarity_dense_large_parted(g["x1200"])[1], g["node_large_parted"], rtol=1e-3)
+    _close(T.class_similarity_dense_large(g["x1200"], g["y1200"]), g["class_large_1200"])
+    _close(T.class_similarity_dense_large(x, y), g["class_large"])
+    for name, fn, args in (("linked_large", T.linked_node_similarity_dense_large, (x, ei)),
+                           ("nbr_large", T.neighborhood_similarity_dense_large, (x, ei)),
+                           ("node_small", T.node_similarity_dense_small, (x,)),
+                           ("linked_small", T.linked_node_similarity_dense_small, (x, ei)),
+                           ("nbr_small", T.neighborhood_similarity_dense_small, (x, ei)),
+                           ("class_small", T.class_similarity_dense_small, (x, y))):
+        got, ref = fn(*args), g[name]
+        assert got[0].shape == ref[0].shape, name
+        _close(got[0], ref[0])
+        _close(got[1], ref[1])
+    from sngnn_b200.toolbox.dense import edge_similarity_weight
+    _close(edge_similarity_weight(g["esw_x"], ei), g["esw"])
+    # device inputs stay on the device
+    out = T.linked_node_similarity_dense_small(x.cuda(), ei.cuda())
+    assert out[0].is_cuda
+
+
+def test_sparse_metrics_match_reference_golden():
+    import sngnn_b200.toolbox as T
+    g = load_golden("toolbox.pt")
+    x, ei, y = g["x"], g["edge_index"].long(), g["y"]
+    adj = T.edge_index_to_sparse_csc_tensor(x, ei)
+    for name, fn, args in (("sp_node", T.node_similarity_sparse, (adj,)), ("sp_linked", T.linked_node_similarity_sparse, (adj, ei)),
+                           ("sp_nbr", T.neighborhood_similarity_sparse, (adj, ei))):
+        got, ref = fn(*args), g[name]
+        assert got[0].shape == ref[0].shape, name
+        _close(got[0], ref[0])
+        _close(got[1], ref[1])
+    _close(T.class_similarity_sparse(adj, y), g["sp_class"])
+    assert sorted(T.__all__) == sorted(
+        ['cosine_similarity_sparse', 'node_similarity_sparse', 'linked_node_similarity_sparse', 'class_similarity_sparse',
+         'plot_class_similarity', 'plot_similarity_distribution', 'edge_index_to_sparse_csc_tensor', 'node_similarity_dense_small',
+         'node_similarity_dense_large_parted', 'class_similarity_dense_small', 'class_similarity_dense_large',
+         'linked_node_similarity_dense_large', 'linked_node_similarity_dense_small', 'neighborhood_similarity_dense_large',
+         'neighborhood_similarity_dense_small'])
+
+
+def test_class_sums_large_shape():
+    """Closed-form all-pairs sum at a size where the N x N route is impossible, against a float64 torch reduction."""
+    import sngnn_b200.toolbox.dense as D
+    torch.manual_seed(0)
+    n, d, k = 300000, 65, 7
+    x = torch.randn(n, d, device="cuda")
+    y = torch.randint(0, k, (n,), device="cuda")
+    got = D.class_similarity_dense_large(x, y).double()
+    xh = torch.nn.functional.normalize(x.double(), dim=-1)
+    s = torch.zeros(k, d, dtype=torch.float64, device="cuda").index_add_(0, y, xh)
+    cnt = torch.bincount(y, minlength=k).double()
+    ref = (s @ s.t()) / (cnt[:, None] * cnt[None, :])
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-9)
