@@ -101,6 +101,7 @@ def run_reference(args):
     if rank != 0:
         return
     from sngnn_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)       # torchrun pins OMP_NUM_THREADS=1; the reference arm uses every host core
     N, Fd, E, C = synth.SHAPES[args.workload]
     x = synth.make_features(N, Fd, args.features, seed=0, zscore=(args.workload == "pokec"))
     rows = min(args.cpu_rows // 4 if args.cpu_rows >= 2048 else args.cpu_rows, N)      # bounded sample per step
@@ -324,7 +325,8 @@ def run_ours(args):
         parity = compare_lists(idx[:rows], cnt[:rows], iref, cref, lambda r, j: (n64[r] * n64[j]).sum(-1), thr)
         parity["rows_checked"] = rows
         parity["fallback_rows"] = n_fallback
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
             cpu_rows = min(args.cpu_rows, N)
             cpu_knn_sample(xc, 128, k, thr)
             tc = cpu_knn_sample(xc, cpu_rows, k, thr)
