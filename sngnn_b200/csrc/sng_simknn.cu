@@ -141,6 +141,7 @@ struct Stage1Params {
     int nsplit, tiles_total;      // 256-column tiles are split across gridDim.y cluster columns
     float thr_lo;                 // approximate scores <= thr_lo can never be selected
     int remove_self;
+    int debug;                    // profiling aid (SNG_KNN_DEBUG): 1 = skip the max tree / inserts, 3 = also skip the TMEM loads
     float* cand_val;              // [nq, nsplit*EW, cand]
     int* cand_idx;                // [nq, nsplit*EW, cand]   (-1 = empty)
     float* cand_min;              // [nq, nsplit*EW]  worst kept approx score if the list filled up, else -inf
@@ -281,6 +282,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // Pruning thresholds are heuristics: ANY threshold is safe because every thread reports the largest threshold it
         // ever pruned with (cand_min) and stage 2 only accepts a row whose k-th exact score clears all of them.
         auto process = [&](const uint32_t (&v)[32], int col0) {
+            if (p.debug) { if (__uint_as_float(v[0] ^ v[31]) == 12345.678f) thr_cur = 0.f; return; }
             float m[11];
 #pragma unroll
             for (int i = 0; i < 10; ++i) m[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
@@ -311,9 +313,11 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const int col0 = t * BN + slice * CPT;
             if (CPT == 64) {
                 // both loads in flight at once; the accumulator stage goes back to the MMA warp before any processing
-                tmem_ld32(taddr, va);
-                tmem_ld32(taddr + 32, vb);
-                tmem_ld_wait();
+                if (!(p.debug & 2)) {
+                    tmem_ld32(taddr, va);
+                    tmem_ld32(taddr + 32, vb);
+                    tmem_ld_wait();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
@@ -707,6 +711,7 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
     p.nq = (int)nq; p.n = (int)n; p.q_offset = (int)q_offset;
     p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = pl.cand;
     p.nsplit = pl.nsplit; p.tiles_total = pl.tiles; p.thr_lo = thr_lo; p.remove_self = remove_self;
+    p.debug = env_int("SNG_KNN_DEBUG", 1, 3);
     p.cand_val = cand_val; p.cand_idx = cand_idx; p.cand_min = cand_min;
     dim3 grid((unsigned)(2 * ((nq + 2 * BM - 1) / (2 * BM))), (unsigned)pl.nsplit);      // x: CTA pairs (cluster of 2), y: column splits
     cudaError_t e = pl.ew == 4 ? launch_ew<4>(grid, pl.smem, st, mq, mdb, p)

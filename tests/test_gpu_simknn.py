@@ -25,7 +25,7 @@ def _score64(x):
 
 
 @pytest.mark.parametrize("n,d,ew,ns", [(1000, 64, 1, 1), (1000, 64, 2, 1), (3000, 65, 4, 3), (2500, 128, 4, 2), (1500, 269, 0, 0),
-                                       (1300, 512, 0, 0), (700, 16, 2, 1), (900, 40, 0, 0), (5000, 65, 0, 0), (257, 65, 4, 1)])
+                                       (1300, 512, 0, 0), (700, 16, 2, 1), (900, 40, 0, 0), (5000, 65, 0, 0), (257, 65, 4, 1), (900, 24, 0, 0), (800, 90, 4, 1), (600, 200, 0, 0)])
 def test_stage1_candidates_contain_true_topk(n, d, ew, ns):
     """Tensor-core stage: every true top-10 neighbour must be among the FP16-scored candidates, and the kept
     FP16 scores must be within the proven error bound of the exact cosine."""
