@@ -72,7 +72,7 @@ struct TopList {
 };
 
 template <int G, bool SELECT_ALL>
-__global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
+__global__ void __launch_bounds__(kThreads, 6) edge_topk_agg_fwd_kernel(
     const float* __restrict__ h, int n, int row_offset, int c, int64_t ldh, const int* __restrict__ rowptr, const int* __restrict__ col,
     int top_k, float thr, float* __restrict__ out, int64_t ldo,
     int* __restrict__ sel_src, float* __restrict__ sel_w, int* __restrict__ sel_cnt) {
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
                     if (st + u * EPW >= nchunk) break;                       // warp-uniform
                     const float d = group_sum<G>(dot4(ni, v[u]));
                     const float ss = group_sum<G>(dot4(v[u], v[u]));
-                    const float sc = d * inv_norm_of(ss);
+                    const float sc = d * inv_norm_of(ss) + 0.0f;            // + 0: -0 becomes +0, so equal scores compare equal as integers too
                     if (SELECT_ALL) {
                         if (j[u] >= 0) fma4(acc, sc, v[u]);
                     } else {
@@ -125,20 +125,20 @@ __global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
             if (!SELECT_ALL) {
                 const bool valid = jl >= 0 && my_s >= thr;
                 if (L.cnt == 0) {
-                    // empty list (normally the row's first and only chunk): rank all candidates of the chunk at once
-                    unsigned m = __ballot_sync(0xffffffffu, valid);
-                    const int nv = __popc(m);
-                    int rank = 0;
-                    while (m) {
-                        const int l = __ffs(m) - 1;
-                        m &= m - 1;
-                        const float os = __shfl_sync(0xffffffffu, my_s, l);
-                        rank += (os > my_s || (os == my_s && l < lane)) ? 1 : 0;
+                    // empty list (normally the row's first and only chunk): top_k rounds of a one-instruction warp max over an
+                    // order-preserving integer image of the score; the lowest lane among the maxima wins = lowest edge position
+                    const unsigned u = __float_as_uint(my_s);
+                    unsigned key = valid ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : 0u;     // 0 = not a candidate
+                    int t = 0;
+                    for (; t < top_k; ++t) {
+                        const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+                        if (mx == 0u) break;
+                        const int w = __ffs(__ballot_sync(0xffffffffu, key == mx)) - 1;
+                        if (lane == w) { L.s[t] = my_s; L.j[t] = jl; key = 0u; }
                     }
-                    if (valid && rank < top_k) { L.s[rank] = my_s; L.j[rank] = jl; }
                     __syncwarp();
-                    L.cnt = min(nv, top_k);
-                    L.kth = (L.cnt == top_k) ? L.s[top_k - 1] : -CUDART_INF_F;
+                    L.cnt = t;
+                    L.kth = (t == top_k) ? L.s[top_k - 1] : -CUDART_INF_F;
                 } else {
                     unsigned m = __ballot_sync(0xffffffffu, valid && (L.cnt < top_k || my_s > L.kth));
                     while (m) {                                              // ascending lane == ascending edge position
