@@ -294,10 +294,11 @@ def run_ours(args):
         k2_ms = timed(k2_fwd, 10, 3)
         _, ss, sw, sc = sel["o"]
         dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
+        _, _, inv_norm = SF.rownorm(h, want_f32=False, want_inv=True)
 
         def k2_bwd():
             dval.zero_(); dnrm.zero_()
-            _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(gg), N, hid, hid, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss),
+            _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(gg), N, hid, hid, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss),
                                                _C.ptr(sw), _C.ptr(sc), _C.ptr(g.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh),
                                                _C.stream()), "sng_edge_agg_bwd")
 

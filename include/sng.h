@@ -70,22 +70,24 @@ SNG_API int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx,
  *   out[i]= (1/max(deg_i,1)) * sum_{e in S_i} s_e * h[src_e]
  * Saved for backward (top_k > 0): sel_src [n,top_k] (source ids, rank order, -1 padded),
  * sel_w [n,top_k] (s_e), sel_cnt [n].  With top_k <= 0 those three may be NULL.
- * Row sharding: the call covers target rows [row_offset, row_offset + n) of `h` (which holds ALL nodes, because
- * sources are arbitrary); rowptr / out / sel_* are local to the shard, `col` holds global source ids.
+ * Row sharding: the call covers target rows [row_offset, row_offset + n) of `h`, which holds ALL n_total nodes
+ * (sources are arbitrary); rowptr / out / sel_* are local to the shard, `col` holds global source ids.
+ * inv_norm [n_total] is filled with 1/max(||h_i||, 1e-12) (a pre-pass of this call) and is an input of the backward.
  */
-SNG_API int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
+SNG_API int sng_edge_topk_agg_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
                           const int32_t* rowptr, const int32_t* col,
                           int top_k, float thr,
                           float* out, int64_t ldo,
                           int32_t* sel_src, float* sel_w, int32_t* sel_cnt,
-                          void* stream);
+                          float* inv_norm, void* stream);
 
 /* K2b backward of the above w.r.t. h (closed form of SURVEY.md §3.4).
  * Pass 1 scatters into the two zero-initialised accumulators dval, dnrm [n, c] (float atomics);
  * pass 2 writes dh = dval + (dnrm - n (n . dnrm)) / r.   `g` = dL/dout [n,c].
  * top_k > 0: uses the saved selection lists (inv_denom[i] = 1/max(deg_i,1));
- * top_k <= 0: iterates the CSR (every edge selected). */
-SNG_API int sng_edge_agg_bwd(const float* h, const float* g, int64_t n, int64_t c, int64_t ld,
+ * top_k <= 0: iterates the CSR (every edge selected).  inv_norm [n] = the array the forward filled
+ * (or sng_rownorm_f32's inv_norm output for selection lists that did not come from the edge forward). */
+SNG_API int sng_edge_agg_bwd(const float* h, const float* inv_norm, const float* g, int64_t n, int64_t c, int64_t ld,
                      const int32_t* rowptr, const int32_t* col,
                      int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_cnt,
                      const float* inv_denom,

@@ -16,6 +16,8 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
 template <int G> struct Unroll { static constexpr int value = (G >= 4) ? 4 : G; };
+// forward scoring: all loads of a 32-edge chunk in flight at once while that fits in registers (G <= 8)
+template <int G> struct UnrollFwd { static constexpr int value = (G <= 8) ? G : 8; };
 
 // ------------------------------------------------------------------------------------------ K0
 __global__ void __launch_bounds__(kThreads) rownorm_kernel(const float* __restrict__ x, int64_t n, int d, int64_t ldx,
@@ -71,64 +73,83 @@ struct TopList {
     }
 };
 
+// inv_r[i] = 1 / max(||h_i||, 1e-12): one warp per row.  The edge kernels gather this scalar per edge (the array is
+// L2 resident) instead of recomputing every source row's norm from its gathered features.
+__global__ void __launch_bounds__(kThreads) row_inv_norm_kernel(const float* __restrict__ h, int64_t n, int c, int64_t ld, float* __restrict__ inv) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * kWarpsPerBlock) {
+        float ss = 0.f;
+        for (int k = lane * 4; k < c; k += 128) { const float4 v = ldg4(h + row * ld + k); ss += dot4(v, v); }
+        ss = group_sum<32>(ss);
+        if (lane == 0) inv[row] = inv_norm_of(ss);
+    }
+}
+
+// K2 forward.  One warp per target row; lane e of the warp owns in-edge e of the current 32-edge chunk (source id,
+// source 1/norm, score); a group of G lanes fetches one source row per step with one 128-bit load per lane.
+// Loads are never predicated: missing edges are redirected to the target row itself and masked afterwards.
 template <int G, bool SELECT_ALL>
-__global__ void __launch_bounds__(kThreads, 6) edge_topk_agg_fwd_kernel(
-    const float* __restrict__ h, int n, int row_offset, int c, int64_t ldh, const int* __restrict__ rowptr, const int* __restrict__ col,
-    int top_k, float thr, float* __restrict__ out, int64_t ldo,
+__global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
+    const float* __restrict__ h, const float* __restrict__ inv_r, int n, int row_offset, int c, int ldh, const int* __restrict__ rowptr,
+    const int* __restrict__ col, int top_k, float thr, float* __restrict__ out, int ldo,
     int* __restrict__ sel_src, float* __restrict__ sel_w, int* __restrict__ sel_cnt) {
     constexpr int EPW = 32 / G;                 // edges per warp step
-    constexpr int U = Unroll<G>::value;         // steps whose loads are issued together
+    constexpr int U = UnrollFwd<G>::value;      // steps whose loads are issued together
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = lane % G, grp = lane / G, c4 = q * 4;
-    const bool ch_ok = c4 < c;
+    const int q = lane % G, grp = lane / G;
+    const bool ch_ok = q * 4 < c;
+    const int c4 = ch_ok ? q * 4 : 0;           // lanes beyond the channel count read channel 0 and contribute with weight 0
+    const float* hb = h + c4;
     TopList L;
     L.s = smem + (size_t)warp * 2 * max(top_k, 1);
     L.j = reinterpret_cast<int*>(L.s + max(top_k, 1));
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int row = blockIdx.x * kWarpsPerBlock + warp; row < n; row += gridDim.x * kWarpsPerBlock) {
+        const int grow = row_offset + row;
         const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-        const float4 hi = ch_ok ? ldg4(h + (int64_t)(row_offset + row) * ldh + c4) : z4;     // target row's own features
-        const float4 ni = scale4(hi, inv_norm_of(group_sum<G>(dot4(hi, hi))));
+        float4 ni = scale4(ldg4(hb + (int64_t)grow * ldh), __ldg(inv_r + grow));     // target row, normalised
+        if (!ch_ok) ni = z4;
         float4 acc = z4;
         L.cnt = 0; L.kth = -CUDART_INF_F;
 
         for (int base = beg; base < end; base += 32) {
             const int nchunk = min(32, end - base);
-            const int jl = lane < nchunk ? __ldg(col + base + lane) : -1;
-            float my_s = -CUDART_INF_F;                          // score of edge base+lane (lane == position inside the chunk)
+            const bool has = lane < nchunk;
+            const int jl = has ? __ldg(col + base + lane) : grow;
+            const float irl = __ldg(inv_r + jl);
+            float my_d = 0.f;                                    // <n_i, h_j> of edge base+lane
             for (int st = 0; st < nchunk; st += EPW * U) {
-                float4 v[U]; int j[U];
+                float4 v[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int e = st + u * EPW + grp;
-                    j[u] = __shfl_sync(0xffffffffu, jl, e & 31);
-                    if (e >= nchunk) j[u] = -1;
-                    v[u] = (j[u] >= 0 && ch_ok) ? ldg4(h + (int64_t)j[u] * ldh + c4) : z4;
+                    const int j = __shfl_sync(0xffffffffu, jl, (st + u * EPW + grp) & 31);
+                    v[u] = ldg4(hb + (int64_t)j * ldh);
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (st + u * EPW >= nchunk) break;                       // warp-uniform
                     const float d = group_sum<G>(dot4(ni, v[u]));
-                    const float ss = group_sum<G>(dot4(v[u], v[u]));
-                    const float sc = d * inv_norm_of(ss) + 0.0f;            // + 0: -0 becomes +0, so equal scores compare equal as integers too
                     if (SELECT_ALL) {
-                        if (j[u] >= 0) fma4(acc, sc, v[u]);
+                        // weight of this step's edge = its score, available in the owning lane only after the assembly below;
+                        // recompute it here from the edge's own 1/norm instead
+                        const int e = st + u * EPW + grp;
+                        const float w = __shfl_sync(0xffffffffu, irl, e & 31);
+                        if (e < nchunk && ch_ok) fma4(acc, d * w, v[u]);
                     } else {
-                        // hand the score of (step, group) to the lane that owns that edge position
-                        const float t = __shfl_sync(0xffffffffu, sc, (lane % EPW) * G);
-                        if (lane / EPW == st / EPW + u) my_s = t;
+                        const float t = __shfl_sync(0xffffffffu, d, (lane % EPW) * G);      // hand (step, group) to the edge's lane
+                        if (lane / EPW == st / EPW + u) my_d = t;
                     }
                 }
             }
             if (!SELECT_ALL) {
-                const bool valid = jl >= 0 && my_s >= thr;
+                const float my_s = my_d * irl + 0.0f;            // + 0: -0 becomes +0, so equal scores are equal as integers too
+                const bool valid = has && my_s >= thr;
                 if (L.cnt == 0) {
-                    // empty list (normally the row's first and only chunk): top_k rounds of a one-instruction warp max over an
-                    // order-preserving integer image of the score; the lowest lane among the maxima wins = lowest edge position
-                    const unsigned u = __float_as_uint(my_s);
-                    unsigned key = valid ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : 0u;     // 0 = not a candidate
+                    // empty list (normally the row's only chunk): top_k rounds of a one-instruction warp max over an
+                    // order-preserving integer image of the score; the lowest lane among the maxima = lowest edge position
+                    const unsigned ub = __float_as_uint(my_s);
+                    unsigned key = valid ? ((ub & 0x80000000u) ? ~ub : (ub | 0x80000000u)) : 0u;     // 0 = not a candidate
                     int t = 0;
                     for (; t < top_k; ++t) {
                         const unsigned mx = __reduce_max_sync(0xffffffffu, key);
@@ -152,22 +173,28 @@ __global__ void __launch_bounds__(kThreads, 6) edge_topk_agg_fwd_kernel(
             }
         }
         if (!SELECT_ALL) {
-            for (int st = 0; st < L.cnt; st += EPW) {
-                const int t = st + grp;
-                if (t < L.cnt && ch_ok) fma4(acc, L.s[t], ldg4(h + (int64_t)L.j[t] * ldh + c4));
+            const int cnt = L.cnt;
+            for (int st = 0; st < cnt; st += EPW) {
+                const int t = min(st + grp, cnt - 1);                        // clamp: the duplicate gets weight 0
+                const float w = st + grp < cnt ? L.s[t] : 0.f;
+                fma4(acc, w, ldg4(hb + (int64_t)L.j[t] * ldh));
             }
-            for (int t = lane; t < top_k; t += 32) {
-                sel_src[(int64_t)row * top_k + t] = t < L.cnt ? L.j[t] : -1;
-                sel_w[(int64_t)row * top_k + t] = t < L.cnt ? L.s[t] : 0.f;
+            if (lane < top_k) {
+                sel_src[(int64_t)row * top_k + lane] = lane < cnt ? L.j[lane] : -1;
+                sel_w[(int64_t)row * top_k + lane] = lane < cnt ? L.s[lane] : 0.f;
             }
-            if (lane == 0) sel_cnt[row] = L.cnt;
+            if (lane + 32 < top_k) {
+                sel_src[(int64_t)row * top_k + lane + 32] = lane + 32 < cnt ? L.j[lane + 32] : -1;
+                sel_w[(int64_t)row * top_k + lane + 32] = lane + 32 < cnt ? L.s[lane + 32] : 0.f;
+            }
+            if (lane == 0) sel_cnt[row] = cnt;
             __syncwarp();
         }
         acc.x = cross_group_sum<G>(acc.x); acc.y = cross_group_sum<G>(acc.y);
         acc.z = cross_group_sum<G>(acc.z); acc.w = cross_group_sum<G>(acc.w);
         if (grp == 0 && ch_ok) {
             const float invd = 1.0f / (float)max(end - beg, 1);
-            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + c4) = scale4(acc, invd);
+            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + q * 4) = scale4(acc, invd);
         }
     }
 }
@@ -202,7 +229,7 @@ __global__ void __launch_bounds__(kThreads) list_agg_fwd_kernel(
 // ------------------------------------------------------------------------------------------ K2b backward
 template <int G, bool SELECT_ALL>
 __global__ void __launch_bounds__(kThreads) edge_agg_bwd_scatter_kernel(
-    const float* __restrict__ h, const float* __restrict__ g, int n, int c, int64_t ld, const int* __restrict__ rowptr,
+    const float* __restrict__ h, const float* __restrict__ inv_r, const float* __restrict__ g, int n, int c, int64_t ld, const int* __restrict__ rowptr,
     const int* __restrict__ col, int top_k, const int* __restrict__ sel_src, const float* __restrict__ sel_w,
     const int* __restrict__ sel_cnt, const float* __restrict__ inv_denom, float* __restrict__ dval, float* __restrict__ dnrm) {
     constexpr int EPW = 32 / G;
@@ -225,7 +252,7 @@ __global__ void __launch_bounds__(kThreads) edge_agg_bwd_scatter_kernel(
         }
         if (cnt == 0) continue;
         const float4 hi = ch_ok ? ldg4(h + (int64_t)row * ld + c4) : z4;
-        const float4 ni = scale4(hi, inv_norm_of(group_sum<G>(dot4(hi, hi))));
+        const float4 ni = scale4(hi, __ldg(inv_r + row));
         const float4 gs = ch_ok ? scale4(ldg4(g + (int64_t)row * ld + c4), invd) : z4;     // g_i / deg_i
         float4 dni = z4;
         for (int st = 0; st < cnt; st += EPW * U) {
@@ -243,8 +270,8 @@ __global__ void __launch_bounds__(kThreads) edge_agg_bwd_scatter_kernel(
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (st + u * EPW >= cnt) break;
-                const float inv_rj = inv_norm_of(group_sum<G>(dot4(v[u], v[u])));
-                const float s = SELECT_ALL ? group_sum<G>(dot4(ni, v[u])) * inv_rj : w[u];
+                const float inv_rj = j[u] >= 0 ? __ldg(inv_r + j[u]) : 0.f;
+                const float s = SELECT_ALL ? group_sum<G>(dot4(ni, v[u])) * inv_rj + 0.0f : w[u];
                 const float ds = group_sum<G>(dot4(v[u], gs));                 // dL/ds_e = (h_j . g_i)/deg_i
                 if (j[u] >= 0 && ch_ok) {
                     atomicAdd(reinterpret_cast<float4*>(dval + (int64_t)j[u] * ld + c4), scale4(gs, s));
@@ -261,7 +288,7 @@ __global__ void __launch_bounds__(kThreads) edge_agg_bwd_scatter_kernel(
 
 // pass 2: dh = dval + (dnrm - n (n . dnrm)) / r      (one lane-group per row)
 template <int G>
-__global__ void __launch_bounds__(kThreads) norm_bwd_finish_kernel(const float* __restrict__ h, int n, int c, int64_t ld,
+__global__ void __launch_bounds__(kThreads) norm_bwd_finish_kernel(const float* __restrict__ h, const float* __restrict__ inv_rv, int n, int c, int64_t ld,
                                                                   const float* __restrict__ dval, const float* __restrict__ dnrm,
                                                                   float* __restrict__ dh) {
     constexpr int RPW = 32 / G;
@@ -273,7 +300,7 @@ __global__ void __launch_bounds__(kThreads) norm_bwd_finish_kernel(const float* 
         const int row = r0 + grp;
         const bool ok = row < n && ch_ok;
         const float4 hi = ok ? ldg4(h + (int64_t)row * ld + c4) : z4;
-        const float inv_r = inv_norm_of(group_sum<G>(dot4(hi, hi)));
+        const float inv_r = row < n ? __ldg(inv_rv + row) : 0.f;
         const float4 ni = scale4(hi, inv_r);
         const float4 dn = ok ? ldg4(dnrm + (int64_t)row * ld + c4) : z4;
         const float proj = group_sum<G>(dot4(ni, dn));
@@ -441,12 +468,14 @@ extern "C" int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx
     return check_launch("sng_rownorm_f32");
 }
 
-extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t row_offset, int64_t c, int64_t ldh, const int32_t* rowptr,
-                                     const int32_t* col, int top_k, float thr, float* out, int64_t ldo, int32_t* sel_src, float* sel_w,
-                                     int32_t* sel_cnt, void* stream) {
+extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
+                                     const int32_t* rowptr, const int32_t* col, int top_k, float thr, float* out, int64_t ldo,
+                                     int32_t* sel_src, float* sel_w, int32_t* sel_cnt, float* inv_norm, void* stream) {
     if (int rc = check_rows("sng_edge_topk_agg_fwd", n, c, ldh)) return rc;
     SNG_REQUIRE(h && rowptr && col && out && ldo % 4 == 0 && ldo >= c, "sng_edge_topk_agg_fwd: null pointer or bad ldo");
-    SNG_REQUIRE(row_offset >= 0 && row_offset + n < (1ll << 31), "sng_edge_topk_agg_fwd: bad row_offset");
+    SNG_REQUIRE(row_offset >= 0 && row_offset + n <= n_total && n_total < (1ll << 31) && ldh < (1ll << 31) && ldo < (1ll << 31),
+                "sng_edge_topk_agg_fwd: bad row_offset / n_total");
+    SNG_REQUIRE(inv_norm, "sng_edge_topk_agg_fwd: inv_norm [n_total] is required");
     SNG_REQUIRE(top_k <= SNG_MAX_TOPK, "sng_edge_topk_agg_fwd: top_k=%d > %d", top_k, SNG_MAX_TOPK);
     SNG_REQUIRE(top_k <= 0 || (sel_src && sel_w && sel_cnt), "sng_edge_topk_agg_fwd: selection outputs required when top_k>0");
     SNG_REQUIRE(top_k <= 0 || thr > -1.1f, "sng_edge_topk_agg_fwd: thr must be > -1.1 (knock-out sentinel of R models.py:153)");
@@ -454,9 +483,10 @@ extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n, int64_t row_offs
     const int grid = grid_for_rows(n, kWarpsPerBlock);
     const size_t smem = (size_t)kWarpsPerBlock * 2 * (top_k > 0 ? top_k : 1) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    row_inv_norm_kernel<<<grid_for_rows(n_total, kWarpsPerBlock), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm);
     SNG_DISPATCH_G(c,
-        if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, (int)n, (int)row_offset, (int)c, ldh, rowptr, col, top_k, thr, out, ldo, sel_src, sel_w, sel_cnt);
-        else edge_topk_agg_fwd_kernel<G, true><<<grid, kThreads, smem, st>>>(h, (int)n, (int)row_offset, (int)c, ldh, rowptr, col, 0, thr, out, ldo, nullptr, nullptr, nullptr));
+        if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
+        else edge_topk_agg_fwd_kernel<G, true><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, 0, thr, out, (int)ldo, nullptr, nullptr, nullptr));
     return check_launch("sng_edge_topk_agg_fwd");
 }
 
@@ -471,19 +501,19 @@ extern "C" int sng_list_agg_fwd(const float* h, int64_t n_rows, int64_t c, int64
     return check_launch("sng_list_agg_fwd");
 }
 
-extern "C" int sng_edge_agg_bwd(const float* h, const float* g, int64_t n, int64_t c, int64_t ld, const int32_t* rowptr,
+extern "C" int sng_edge_agg_bwd(const float* h, const float* inv_norm, const float* g, int64_t n, int64_t c, int64_t ld, const int32_t* rowptr,
                                 const int32_t* col, int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_cnt,
                                 const float* inv_denom, float* dval, float* dnrm, float* dh, void* stream) {
     if (int rc = check_rows("sng_edge_agg_bwd", n, c, ld)) return rc;
-    SNG_REQUIRE(h && g && dval && dnrm && dh, "sng_edge_agg_bwd: null pointer");
+    SNG_REQUIRE(h && inv_norm && g && dval && dnrm && dh, "sng_edge_agg_bwd: null pointer");
     SNG_REQUIRE(top_k > 0 ? (sel_src && sel_w && sel_cnt && inv_denom) : (rowptr && col), "sng_edge_agg_bwd: missing selection list / CSR");
     if (n == 0) return SNG_OK;
     const int grid = grid_for_rows(n, kWarpsPerBlock);
     cudaStream_t st = (cudaStream_t)stream;
     SNG_DISPATCH_G(c,
-        if (top_k > 0) edge_agg_bwd_scatter_kernel<G, false><<<grid, kThreads, 0, st>>>(h, g, (int)n, (int)c, ld, rowptr, col, top_k, sel_src, sel_w, sel_cnt, inv_denom, dval, dnrm);
-        else edge_agg_bwd_scatter_kernel<G, true><<<grid, kThreads, 0, st>>>(h, g, (int)n, (int)c, ld, rowptr, col, 0, nullptr, nullptr, nullptr, nullptr, dval, dnrm);
-        norm_bwd_finish_kernel<G><<<grid_for_rows(n, kWarpsPerBlock * (32 / G)), kThreads, 0, st>>>(h, (int)n, (int)c, ld, dval, dnrm, dh));
+        if (top_k > 0) edge_agg_bwd_scatter_kernel<G, false><<<grid, kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)c, ld, rowptr, col, top_k, sel_src, sel_w, sel_cnt, inv_denom, dval, dnrm);
+        else edge_agg_bwd_scatter_kernel<G, true><<<grid, kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)c, ld, rowptr, col, 0, nullptr, nullptr, nullptr, nullptr, dval, dnrm);
+        norm_bwd_finish_kernel<G><<<grid_for_rows(n, kWarpsPerBlock * (32 / G)), kThreads, 0, st>>>(h, inv_norm, (int)n, (int)c, ld, dval, dnrm, dh));
     return check_launch("sng_edge_agg_bwd");
 }
 

@@ -47,12 +47,13 @@ class EdgeTopkAgg(torch.autograd.Function):
             sel_cnt = torch.empty(n, dtype=torch.int32, device=h.device)
         else:
             sel_src = sel_w = sel_cnt = None
-        _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h), n, 0, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
+        inv_norm = torch.empty(n, dtype=torch.float32, device=h.device)
+        _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h), n, n, 0, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
                                                 float(thr if thr is not None else 0.0), _C.ptr(out), c,
-                                                _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.stream()),
+                                                _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(inv_norm), _C.stream()),
                  "sng_edge_topk_agg_fwd")
         ctx.graph, ctx.k = graph, k
-        ctx.save_for_backward(h, sel_src, sel_w, sel_cnt)
+        ctx.save_for_backward(h, sel_src, sel_w, sel_cnt, inv_norm)
         ctx.mark_non_differentiable(*[t for t in (sel_src, sel_w, sel_cnt) if t is not None])
         if k > 0:
             return out, sel_src, sel_w, sel_cnt
@@ -60,14 +61,14 @@ class EdgeTopkAgg(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, *_):
-        h, sel_src, sel_w, sel_cnt = ctx.saved_tensors
+        h, sel_src, sel_w, sel_cnt, inv_norm = ctx.saved_tensors
         graph, k = ctx.graph, ctx.k
         n, c = h.shape
         g = g.contiguous()
         dval = torch.zeros_like(h)
         dnrm = torch.zeros_like(h)
         dh = torch.empty_like(h)
-        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(g), n, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
+        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
                                            _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(graph.inv_deg),
                                            _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
                  "sng_edge_agg_bwd")
@@ -85,9 +86,11 @@ def edge_topk_agg_rows(h_all, shard, row_offset, top_k=None, thr=None):
     sel_src = torch.empty(n, max(k, 1), dtype=torch.int32, device=h_all.device) if k > 0 else None
     sel_w = torch.empty(n, max(k, 1), dtype=torch.float32, device=h_all.device) if k > 0 else None
     sel_cnt = torch.empty(n, dtype=torch.int32, device=h_all.device) if k > 0 else None
-    _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h_all), n, int(row_offset), c, c, _C.ptr(shard.rowptr_in), _C.ptr(shard.col_in), k,
-                                            float(thr if thr is not None else 0.0), _C.ptr(out), c,
-                                            _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.stream()), "sng_edge_topk_agg_fwd")
+    inv_norm = torch.empty(h_all.size(0), dtype=torch.float32, device=h_all.device)
+    _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h_all), h_all.size(0), n, int(row_offset), c, c, _C.ptr(shard.rowptr_in),
+                                            _C.ptr(shard.col_in), k, float(thr if thr is not None else 0.0), _C.ptr(out), c,
+                                            _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(inv_norm), _C.stream()),
+             "sng_edge_topk_agg_fwd")
     return out, sel_src, sel_w, sel_cnt
 
 
@@ -119,7 +122,8 @@ class ListAgg(torch.autograd.Function):
             raise RuntimeError("backward through a row-sharded list aggregation is not supported")
         g = g.contiguous()
         dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
-        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(g), n, c, c, None, None, idx.size(1), _C.ptr(idx), _C.ptr(sim),
+        _, _, inv_norm = rownorm(h, want_f32=False, want_inv=True)
+        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, c, c, None, None, idx.size(1), _C.ptr(idx), _C.ptr(sim),
                                            _C.ptr(cnt), _C.ptr(inv_denom), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
                  "sng_edge_agg_bwd")
         return dh, None, None, None, None
