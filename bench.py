@@ -346,7 +346,9 @@ def run_ours(args):
                            "features": args.features, "l2": "inputs larger than L2 (x-hat f16 %.0f MB, f32 %.0f MB)" % (N * ldh * 2 / 1e6, N * ld32 * 4 / 1e6),
                            "parallelism": f"row-shard x{world}" + (" + NCCL all-gather of x-hat" if world > 1 else "")},
                 "e2e": {"value": pairs / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-                "gpu_launches": 4 * args.steps, "kernels_per_step": ["rownorm_kernel", "simknn_stage1_kernel", "simknn_rescore_kernel", "simknn_fallback_kernel"],
+                "gpu_launches": 12 * args.steps,
+                "kernels_per_step": ["rownorm_kernel", "simknn_stage1_kernel", "simknn_rescore_kernel", "4 x (simknn_fb_scan_kernel, simknn_fb_merge_kernel)",
+                                     "simknn_fb_stream_kernel"],
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
         line.update(extras)
         print(json.dumps(line))
