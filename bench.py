@@ -221,19 +221,26 @@ def run_ours(args):
     idx, sim, cnt, nfb = out["r"]
     n_fallback = int(nfb)
 
-    # ---- the dominant kernel alone (roofline): tensor-core stage on this rank's rows -----------------------
+    # ---- the dominant kernel alone (roofline): tensor-core main pass on this rank's rows, launched exactly as the
+    # build launches it (same plan; thresholds seeded by the seed pass, which is timed separately) ---------------
     xf, xh = normalise_and_gather(x[lo:hi])
     import ctypes
-    ew, cand = simknn.default_cand(k, Fd)
+    plan = simknn.build_plan(nq, N, Fd, k)
+    ew, cand = plan["ew"], plan["cand"]
     ci = torch.empty(nq * 512, dtype=torch.int32, device=dev)      # lists * cand <= 512 slots per row
     cv = torch.empty(nq * 512, dtype=torch.float32, device=dev)
     cm = torch.empty(nq * 64, dtype=torch.float32, device=dev)
     ns = ctypes.c_int(0)
     thr_lo = thr - 1.01 * (2.0 ** -10 + 1.2e-4)
+    seeds, ms_seed = None, 0.0
+    if plan["seed_stride"] > 0:
+        seeds = simknn.seed_pass(xh[lo:hi], xh, Fd, plan["seed_stride"], ew)
+        ms_seed = timed(lambda: simknn.seed_pass(xh[lo:hi], xh, Fd, plan["seed_stride"], ew), max(2, args.steps // 2), 1)
 
     def stage1_only():
         _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh[lo:]), _C.ptr(xh), ldh, nq, lo, N, Fd, cand, thr_lo, 1, _C.ptr(ci), _C.ptr(cv),
-                                            _C.ptr(cm), ew, 0, ctypes.byref(ns), _C.stream()), "sng_simknn_stage1")
+                                            _C.ptr(cm), ew, plan["nsplit"], ctypes.byref(ns), _C.ptr(seeds), plan["seed_q"],
+                                            plan["seed_stride"], _C.stream()), "sng_simknn_stage1")
 
     ms_k1 = timed(stage1_only, max(2, args.steps // 2), 1)
     flops = 2.0 * nq * N * Fd
@@ -242,9 +249,10 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"stage1:{args.workload}:{world}")
-    roofline = {"bound": "tensor", "kernel": "simknn_stage1_kernel", "achieved": achieved_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["tf_sust"], "traffic": traffic, "peak_source": pk["src"] + " (sustained bf16/fp16 dense)",
-                "kernel_ms": ms_k1, "algorithmic_flops_per_launch": flops, "share_of_step": ms_k1 / ms}
+    roofline = {"bound": "tensor", "kernel": "simknn_stage1_kernel<%d,false> (main pass)" % ew, "achieved": achieved_tf, "peak": pk["tf_sust"],
+                "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sust"], "traffic": traffic,
+                "peak_source": pk["src"] + " (sustained bf16/fp16 dense)", "kernel_ms": ms_k1, "algorithmic_flops_per_launch": flops,
+                "share_of_step": ms_k1 / ms, "seed_pass_ms": ms_seed, "plan": plan}
 
     # ---- SNGNN++ epoch + aggregation kernels on the pokec-shaped graph (rank 0 reports; replicas at N>1) ------
     extras = {}
@@ -346,8 +354,9 @@ def run_ours(args):
                            "features": args.features, "l2": "inputs larger than L2 (x-hat f16 %.0f MB, f32 %.0f MB)" % (N * ldh * 2 / 1e6, N * ld32 * 4 / 1e6),
                            "parallelism": f"row-shard x{world}" + (" + NCCL all-gather of x-hat" if world > 1 else "")},
                 "e2e": {"value": pairs / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-                "gpu_launches": 12 * args.steps,
-                "kernels_per_step": ["rownorm_kernel", "simknn_stage1_kernel", "simknn_rescore_kernel", "4 x (simknn_fb_scan_kernel, simknn_fb_merge_kernel)",
+                "gpu_launches": (12 + (1 if plan["seed_stride"] > 0 else 0)) * args.steps,
+                "kernels_per_step": ["rownorm_kernel"] + (["simknn_stage1_kernel<seed>"] if plan["seed_stride"] > 0 else []) +
+                                    ["simknn_stage1_kernel", "simknn_rescore_kernel", "4 x (simknn_fb_scan_kernel, simknn_fb_merge_kernel)",
                                      "simknn_fb_stream_kernel"],
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
         line.update(extras)

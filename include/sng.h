@@ -168,12 +168,27 @@ SNG_API int sng_simknn_build(const uint16_t* xq_f16, const uint16_t* xall_f16, i
 /* Stage 1 only (profiling / tests): cand_idx / cand_val [nq, lists, cand], cand_min [nq, lists] (upper bound of every
  * score that list dropped, -inf if it dropped nothing above thr_lo); lists = column splits x epilogue warps per TMEM
  * lane quarter.  force_ew in {0,1,2,4} picks the epilogue width (0 = auto), force_nsplit > 0 the number of column
- * splits; *lists_out receives lists (size the outputs for lists * cand <= 512 slots per row). */
+ * splits; *lists_out receives lists (size the outputs for lists * cand <= 512 slots per row).
+ * seeds (may be NULL) = output of sng_simknn_seed with the same seed_stride: every row then starts pruning at the
+ * seed_q-th largest of its 16 group maxima instead of thr_lo. */
 SNG_API int sng_simknn_stage1(const uint16_t* xq_f16, const uint16_t* xall_f16, int64_t ldh,
                       int64_t nq, int64_t q_offset, int64_t n, int64_t d,
                       int cand, float thr_lo, int remove_self,
                       int32_t* cand_idx, float* cand_val, float* cand_min,
-                      int force_ew, int force_nsplit, int* lists_out, void* stream);
+                      int force_ew, int force_nsplit, int* lists_out,
+                      const float* seeds, int seed_q, int seed_stride, void* stream);
+
+/* Seed pass only (profiling / tests): the same tensor-core pipeline over every seed_stride-th database row with a
+ * branch-free epilogue; seeds_out [nq, 16] = maxima of the row's FP16 scores over 16 disjoint groups of sampled columns
+ * (group of sample column c: ((c >> 8) & 1) * 8 + ((c & 255) >> 5)).  sng_simknn_build runs it first (when the plan
+ * says so) to start every row's pruning threshold near its final value. */
+SNG_API int sng_simknn_seed(const uint16_t* xq_f16, const uint16_t* xall_f16, int64_t ldh,
+                    int64_t nq, int64_t n, int64_t d, int seed_stride, int force_ew,
+                    float* seeds_out, void* stream);
+
+/* Launch plan of sng_simknn_build for a shape: out8 = {epilogue warps per lane quarter, candidate slots per list,
+ * column splits, seed stride (0 = no seed pass), seed quantile, B ring stages, K blocks of 64, lists per row}. */
+SNG_API int sng_simknn_plan(int64_t nq, int64_t n, int64_t d, int top_k, int32_t* out8);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ import torch
 from sngnn_b200 import _C, simknn, synth
 
 dev = "cuda"
-def run(n, d, kind, thr_lo, mb, ns, cand=16, reps=3, nq=None):
+def run(n, d, kind, thr_lo, mb, ns, cand=16, reps=3, nq=None, seed_stride=0, seed_q=0):
     x = synth.make_features(n, d, kind, seed=0, device=dev)
     xf, xh = simknn.normalize_operands(x)
     nq = nq or n
@@ -13,15 +13,25 @@ def run(n, d, kind, thr_lo, mb, ns, cand=16, reps=3, nq=None):
     cv = torch.empty(nq * 512, dtype=torch.float32, device=dev)
     cm = torch.empty(nq * 64, dtype=torch.float32, device=dev)
     nsv = ctypes.c_int(0)
+    seeds = None
+    if seed_stride > 0:
+        def g():
+            return simknn.seed_pass(xh[:nq], xh, d, seed_stride, mb)
+        seeds = g(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps): g()
+        b.record(); torch.cuda.synchronize()
+        print(json.dumps(dict(seed_pass_ms=round(a.elapsed_time(b) / reps, 3), stride=seed_stride)), flush=True)
     def f():
-        _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh), _C.ptr(xh), xh.size(1), nq, 0, n, d, cand, thr_lo, 1, _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), mb, ns, ctypes.byref(nsv), _C.stream()), "s1")
+        _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh), _C.ptr(xh), xh.size(1), nq, 0, n, d, cand, thr_lo, 1, _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), mb, ns, ctypes.byref(nsv), _C.ptr(seeds), seed_q, seed_stride, _C.stream()), "s1")
     f(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps): f()
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / reps
-    print(json.dumps(dict(n=n, nq=nq, d=d, kind=kind, thr_lo=thr_lo, ew=mb, lists=nsv.value, cand=cand, ms=round(ms, 3),
+    print(json.dumps(dict(n=n, nq=nq, d=d, kind=kind, thr_lo=thr_lo, ew=mb, lists=nsv.value, cand=cand, seed=(seed_stride, seed_q), ms=round(ms, 3),
                           gpairs=round(nq * n / ms / 1e6, 1), tflops=round(2 * nq * n * d / ms / 1e9, 1))), flush=True)
 
 if __name__ == "__main__":

@@ -38,6 +38,7 @@ constexpr int kMaxStages = 10;
 constexpr int kFallbackBlocks = 32;
 constexpr int kMaxCandTotal = 512;      // lists per row * cand <= this (stage-2 shared memory)
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+constexpr int kSeedGroups = 16;         // disjoint column groups of the seed sample: (tile parity) x (32-column chunk of the tile)
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,15 +142,29 @@ struct Stage1Params {
     int nsplit, tiles_total;      // 256-column tiles are split across gridDim.y cluster columns
     float thr_lo;                 // approximate scores <= thr_lo can never be selected
     int remove_self;
-    int debug;                    // profiling aid (SNG_KNN_DEBUG): 1 = skip the max tree / inserts, 3 = also skip the TMEM loads
+    int issuers;                  // MMA-issuing warps (1 or 2)
+    int debug;                    // profiling aid (SNG_KNN_DEBUG): 1 = skip the max tree / inserts, 2 = skip the TMEM loads, 4 = skip the B loads
     float* cand_val;              // [nq, nsplit*EW, cand]
     int* cand_idx;                // [nq, nsplit*EW, cand]   (-1 = empty)
     float* cand_min;              // [nq, nsplit*EW]  worst kept approx score if the list filled up, else -inf
+    // threshold seeding (see "Seeding" below): the seed pass writes seed_out, the main pass reads seeds
+    const float* seeds;           // [nq, kSeedGroups] group maxima over a 1/seed_stride column sample, or nullptr
+    float* seed_out;              // SEED kernel only
+    int seed_q, seed_stride;      // row threshold = seed_q-th largest group maximum; sample = every seed_stride-th column
+    long long* trace;             // SNG_KNN_TRACE: [64 tiles][4] clock64 stamps of cluster 0's leader CTA, else nullptr
 };
 
 // EW = epilogue warps per TMEM lane quarter; every epilogue thread owns one query row x (256/EW) columns of each tile
 // and its own candidate list; the EW threads of a row share one pruning threshold.
-template <int EW>
+//
+// Seeding.  A list that starts from thr_lo inserts ~L ln(n/L) times, and every insert is a slow, divergent detour off the
+// max-tree fast path (ncu, pokec shape: 3/4 of all warp instructions).  So the build first runs this kernel in SEED mode
+// over every seed_stride-th database row: the epilogue is a branch-free running maximum per (row, column group), 16 groups
+// per row.  The main pass starts each row at tau = the seed_q-th largest group maximum: at least seed_q sampled columns
+// score >= tau, so >= top_k columns of the full set do unless >= seed_q of the row's true top_k fell into the 1/stride
+// sample (probability chosen < 2e-5 on the host).  As with every pruning threshold here, a bad tau costs time, never
+// correctness: tau is reported through cand_min and stage 2 sends unproven rows to the exact scan.
+template <int EW, bool SEED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 128 * EW, 1)
 simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const Stage1Params p) {
     constexpr int CPT = BN / EW;                                  // columns per thread per tile
@@ -187,7 +202,36 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else if (warp == 3) {
-        for (int i = lane; i < BM; i += 32) row_thr[i] = p.thr_lo;
+        for (int i = lane; i < BM; i += 32) {
+            float tau = p.thr_lo;
+            const int grow = row0 + i;
+            if (!SEED && p.seeds != nullptr && grow < p.nq) {
+                float g[kSeedGroups];
+#pragma unroll
+                for (int j = 0; j < kSeedGroups / 4; ++j) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.seeds + (size_t)grow * kSeedGroups) + j);
+                    g[4 * j] = t4.x; g[4 * j + 1] = t4.y; g[4 * j + 2] = t4.z; g[4 * j + 3] = t4.w;
+                }
+                const int self = p.q_offset + grow;                  // the row itself may sit in the sample: drop its group
+                if (p.remove_self && self % p.seed_stride == 0) {
+                    const int cs = self / p.seed_stride, sg = ((cs >> 8) & 1) * 8 + ((cs & 255) >> 5);
+#pragma unroll
+                    for (int j = 0; j < kSeedGroups; ++j) if (j == sg) g[j] = -CUDART_INF_F;
+                }
+                float cur = CUDART_INF_F;
+                for (int r = 0; r < p.seed_q; ++r) {                 // seed_q-th largest by repeated removal of the maximum
+                    float mx = -CUDART_INF_F;
+#pragma unroll
+                    for (int j = 0; j < kSeedGroups; ++j) mx = fmaxf(mx, g[j]);
+                    bool gone = false;
+#pragma unroll
+                    for (int j = 0; j < kSeedGroups; ++j) if (!gone && g[j] == mx) { g[j] = -CUDART_INF_F; gone = true; }
+                    cur = mx;
+                }
+                tau = fmaxf(tau, cur);
+            }
+            row_thr[i] = tau;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -211,26 +255,40 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (issuer) {
-                    tma_load_2d_pair(base + b_off + (uint32_t)stage * kTileBytes, &map_db, (bar_full + 8 * stage) & kPeerMask, kb * BK, brow);
-                    if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * kTileBytes);
-                    else mbar_arrive_cluster(bar_full + 8 * stage, 0);
+                    if (!(p.debug & 4)) {
+                        tma_load_2d_pair(base + b_off + (uint32_t)stage * kTileBytes, &map_db, (bar_full + 8 * stage) & kPeerMask, kb * BK, brow);
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * kTileBytes);
+                        else mbar_arrive_cluster(bar_full + 8 * stage, 0);
+                    } else {                                        // profiling: no B traffic at all, the MMAs read stale shared memory
+                        mbar_arrive_cluster(bar_full + 8 * stage, 0);
+                    }
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp runs the loop, one lane issues)
-        if (rank == 0) {
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------------------------ MMA issuers (leader CTA; whole warp runs the loop, one lane issues)
+        // The chain "accumulator free -> B landed -> issue -> commit" costs one thread ~1300 cycles per tile (mbarrier
+        // try_wait ~90 each even when complete, plus issue / commit latencies; measured with SNG_KNN_TRACE), twice the
+        // 640 cycles the tensor pipe needs for a K = 80 tile.  So TWO warps issue, each owning every other tile and one
+        // of the two accumulator stages; their chains overlap and the pipe stays fed.  (tcgen05.commit tracks the MMAs
+        // of the executing thread only, and each accumulator is only ever written by one of the two threads.)
+        const int w = warp - 1;
+        if (rank == 0 && w < p.issuers) {
             const bool issuer = elect_one();
             mbar_wait(bar_a, 0);
             tc_fence_after();
             const uint64_t adesc0 = make_smem_desc(base + a_off);
             const uint64_t bdesc0 = make_smem_desc(base + b_off);
             int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int t = t_beg; t < t_end; ++t) {
+            auto advance = [&](int steps) { for (int i = 0; i < steps; ++i) if (++stage == p.stages) { stage = 0; phase ^= 1; } };
+            advance(w * p.kblocks);
+            for (int t = t_beg + w; t < t_end; t += p.issuers) {
+                const int acc = (t - t_beg) & 1;
+                const uint32_t acc_phase = (uint32_t)((t - t_beg) >> 1) & 1u;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
+                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 4 + 0] = clock64();
                 const uint32_t tmem_d = (uint32_t)(acc * BN);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
@@ -246,13 +304,15 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                         if (kb == p.kblocks - 1) umma_commit_pair(bar_tfull + 8 * acc);   // accumulator of tile t complete (both CTAs)
                     }
                     __syncwarp();
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    advance(1);
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 4 + 1] = clock64();
+                advance((p.issuers - 1) * p.kblocks);                   // the other issuer's tile
             }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue: thread = one query row x CPT columns per tile
+        constexpr int CT = CPT / 32;                               // 32-column chunks per thread per tile
         const int quarter = warp & 3, slice = (warp - 4) >> 2;
         const int r = quarter * 32 + lane;                        // row within the CTA == TMEM lane
         const int grow = row0 + r;
@@ -262,6 +322,9 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         int* li = list_idx + (size_t)slice * L * BM + r;
         int cnt = 0;
         float thr_cur = p.thr_lo;                                  // max(own list minimum once full, shared row threshold)
+        float gmax[2 * CT];                                        // SEED: running maxima of this thread's column groups
+#pragma unroll
+        for (int i = 0; i < 2 * CT; ++i) gmax[i] = -CUDART_INF_F;
 
         int minpos = 0;
         auto insert = [&](float x, int col) {
@@ -281,24 +344,52 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         };
         // Pruning thresholds are heuristics: ANY threshold is safe because every thread reports the largest threshold it
         // ever pruned with (cand_min) and stage 2 only accepts a row whose k-th exact score clears all of them.
-        auto process = [&](const uint32_t (&v)[32], int col0) {
+        // `ci` = chunk index within the thread's tile slice (compile time after unrolling), `odd` = tile parity.
+        auto process = [&](const uint32_t (&v)[32], int col0, int ci, bool odd) {
             if (p.debug) { if (__uint_as_float(v[0] ^ v[31]) == 12345.678f) thr_cur = 0.f; return; }
             float m[11];
 #pragma unroll
             for (int i = 0; i < 10; ++i) m[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
             m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
             const float m0 = max3(m[0], m[1], m[2]), m1 = max3(m[3], m[4], m[5]), m2 = max3(m[6], m[7], m[8]);
-            const float mx = max3(max3(m0, m1, m2), m[9], m[10]);
-            if (__any_sync(0xffffffffu, mx > thr_cur)) {           // rare, warp-uniform slow path (kept compact: one copy of insert)
-                uint32_t mask = 0;
+            float mx = max3(max3(m0, m1, m2), m[9], m[10]);
+            if (SEED) {
+                if (col0 + 32 > n) {                                 // last tile: zero-filled columns beyond n must not count
+                    mx = -CUDART_INF_F;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) > thr_cur ? 1u : 0u) << i;
-                uint32_t todo = __reduce_or_sync(0xffffffffu, mask);
+                    for (int i = 0; i < 32; ++i) if (col0 + i < n) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
+                gmax[ci] = fmaxf(gmax[ci], odd ? -CUDART_INF_F : mx);
+                gmax[CT + ci] = fmaxf(gmax[CT + ci], odd ? mx : -CUDART_INF_F);
+                return;
+            }
+            if (__any_sync(0xffffffffu, mx > thr_cur)) {           // rare, warp-uniform slow path (kept compact: one copy of insert)
+                uint32_t tm = 0;
+#pragma unroll
+                for (int i = 0; i < 11; ++i) tm |= (m[i] > thr_cur ? 1u : 0u) << i;
+                uint32_t todo = __reduce_or_sync(0xffffffffu, tm);  // triples of columns in which some lane has a hit
                 while (todo) {
                     const int i = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const float x = select32(v, i);
-                    if (x > thr_cur) insert(x, col0 + i);
+                    uint32_t x0, x1, x2;
+                    switch (i) {
+                        case 0: x0 = v[0]; x1 = v[1]; x2 = v[2]; break;
+                        case 1: x0 = v[3]; x1 = v[4]; x2 = v[5]; break;
+                        case 2: x0 = v[6]; x1 = v[7]; x2 = v[8]; break;
+                        case 3: x0 = v[9]; x1 = v[10]; x2 = v[11]; break;
+                        case 4: x0 = v[12]; x1 = v[13]; x2 = v[14]; break;
+                        case 5: x0 = v[15]; x1 = v[16]; x2 = v[17]; break;
+                        case 6: x0 = v[18]; x1 = v[19]; x2 = v[20]; break;
+                        case 7: x0 = v[21]; x1 = v[22]; x2 = v[23]; break;
+                        case 8: x0 = v[24]; x1 = v[25]; x2 = v[26]; break;
+                        case 9: x0 = v[27]; x1 = v[28]; x2 = v[29]; break;
+                        default: x0 = v[30]; x1 = v[31]; x2 = 0xff800000u; break;
+                    }
+#pragma unroll 1
+                    for (int e = 0; e < 3; ++e) {
+                        const float x = __uint_as_float(e == 0 ? x0 : (e == 1 ? x1 : x2));
+                        if (x > thr_cur) insert(x, col0 + 3 * i + e);
+                    }
                 }
             }
         };
@@ -308,9 +399,12 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int t = t_beg; t < t_end; ++t) {
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            thr_cur = fmaxf(thr_cur, row_thr[r]);
+            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && threadIdx.x == kNonEpiThreads;
+            if (tr) p.trace[(t - t_beg) * 4 + 2] = clock64();
+            if (!SEED) thr_cur = fmaxf(thr_cur, row_thr[r]);
             const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * CPT);
             const int col0 = t * BN + slice * CPT;
+            const bool odd = (t & 1) != 0;
             if (CPT == 64) {
                 // both loads in flight at once; the accumulator stage goes back to the MMA warp before any processing
                 if (!(p.debug & 2)) {
@@ -321,29 +415,37 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
-                process(va, col0);
-                process(vb, col0 + 32);
+                if (tr) p.trace[(t - t_beg) * 4 + 3] = clock64();
+                process(va, col0, 0, odd);
+                process(vb, col0 + 32, CT > 1 ? 1 : 0, odd);
             } else {
                 tmem_ld32(taddr, va);
 #pragma unroll
-                for (int c = 0; c < CPT / 32; c += 2) {
+                for (int c = 0; c < CT; c += 2) {
                     tmem_ld_wait();
                     tmem_ld32(taddr + (c + 1) * 32, vb);
-                    process(va, col0 + c * 32);
+                    process(va, col0 + c * 32, c, odd);
                     tmem_ld_wait();
-                    if (c + 2 < CPT / 32) tmem_ld32(taddr + (c + 2) * 32, va);
+                    if (c + 2 < CT) tmem_ld32(taddr + (c + 2) * 32, va);
                     else {
                         // every load of this accumulator stage has landed: hand the stage back to the leader's MMA warp
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
                     }
-                    process(vb, col0 + (c + 1) * 32);
+                    process(vb, col0 + (c + 1) * 32, c + 1, odd);
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (grow < p.nq) {
+        if (SEED) {
+            if (grow < p.nq) {
+                // group id of sample column cs = ((cs >> 8) & 1) * 8 + ((cs & 255) >> 5)  (tile parity, chunk of the tile)
+#pragma unroll
+                for (int i = 0; i < 2 * CT; ++i)
+                    p.seed_out[(size_t)grow * kSeedGroups + (i / CT) * 8 + slice * CT + (i % CT)] = gmax[i];
+            }
+        } else if (grow < p.nq) {
             const int lists = p.nsplit * EW, li_id = (int)blockIdx.y * EW + slice;
             const size_t o = ((size_t)grow * lists + li_id) * L;
             for (int s = 0; s < L; ++s) {
@@ -613,12 +715,13 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [rows, ld] FP16 row-major, box = 64 (K) x 128 (rows), 128-byte swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t ld) {
+// [rows, ld] FP16 row-major, box = 64 (K) x 128 (rows), 128-byte swizzle, zero fill out of bounds.  `row_stride` > 1
+// maps every row_stride-th row of the matrix (the seed pass's column sample); `ld` stays the K extent.
+static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t ld, int64_t row_stride = 1) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return SNG_ERR_CUDA; }
     cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2 * (cuuint64_t)row_stride};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(ptr), gdim, gstr, box, estr,
@@ -630,9 +733,24 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
 
 struct Plan {
     int ew, stages, cand, nsplit, kblocks, ksteps_last, tiles;
+    int seed_stride, seed_q;      // 0 = no seed pass
     size_t smem;
     int lists() const { return nsplit * ew; }
 };
+
+// Smallest q with P(Binomial(top_k, 1/stride) >= q) <= tol: the chance that q of a row's true top_k landed in the sample.
+static int seed_quantile(int top_k, int stride, double tol) {
+    const double pr = 1.0 / stride;
+    double pmf = 1.0;
+    for (int i = 0; i < top_k; ++i) pmf *= 1.0 - pr;          // P(X = 0)
+    double tail = 1.0 - pmf;                                   // P(X >= 1)
+    for (int q = 1; q <= top_k; ++q) {
+        if (tail <= tol) return q;
+        pmf *= (double)(top_k - q + 1) / q * pr / (1.0 - pr);  // P(X = q)
+        tail -= pmf;
+    }
+    return top_k + 1;
+}
 
 static size_t smem_bytes(int ew, int kblocks, int stages, int cand) {
     return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)ew * cand * BM * 8 + BM * 4 + 8 * (2 * kMaxStages + 5) + 16;
@@ -671,7 +789,8 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
         for (int ew = force_ew ? force_ew : ew_pref; ew >= 1 && !pl->ew; ew >>= 1) {
             const int c = top_k > 0 ? cand_for(top_k, ew) : cand;
             if (ew * c <= kMaxCandTotal) {
-                const int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
+                int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
+                if (env_int("SNG_KNN_STAGES", 2, kMaxStages)) want = env_int("SNG_KNN_STAGES", 2, kMaxStages);
                 for (int st = want; st >= (pass ? 2 : 3); --st) {
                     const size_t sz = smem_bytes(ew, pl->kblocks, st, c);
                     if (sz <= kMaxSmem) { pl->ew = ew; pl->stages = st; pl->smem = sz; pl->cand = c; break; }
@@ -691,34 +810,69 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     while (ns > 1 && ns * pl->ew * pl->cand > kMaxCandTotal) --ns;
     if (ns < 1) ns = 1;
     pl->nsplit = ns;
+    // threshold seeding: only for full builds (top_k known) that sweep many tiles with one list set per row
+    pl->seed_stride = pl->seed_q = 0;
+    // (the seed pass is never column-split, so with many splits it would cost as much as the main pass)
+    const bool forced = env_int("SNG_KNN_SEED_S", 2, 256) != 0;
+    if (top_k > 0 && (ns <= 2 || forced) && !getenv("SNG_KNN_NOSEED")) {
+        int stride = env_int("SNG_KNN_SEED_S", 2, 256);
+        if (!stride) stride = 16;
+        int q = env_int("SNG_KNN_SEED_Q", 1, kSeedGroups - 2);
+        if (!q) q = seed_quantile(top_k, stride, 2e-5);
+        if (pl->tiles / stride >= 32 && q <= kSeedGroups - 4) { pl->seed_stride = stride; pl->seed_q = q; }
+    }
     return SNG_OK;
 }
 
-template <int EW>
+template <int EW, bool SEED>
 static cudaError_t launch_ew(dim3 grid, size_t smem, cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mdb, const Stage1Params& p) {
-    cudaError_t e = cudaFuncSetAttribute(simknn_stage1_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(simknn_stage1_kernel<EW, SEED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    simknn_stage1_kernel<EW><<<grid, kNonEpiThreads + 128 * EW, smem, st>>>(mq, mdb, p);
+    simknn_stage1_kernel<EW, SEED><<<grid, kNonEpiThreads + 128 * EW, smem, st>>>(mq, mdb, p);
     return cudaSuccess;
 }
 
+// seeds != nullptr && seed_out == nullptr: main pass starting from the seeded thresholds;  seed_out != nullptr: SEED pass.
 static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n,
-                         float thr_lo, int remove_self, float* cand_val, int* cand_idx, float* cand_min, cudaStream_t st) {
+                         float thr_lo, int remove_self, float* cand_val, int* cand_idx, float* cand_min, const float* seeds,
+                         float* seed_out, cudaStream_t st) {
+    const bool seed_pass = seed_out != nullptr;
+    const int64_t n_db = seed_pass ? (n + pl.seed_stride - 1) / pl.seed_stride : n;
     CUtensorMap mq, mdb;
     if (int rc = make_map(&mq, xq, nq, ldb)) return rc;
-    if (int rc = make_map(&mdb, xall, n, ldb)) return rc;
+    if (int rc = make_map(&mdb, xall, n_db, ldb, seed_pass ? pl.seed_stride : 1)) return rc;
     Stage1Params p;
-    p.nq = (int)nq; p.n = (int)n; p.q_offset = (int)q_offset;
-    p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = pl.cand;
-    p.nsplit = pl.nsplit; p.tiles_total = pl.tiles; p.thr_lo = thr_lo; p.remove_self = remove_self;
-    p.debug = env_int("SNG_KNN_DEBUG", 1, 3);
+    p.nq = (int)nq; p.n = (int)n_db; p.q_offset = (int)q_offset;
+    p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = seed_pass ? 0 : pl.cand;
+    p.nsplit = seed_pass ? 1 : pl.nsplit; p.tiles_total = (int)((n_db + BN - 1) / BN); p.thr_lo = thr_lo; p.remove_self = remove_self;
+    p.debug = env_int("SNG_KNN_DEBUG", 1, 7);
+    p.issuers = env_int("SNG_KNN_ISSUERS", 1, 2) ? env_int("SNG_KNN_ISSUERS", 1, 2) : (pl.kblocks <= 3 ? 2 : 1);
     p.cand_val = cand_val; p.cand_idx = cand_idx; p.cand_min = cand_min;
-    dim3 grid((unsigned)(2 * ((nq + 2 * BM - 1) / (2 * BM))), (unsigned)pl.nsplit);      // x: CTA pairs (cluster of 2), y: column splits
-    cudaError_t e = pl.ew == 4 ? launch_ew<4>(grid, pl.smem, st, mq, mdb, p)
-                  : pl.ew == 2 ? launch_ew<2>(grid, pl.smem, st, mq, mdb, p)
-                               : launch_ew<1>(grid, pl.smem, st, mq, mdb, p);
+    p.seeds = seed_pass ? nullptr : seeds; p.seed_out = seed_out; p.seed_q = pl.seed_q; p.seed_stride = pl.seed_stride > 0 ? pl.seed_stride : 1;
+    dim3 grid((unsigned)(2 * ((nq + 2 * BM - 1) / (2 * BM))), (unsigned)p.nsplit);        // x: CTA pairs (cluster of 2), y: column splits
+    p.trace = nullptr;
+    if (getenv("SNG_KNN_TRACE") && !seed_pass) {              // debugging aid only: allocates, synchronises and prints
+        cudaMalloc(&p.trace, 64 * 4 * sizeof(long long));
+        cudaMemset(p.trace, 0, 64 * 4 * sizeof(long long));
+    }
+    cudaError_t e;
+    if (seed_pass) e = pl.ew == 4 ? launch_ew<4, true>(grid, pl.smem, st, mq, mdb, p)
+                     : pl.ew == 2 ? launch_ew<2, true>(grid, pl.smem, st, mq, mdb, p)
+                                  : launch_ew<1, true>(grid, pl.smem, st, mq, mdb, p);
+    else e = pl.ew == 4 ? launch_ew<4, false>(grid, pl.smem, st, mq, mdb, p)
+           : pl.ew == 2 ? launch_ew<2, false>(grid, pl.smem, st, mq, mdb, p)
+                        : launch_ew<1, false>(grid, pl.smem, st, mq, mdb, p);
     if (e != cudaSuccess) { cudaGetLastError(); set_error("simknn stage 1: cudaFuncSetAttribute(%zu B smem): %s", pl.smem, cudaGetErrorString(e)); return SNG_ERR_CUDA; }
-    return check_launch("simknn stage 1");
+    if (p.trace) {
+        long long h[64 * 4];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(p.trace);
+        fprintf(stderr, "tile  mma:tempty_ok  mma:issued  epi:tfull_ok  epi:released   (cycles since tile 0's tempty_ok)\n");
+        for (int t = 0; t < 64; ++t)
+            fprintf(stderr, "%4d %10lld %10lld %10lld %10lld\n", t, h[4 * t] - h[0], h[4 * t + 1] - h[0], h[4 * t + 2] - h[0], h[4 * t + 3] - h[0]);
+    }
+    return check_launch(seed_pass ? "simknn seed pass" : "simknn stage 1");
 }
 
 static int check_common(const char* fn, const void* xq, const void* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n, int64_t d) {
@@ -747,12 +901,37 @@ extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, i
     if (make_plan(&pl, nq, n, d, top_k, 0, 0)) return 0;
     const size_t slots = (size_t)nq * pl.lists() * pl.cand;
     const size_t part = (size_t)kFbWaveRows * ((n + kChunk - 1) / kChunk) * top_k;
-    return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + 2 * align256(part * 4) + 1024;
+    return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + 2 * align256(part * 4) +
+           align256((size_t)nq * kSeedGroups * 4) + 1024;
+}
+
+// The launch plan sng_simknn_build uses for this shape: out[0..7] = epilogue warps per lane quarter, candidate slots per list,
+// column splits, seed stride (0 = no seed pass), seed quantile, B ring stages, K blocks, lists per row.
+extern "C" int sng_simknn_plan(int64_t nq, int64_t n, int64_t d, int top_k, int32_t* out8) {
+    SNG_REQUIRE(out8 && nq > 0 && n > 0 && d > 0 && top_k >= 1 && top_k <= SNG_KNN_MAX_TOPK, "sng_simknn_plan: bad arguments");
+    Plan pl;
+    if (int rc = make_plan(&pl, nq, n, d, top_k, 0, 0)) return rc;
+    out8[0] = pl.ew; out8[1] = pl.cand; out8[2] = pl.nsplit; out8[3] = pl.seed_stride; out8[4] = pl.seed_q; out8[5] = pl.stages;
+    out8[6] = pl.kblocks; out8[7] = pl.lists();
+    return SNG_OK;
+}
+
+// Seed pass only (profiling / tests): seeds_out [nq, 16] = per-row maxima of the 16 column groups of the stride-sample.
+extern "C" int sng_simknn_seed(const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t n, int64_t d, int seed_stride,
+                               int force_ew, float* seeds_out, void* stream) {
+    if (int rc = check_common("sng_simknn_seed", xq, xall, ldb, nq, 0, n, d)) return rc;
+    SNG_REQUIRE(seeds_out && seed_stride >= 1 && seed_stride <= 256, "sng_simknn_seed: bad seed_stride / output");
+    SNG_REQUIRE(force_ew == 0 || force_ew == 1 || force_ew == 2 || force_ew == 4, "sng_simknn_seed: force_ew must be 0, 1, 2 or 4");
+    Plan pl;
+    if (int rc = make_plan(&pl, nq, n, d, 0, 8, force_ew)) return rc;
+    pl.seed_stride = seed_stride; pl.seed_q = 1;
+    return launch_stage1(pl, xq, xall, ldb, nq, 0, n, -3.0e38f, 0, nullptr, nullptr, nullptr, nullptr, seeds_out, (cudaStream_t)stream);
 }
 
 extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n, int64_t d,
                                  int cand, float thr_lo, int remove_self, int32_t* cand_idx, float* cand_val, float* cand_min,
-                                 int force_ew, int force_nsplit, int* lists_out, void* stream) {
+                                 int force_ew, int force_nsplit, int* lists_out, const float* seeds, int seed_q, int seed_stride,
+                                 void* stream) {
     if (int rc = check_common("sng_simknn_stage1", xq, xall, ldb, nq, q_offset, n, d)) return rc;
     SNG_REQUIRE(cand >= 8 && cand <= 128 && cand_idx && cand_val && cand_min, "sng_simknn_stage1: bad cand / outputs");
     SNG_REQUIRE(force_ew == 0 || force_ew == 1 || force_ew == 2 || force_ew == 4, "sng_simknn_stage1: force_ew must be 0, 1, 2 or 4");
@@ -761,7 +940,10 @@ extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64
     if (force_nsplit > 0) pl.nsplit = force_nsplit < pl.tiles ? force_nsplit : pl.tiles;
     SNG_REQUIRE(pl.lists() * cand <= kMaxCandTotal, "sng_simknn_stage1: nsplit*ew*cand = %d exceeds %d", pl.lists() * cand, kMaxCandTotal);
     if (lists_out) *lists_out = pl.lists();
-    return launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min, (cudaStream_t)stream);
+    SNG_REQUIRE(!seeds || (seed_q >= 1 && seed_q <= kSeedGroups - 2 && seed_stride >= 1),
+                "sng_simknn_stage1: seeds need 1 <= seed_q <= %d, seed_stride >= 1", kSeedGroups - 2);
+    pl.seed_q = seeds ? seed_q : 0; pl.seed_stride = seeds ? seed_stride : 0;
+    return launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min, seeds, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_t ldb, const float* xq32, const float* xall32, int64_t ld32,
@@ -785,11 +967,15 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
     const size_t part = (size_t)kFbWaveRows * n_chunks * top_k;
     float* part_s = reinterpret_cast<float*>(w); w += align256(part * 4);
-    int* part_i = reinterpret_cast<int*>(w);
+    int* part_i = reinterpret_cast<int*>(w); w += align256(part * 4);
+    float* seeds = reinterpret_cast<float*>(w);
     if (cudaMemsetAsync(n_fallback, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
     // approximate scores below thr - eps can never reach thr exactly
     const float thr_lo = thr - 1.01f * kScoreEps;
-    if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min, st)) return rc;
+    if (pl.seed_stride > 0)
+        if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, nullptr, nullptr, nullptr, nullptr, seeds, st)) return rc;
+    if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min,
+                               pl.seed_stride > 0 ? seeds : nullptr, nullptr, st)) return rc;
     const int d4 = (int)((d + 3) / 4);
     {
         const int blocks = (int)((nq + 7) / 8 < (int64_t)sm_count() * 8 ? (nq + 7) / 8 : (int64_t)sm_count() * 8);

@@ -70,18 +70,27 @@ def knn_to_csr(idx, cnt):
     return rowptr.to(torch.int32), idx.reshape(-1)[flat].contiguous(), flat
 
 
-def default_cand(top_k, d):
-    """(epilogue warps per lane quarter, candidate slots per list) that sng_simknn_build picks for (top_k, d);
-    mirrors make_plan / cand_for in csrc/sng_simknn.cu (used to reproduce its stage-1 launch for profiling)."""
-    import os
-    d16 = _pad_to(d, 16)
-    ew = int(os.environ.get("SNG_KNN_EW", 0)) or (4 if d16 <= 128 else (2 if d16 <= 320 else 1))
-    cand = int(os.environ.get("SNG_KNN_CAND", 0)) or (max(top_k + {4: 4, 2: 10, 1: 16}[ew], 14) + 1) // 2 * 2
-    return ew, cand
+def build_plan(nq, n, d, top_k):
+    """The launch plan sng_simknn_build picks for this shape (sng_simknn_plan): dict with ew (epilogue warps per TMEM
+    lane quarter), cand (slots per list), nsplit, seed_stride (0 = no seed pass), seed_q, stages, kblocks, lists."""
+    import ctypes
+    out = (ctypes.c_int32 * 8)()
+    _C.check(_C.lib().sng_simknn_plan(nq, n, d, int(top_k), out), "sng_simknn_plan")
+    return dict(zip(("ew", "cand", "nsplit", "seed_stride", "seed_q", "stages", "kblocks", "lists"), list(out)))
 
 
-def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_nsplit=0):
-    """Tensor-core stage only (tests / profiling): FP16-scored candidate lists [N, lists, cand] + per-list drop bounds."""
+def seed_pass(xh_q, xh_all, d, seed_stride, force_ew=0):
+    """Tensor-core seed pass only (tests / profiling): [nq, 16] group maxima over every seed_stride-th database row."""
+    nq, n = xh_q.size(0), xh_all.size(0)
+    seeds = torch.empty(nq, 16, dtype=torch.float32, device=xh_q.device)
+    _C.check(_C.lib().sng_simknn_seed(_C.ptr(xh_q), _C.ptr(xh_all), xh_all.size(1), nq, n, d, int(seed_stride), force_ew,
+                                      _C.ptr(seeds), _C.stream()), "sng_simknn_seed")
+    return seeds
+
+
+def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_nsplit=0, seed_stride=0, seed_q=0):
+    """Tensor-core stage only (tests / profiling): FP16-scored candidate lists [N, lists, cand] + per-list drop bounds.
+    seed_stride > 0 runs the seed pass first and starts every row at its seed_q-th largest group maximum."""
     import ctypes
     xf, xh = normalize_operands(x)
     n, d = x.shape
@@ -91,8 +100,10 @@ def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_
     cv = torch.empty(n * slots, dtype=torch.float32, device=dev)
     cm = torch.empty(n * 64, dtype=torch.float32, device=dev)
     nl = ctypes.c_int(0)
+    seeds = seed_pass(xh, xh, d, seed_stride, force_ew) if seed_stride > 0 else None
     _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh), _C.ptr(xh), xh.size(1), n, 0, n, d, cand, float(thr_lo), int(remove_self),
-                                        _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), force_ew, force_nsplit, ctypes.byref(nl), _C.stream()),
+                                        _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), force_ew, force_nsplit, ctypes.byref(nl),
+                                        _C.ptr(seeds), int(seed_q), int(seed_stride), _C.stream()),
              "sng_simknn_stage1")
     s = nl.value
     return ci[: n * s * cand].reshape(n, s, cand), cv[: n * s * cand].reshape(n, s, cand), cm[: n * s].reshape(n, s), xf, xh

@@ -115,3 +115,52 @@ def test_allpairs_model_mode_matches_oracle():
     h = torch.nn.functional.linear(x, conv.lin.weight.detach().cpu(), conv.lin.bias.detach().cpu())
     ref = sn_ref.sn_aggregate(h, ei, k, thr)
     torch.testing.assert_close(out.detach().cpu(), ref, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,d,stride,ew", [(20000, 65, 2, 4), (17000, 128, 2, 4), (33000, 200, 4, 2), (16500, 400, 2, 1)])
+def test_seed_pass_group_maxima(n, d, stride, ew):
+    """SEED mode of the tensor-core kernel: seeds[r, g] = max FP16 score of row r over the sampled columns of group g
+    (sample = every stride-th database row; group of sample column c = ((c>>8)&1)*8 + ((c&255)>>5))."""
+    from sngnn_b200 import simknn
+    x = _features(n, d, "clustered", seed=n)
+    xf, xh = simknn.normalize_operands(x.to(DEV))
+    nq = 700
+    seeds = simknn.seed_pass(xh[:nq], xh, d, stride, ew).cpu()
+    torch.cuda.synchronize()
+    xs = xh[::stride].float()
+    sc = (xh[:nq].float() @ xs.t()).cpu()                        # products of FP16 values, FP32 accumulation
+    cs = torch.arange(xs.size(0))
+    grp = ((cs >> 8) & 1) * 8 + ((cs & 255) >> 5)
+    ref = torch.full((nq, 16), float("-inf"))
+    for g in range(16):
+        if (grp == g).any():
+            ref[:, g] = sc[:, grp == g].max(1).values
+    assert torch.isfinite(seeds).all() == torch.isfinite(ref).all()
+    fin = torch.isfinite(ref)
+    assert (seeds[fin] - ref[fin]).abs().max() < 2e-4            # summation order of the tensor cores vs torch
+
+
+@pytest.mark.parametrize("n,d,k,thr,rs,kind,stride,q", [(20000, 65, 10, -1.0, True, "normal", 2, 0), (20000, 65, 10, 0.5, True, "clustered", 2, 0),
+                                                         (36000, 128, 5, -1.0, False, "clustered", 4, 0), (20000, 40, 10, -1.0, True, "normal", 2, 1)])
+def test_seeded_build_matches_oracle(n, d, k, thr, rs, kind, stride, q, monkeypatch):
+    """Full build with threshold seeding switched on (SNG_KNN_SEED_S shrinks the stride so it engages at test sizes;
+    q = 1 makes the seeded threshold far too aggressive, so the proof must send many rows to the exact scan)."""
+    from sngnn_b200 import simknn
+    monkeypatch.setenv("SNG_KNN_SEED_S", str(stride))
+    if q:
+        monkeypatch.setenv("SNG_KNN_SEED_Q", str(q))
+    x = _features(n, d, kind, seed=n + d + k)
+    plan = simknn.build_plan(n, n, d, k)
+    assert plan["seed_stride"] == stride and plan["seed_q"] >= 1, plan
+    idx, sim, cnt, nfb = simknn.build_knn(x.to(DEV), k, thr, rs, return_fallback=True)
+    torch.cuda.synchronize()
+    rows = 1500                                                  # oracle on a slab of query rows (all columns)
+    sl = slice(n // 2, n // 2 + rows)
+    idx_ref, sim_ref, cnt_ref = _oracle(x, k, thr, rs, sl.start, sl.stop)
+    score = _score64(x)
+    res = compare_lists(idx[sl], cnt[sl], idx_ref, cnt_ref, lambda r, j: score(r + sl.start, j), thr)
+    print(f"seeded n={n} d={d} k={k} thr={thr} plan={plan}: {res} fallback_rows={int(nfb)}")
+    assert res["out_of_band"] == 0, res
+    assert check_tie_order(idx, sim, cnt)
+    if q == 1:
+        assert int(nfb) > 0
