@@ -36,8 +36,14 @@ constexpr int kUmmaK = 16;
 constexpr int kNonEpiThreads = 128;
 constexpr int kMaxStages = 10;
 constexpr int kFallbackBlocks = 32;
-constexpr int kMaxCandTotal = 512;      // lists per row * cand <= this (stage-2 shared memory)
+constexpr int kMaxCandTotal = 192;      // lists per row * cand <= this; stage 2 expands every candidate into 3 columns
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+#ifdef SNG_KNN_EVTRACE
+constexpr bool kEvTrace = true;          // per-event statistics in SNG_KNN_TRACE runs (costs local memory in the epilogue)
+#else
+constexpr bool kEvTrace = false;
+#endif
+constexpr int kQueue = 256;             // hit queue entries per CTA (power of two); one entry = 64 bytes
 constexpr int kSeedGroups = 16;         // disjoint column groups of the seed sample: (tile parity) x (32-column chunk of the tile)
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -138,20 +144,20 @@ struct Stage1Params {
     int nq, n, q_offset;          // query rows in this call, database rows, global id of query row 0
     int kblocks, ksteps_last;     // K tiling: kblocks tiles of 64, the last one has ksteps_last MMA steps of 16
     int stages;                   // B ring depth (K blocks)
-    int cand;                     // candidate slots per list (L)
+    int cand;                     // candidate slots per row list (L)
     int nsplit, tiles_total;      // 256-column tiles are split across gridDim.y cluster columns
     float thr_lo;                 // approximate scores <= thr_lo can never be selected
     int remove_self;
     int issuers;                  // MMA-issuing warps (1 or 2)
     int debug;                    // profiling aid (SNG_KNN_DEBUG): 1 = skip the max tree / inserts, 2 = skip the TMEM loads, 4 = skip the B loads
-    float* cand_val;              // [nq, nsplit*EW, cand]
-    int* cand_idx;                // [nq, nsplit*EW, cand]   (-1 = empty)
-    float* cand_min;              // [nq, nsplit*EW]  worst kept approx score if the list filled up, else -inf
+    float* cand_val;              // [nq, nsplit, cand]
+    int* cand_idx;                // [nq, nsplit, cand]   (-1 = empty)
+    float* cand_min;              // [nq, nsplit]  largest threshold the row's list pruned with, -inf if it never left thr_lo
     // threshold seeding (see "Seeding" below): the seed pass writes seed_out, the main pass reads seeds
     const float* seeds;           // [nq, kSeedGroups] group maxima over a 1/seed_stride column sample, or nullptr
     float* seed_out;              // SEED kernel only
     int seed_q, seed_stride;      // row threshold = seed_q-th largest group maximum; sample = every seed_stride-th column
-    long long* trace;             // SNG_KNN_TRACE: [64 tiles][4] clock64 stamps of cluster 0's leader CTA, else nullptr
+    long long* trace;             // SNG_KNN_TRACE: [64 tiles][8] clock64 stamps of cluster 0's leader CTA, else nullptr
 };
 
 // EW = epilogue warps per TMEM lane quarter; every epilogue thread owns one query row x (256/EW) columns of each tile
@@ -176,12 +182,21 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t rank = cluster_ctarank();                      // 0 = leader (issues the MMAs)
     const uint32_t a_off = 0;
     const uint32_t b_off = a_off + (uint32_t)p.kblocks * kTileBytes;
+    // per-ROW candidate lists (slot-major: slot s of row r at [s * BM + r]), their bookkeeping, and the hit queue
     const uint32_t list_off = b_off + (uint32_t)p.stages * kTileBytes;
-    const uint32_t thr_off = list_off + (uint32_t)EW * p.cand * BM * 8u;
-    const uint32_t bar_off = thr_off + BM * 4u;
+    const uint32_t thr_off = list_off + (uint32_t)p.cand * BM * 8u;
+    const uint32_t q_off = (thr_off + BM * 12u + 15u) & ~15u;         // row_thr, list_cnt, list_minpos; then the 16-byte aligned queue
+    const uint32_t bar_off = q_off + kQueue * 68u + 16u;             // entries (64 B), flags (4 B) + {q_head, q_tail, done}
     float* list_val = reinterpret_cast<float*>(smem + list_off);
-    int* list_idx = reinterpret_cast<int*>(smem + list_off + (size_t)EW * p.cand * BM * 4);
+    int* list_idx = reinterpret_cast<int*>(smem + list_off + (size_t)p.cand * BM * 4);
     volatile float* row_thr = reinterpret_cast<volatile float*>(smem + thr_off);
+    int* list_cnt = reinterpret_cast<int*>(smem + thr_off + BM * 4);
+    int* list_minpos = reinterpret_cast<int*>(smem + thr_off + BM * 8);
+    float4* q_ent = reinterpret_cast<float4*>(smem + q_off);         // entry e = q_ent[4e .. 4e+3]: 11 triple maxima, col0, row
+    volatile int* q_flag = reinterpret_cast<volatile int*>(smem + q_off + kQueue * 64);
+    unsigned* q_head = reinterpret_cast<unsigned*>(smem + q_off + kQueue * 68);
+    volatile unsigned* q_tail = reinterpret_cast<volatile unsigned*>(smem + q_off + kQueue * 68 + 4);
+    unsigned* q_done = reinterpret_cast<unsigned*>(smem + q_off + kQueue * 68 + 8);
     const uint32_t bar_full = base + bar_off;                       // [kMaxStages]  leader only: B K-block landed in both CTAs
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;           // [kMaxStages]  per CTA: MMAs that read the stage retired
     const uint32_t bar_a = bar_empty + 8 * kMaxStages;              // [1]           leader only: both A blocks landed
@@ -231,7 +246,11 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 tau = fmaxf(tau, cur);
             }
             row_thr[i] = tau;
+            list_cnt[i] = 0;
+            list_minpos[i] = 0;
         }
+        for (int i = lane; i < kQueue; i += 32) q_flag[i] = 0;
+        if (lane == 0) { *q_head = 0u; *q_tail = 0u; *q_done = 0u; }
     }
     tc_fence_before();
     __syncthreads();
@@ -239,6 +258,9 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     tc_fence_after();
     if (*tmem_slot != 0u) __trap();            // the CTA owns the SM, so all 512 columns start at 0; addresses below assume it
 
+    long long life_clk = 0; unsigned long long life_ns = 0;
+    const bool life = p.trace && threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2);
+    if (life) { life_clk = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(life_ns)); }
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs, whole warp, one lane issues)
         const bool issuer = elect_one();
@@ -288,11 +310,13 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 const uint32_t acc_phase = (uint32_t)((t - t_beg) >> 1) & 1u;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 4 + 0] = clock64();
+                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 8 + 0] = clock64();
                 const uint32_t tmem_d = (uint32_t)(acc * BN);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
+                    const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0 && kb == 0;
+                    if (trm) p.trace[(t - t_beg) * 8 + 4] = clock64();
                     const int ksteps = (kb == p.kblocks - 1) ? p.ksteps_last : (BK / kUmmaK);
                     // descriptors count 16-byte units: one 16 KiB tile = 1024 units, one K step (32 B) = 2 units
                     const uint64_t adesc = adesc0 + (uint64_t)(kb * (kTileBytes >> 4));
@@ -300,14 +324,98 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     if (issuer) {
                         for (int ks = 0; ks < ksteps; ++ks)
                             umma_f16_pair(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), kIdesc, (kb | ks) != 0 ? 1u : 0u);
+                        if (trm) p.trace[(t - t_beg) * 8 + 5] = clock64();
                         umma_commit_pair(bar_empty + 8 * stage);        // frees this B stage in both CTAs when the MMAs retire
+                        if (trm) p.trace[(t - t_beg) * 8 + 6] = clock64();
                         if (kb == p.kblocks - 1) umma_commit_pair(bar_tfull + 8 * acc);   // accumulator of tile t complete (both CTAs)
                     }
                     __syncwarp();
                     advance(1);
                 }
-                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 4 + 1] = clock64();
+                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 8 + 1] = clock64();
                 advance((p.issuers - 1) * p.kblocks);                   // the other issuer's tile
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ list warp: drains the hit queue into the per-row lists
+        // The epilogue warps only FILTER: a lane whose 32-score chunk beats the row threshold dumps the chunk's 11 column-triple
+        // maxima (already in registers from the max tree) into a shared-memory queue -- ~25 instructions -- and moves on.
+        // This warp owns the candidate lists, at column-TRIPLE granularity (stage 2 rescoring expands a triple into its 3
+        // columns).  Everything data dependent and slow happens here, off the warps whose pace gates the tensor pipe: an
+        // accumulator stage is reusable only once ALL 32 epilogue warps of the pair have drained it, and on a busy SM a
+        // dependent chain of ~150 instructions (the former in-line insert) costs ~1900 cycles, three tile periods.
+        if (!SEED) {
+            const int L = p.cand;
+            unsigned tail = 0;
+            while (true) {
+                const unsigned s = (tail + lane) & (kQueue - 1);
+                const unsigned ready = __ballot_sync(0xffffffffu, q_flag[s] != 0);
+                const int nr = ready == 0xffffffffu ? 32 : __ffs(~ready) - 1;       // leading published entries
+                if (nr == 0) {
+                    const unsigned done = *reinterpret_cast<volatile unsigned*>(q_done);
+                    const unsigned head = *reinterpret_cast<volatile unsigned*>(q_head);
+                    if (done == (unsigned)(4 * EW) && head == tail) break;
+                    __nanosleep(40);
+                    continue;
+                }
+                __threadfence_block();
+                const bool mine = lane < nr;
+                float m[12]; int row = -1 - lane, col0 = 0;                          // distinct sentinel rows for idle lanes
+                if (mine) {
+                    const float4 e0 = q_ent[4 * s], e1 = q_ent[4 * s + 1], e2 = q_ent[4 * s + 2], e3 = q_ent[4 * s + 3];
+                    m[0] = e0.x; m[1] = e0.y; m[2] = e0.z; m[3] = e0.w; m[4] = e1.x; m[5] = e1.y; m[6] = e1.z; m[7] = e1.w;
+                    m[8] = e2.x; m[9] = e2.y; m[10] = e2.z; col0 = __float_as_int(e2.w); row = __float_as_int(e3.x);
+                }
+                unsigned pending = __ballot_sync(0xffffffffu, mine);
+                while (pending) {                                                   // entries of one row are applied one at a time
+                    const unsigned same = __match_any_sync(0xffffffffu, row) & pending;
+                    const bool go = mine && ((pending >> lane) & 1u) && (__ffs(same) - 1 == lane);
+                    if (go) {
+                        float thr = row_thr[row];
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) {
+                            const float val = m[i];
+                            if (val > thr) {
+                                int c = list_cnt[row], slot;
+                                if (c < L) { slot = c; list_cnt[row] = ++c; }
+                                else slot = list_minpos[row];
+                                list_val[slot * BM + row] = val;
+                                list_idx[slot * BM + row] = col0 + 3 * i;
+                                if (c == L) {                                        // full: the minimum becomes the row's threshold
+                                    float mn = list_val[row]; int mp = 0;
+#pragma unroll 4
+                                    for (int s2 = 1; s2 < L; ++s2) { const float y = list_val[s2 * BM + row]; if (y < mn) { mn = y; mp = s2; } }
+                                    list_minpos[row] = mp;
+                                    if (mn > thr) { thr = mn; row_thr[row] = mn; }
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    pending &= ~__ballot_sync(0xffffffffu, go);
+                }
+                if (mine) q_flag[s] = 0;
+                __threadfence_block();
+                __syncwarp();
+                tail += (unsigned)nr;
+                if (lane == 0) *q_tail = tail;
+            }
+            // all epilogue warps are done and the queue is empty: emit the lists and the drop bounds
+            __threadfence_block();
+            const int lists = p.nsplit;
+            for (int i = lane; i < BM * L; i += 32) {
+                const int r = i / L, sl = i - r * L, grow = row0 + r;
+                if (grow < p.nq) {
+                    const size_t o = ((size_t)grow * lists + blockIdx.y) * L + sl;
+                    const bool ok = sl < list_cnt[r];
+                    p.cand_val[o] = ok ? list_val[sl * BM + r] : -CUDART_INF_F;
+                    p.cand_idx[o] = ok ? list_idx[sl * BM + r] : -1;
+                }
+            }
+            for (int r = lane; r < BM; r += 32) {
+                const int grow = row0 + r;
+                // bound on everything dropped for this row: the final threshold (seed, evictions and filtered columns included)
+                if (grow < p.nq) p.cand_min[(size_t)grow * lists + blockIdx.y] = row_thr[r] > p.thr_lo ? row_thr[r] : -CUDART_INF_F;
             }
         }
     } else if (warp >= 4) {
@@ -317,42 +425,27 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int r = quarter * 32 + lane;                        // row within the CTA == TMEM lane
         const int grow = row0 + r;
         const int self_col = p.remove_self ? (p.q_offset + grow) : -1;
-        const int L = p.cand, n = p.n;
-        float* lv = list_val + (size_t)slice * L * BM + r;         // slot s at lv[s * BM]
-        int* li = list_idx + (size_t)slice * L * BM + r;
-        int cnt = 0;
-        float thr_cur = p.thr_lo;                                  // max(own list minimum once full, shared row threshold)
+        const int n = p.n;
+        float thr_cur = p.thr_lo;                                  // the row's pruning threshold as last read from shared memory
+        long long ev_chunks = 0, ev_n = 0, ev_cyc = 0, ev_max = 0, ev_push = 0;   // SNG_KNN_TRACE statistics of warp 4 of CTA 0
         float gmax[2 * CT];                                        // SEED: running maxima of this thread's column groups
 #pragma unroll
         for (int i = 0; i < 2 * CT; ++i) gmax[i] = -CUDART_INF_F;
 
-        int minpos = 0;
-        auto insert = [&](float x, int col) {
-            if (col >= n || col == self_col) return;
-            int slot = minpos;
-            if (cnt < L) slot = cnt++;
-            lv[slot * BM] = x;
-            li[slot * BM] = col;
-            if (cnt == L) {                                          // list full: its minimum becomes this thread's threshold
-                float mn = lv[0]; int mp = 0;
-#pragma unroll 4
-                for (int s2 = 1; s2 < L; ++s2) { const float y = lv[s2 * BM]; if (y < mn) { mn = y; mp = s2; } }
-                minpos = mp;
-                if (mn > thr_cur) thr_cur = mn;
-                if (mn > row_thr[r]) row_thr[r] = mn;              // shared with the row's other threads (any value is safe, see below)
-            }
-        };
-        // Pruning thresholds are heuristics: ANY threshold is safe because every thread reports the largest threshold it
-        // ever pruned with (cand_min) and stage 2 only accepts a row whose k-th exact score clears all of them.
+        // Pruning thresholds are heuristics: ANY threshold is safe because the row reports the largest threshold anything
+        // was pruned with (cand_min) and stage 2 only accepts a row whose k-th exact score clears it.
         // `ci` = chunk index within the thread's tile slice (compile time after unrolling), `odd` = tile parity.
-        auto process = [&](const uint32_t (&v)[32], int col0, int ci, bool odd) {
-            if (p.debug) { if (__uint_as_float(v[0] ^ v[31]) == 12345.678f) thr_cur = 0.f; return; }
+        auto process = [&](uint32_t (&v)[32], int col0, int ci, bool odd) {
+            if (p.debug & 1) { if (__uint_as_float(v[0] ^ v[31]) == 12345.678f) thr_cur = 0.f; return; }
             float m[11];
+            auto tree = [&]() {
 #pragma unroll
-            for (int i = 0; i < 10; ++i) m[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
-            m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-            const float m0 = max3(m[0], m[1], m[2]), m1 = max3(m[3], m[4], m[5]), m2 = max3(m[6], m[7], m[8]);
-            float mx = max3(max3(m0, m1, m2), m[9], m[10]);
+                for (int i = 0; i < 10; ++i) m[i] = max3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+                m[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+                const float m0 = max3(m[0], m[1], m[2]), m1 = max3(m[3], m[4], m[5]), m2 = max3(m[6], m[7], m[8]);
+                return max3(max3(m0, m1, m2), m[9], m[10]);
+            };
+            float mx = tree();
             if (SEED) {
                 if (col0 + 32 > n) {                                 // last tile: zero-filled columns beyond n must not count
                     mx = -CUDART_INF_F;
@@ -363,33 +456,34 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 gmax[CT + ci] = fmaxf(gmax[CT + ci], odd ? mx : -CUDART_INF_F);
                 return;
             }
-            if (__any_sync(0xffffffffu, mx > thr_cur)) {           // rare, warp-uniform slow path (kept compact: one copy of insert)
-                uint32_t tm = 0;
+            const bool cnt_on = kEvTrace && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == kNonEpiThreads;
+            if (cnt_on) ++ev_chunks;
+            if (__any_sync(0xffffffffu, mx > thr_cur)) {           // rare slow path
+                const long long ev0 = cnt_on ? clock64() : 0;
+                if (p.debug & 8) return;
+                if ((unsigned)(self_col - col0) < 32u || col0 + 32 > n) {
+                    // the chunk holds the row's own column, or columns beyond n (zero filled): once per row / last tile only
 #pragma unroll
-                for (int i = 0; i < 11; ++i) tm |= (m[i] > thr_cur ? 1u : 0u) << i;
-                uint32_t todo = __reduce_or_sync(0xffffffffu, tm);  // triples of columns in which some lane has a hit
-                while (todo) {
-                    const int i = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    uint32_t x0, x1, x2;
-                    switch (i) {
-                        case 0: x0 = v[0]; x1 = v[1]; x2 = v[2]; break;
-                        case 1: x0 = v[3]; x1 = v[4]; x2 = v[5]; break;
-                        case 2: x0 = v[6]; x1 = v[7]; x2 = v[8]; break;
-                        case 3: x0 = v[9]; x1 = v[10]; x2 = v[11]; break;
-                        case 4: x0 = v[12]; x1 = v[13]; x2 = v[14]; break;
-                        case 5: x0 = v[15]; x1 = v[16]; x2 = v[17]; break;
-                        case 6: x0 = v[18]; x1 = v[19]; x2 = v[20]; break;
-                        case 7: x0 = v[21]; x1 = v[22]; x2 = v[23]; break;
-                        case 8: x0 = v[24]; x1 = v[25]; x2 = v[26]; break;
-                        case 9: x0 = v[27]; x1 = v[28]; x2 = v[29]; break;
-                        default: x0 = v[30]; x1 = v[31]; x2 = 0xff800000u; break;
-                    }
-#pragma unroll 1
-                    for (int e = 0; e < 3; ++e) {
-                        const float x = __uint_as_float(e == 0 ? x0 : (e == 1 ? x1 : x2));
-                        if (x > thr_cur) insert(x, col0 + 3 * i + e);
-                    }
+                    for (int i = 0; i < 32; ++i) if (col0 + i == self_col || col0 + i >= n) v[i] = 0xff800000u;
+                    mx = tree();
+                }
+                if (mx > thr_cur) {                                  // hit lanes only: dump the triple maxima for the list warp
+                    const unsigned at = atomicAdd(q_head, 1u);
+                    while ((int)(at - *q_tail) >= kQueue) __nanosleep(20);           // queue full: wait for the list warp
+                    const unsigned s = at & (kQueue - 1);
+                    q_ent[4 * s] = make_float4(m[0], m[1], m[2], m[3]);
+                    q_ent[4 * s + 1] = make_float4(m[4], m[5], m[6], m[7]);
+                    q_ent[4 * s + 2] = make_float4(m[8], m[9], m[10], __int_as_float(col0));
+                    q_ent[4 * s + 3] = make_float4(__int_as_float(r), 0.f, 0.f, 0.f);
+                    __threadfence_block();
+                    q_flag[s] = 1;                                                   // publishes the entry
+                    if (cnt_on) ++ev_push;
+                }
+                __syncwarp();
+                thr_cur = fmaxf(thr_cur, row_thr[r]);                // the list warp may already have raised it
+                if (cnt_on) {
+                    const long long dt = clock64() - ev0;
+                    ++ev_n; ev_cyc += dt; ev_max = dt > ev_max ? dt : ev_max;
                 }
             }
         };
@@ -400,7 +494,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && threadIdx.x == kNonEpiThreads;
-            if (tr) p.trace[(t - t_beg) * 4 + 2] = clock64();
+            if (tr) p.trace[(t - t_beg) * 8 + 2] = clock64();
             if (!SEED) thr_cur = fmaxf(thr_cur, row_thr[r]);
             const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * CPT);
             const int col0 = t * BN + slice * CPT;
@@ -415,7 +509,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
-                if (tr) p.trace[(t - t_beg) * 4 + 3] = clock64();
+                if (tr) p.trace[(t - t_beg) * 8 + 3] = clock64();
                 process(va, col0, 0, odd);
                 process(vb, col0 + 32, CT > 1 ? 1 : 0, odd);
             } else {
@@ -445,19 +539,22 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 for (int i = 0; i < 2 * CT; ++i)
                     p.seed_out[(size_t)grow * kSeedGroups + (i / CT) * 8 + slice * CT + (i % CT)] = gmax[i];
             }
-        } else if (grow < p.nq) {
-            const int lists = p.nsplit * EW, li_id = (int)blockIdx.y * EW + slice;
-            const size_t o = ((size_t)grow * lists + li_id) * L;
-            for (int s = 0; s < L; ++s) {
-                p.cand_val[o + s] = s < cnt ? lv[s * BM] : -CUDART_INF_F;
-                p.cand_idx[o + s] = s < cnt ? li[s * BM] : -1;
+        } else {
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) atomicAdd(q_done, 1u);                    // this warp will push nothing more
+            if (kEvTrace && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == kNonEpiThreads) {
+                p.trace[525] = ev_chunks; p.trace[520] = ev_n; p.trace[521] = ev_push; p.trace[526] = ev_cyc; p.trace[527] = ev_max;
             }
-            // bound on everything this thread ever dropped: the largest threshold it pruned with (its own evictions included)
-            p.cand_min[(size_t)grow * lists + li_id] = thr_cur > p.thr_lo ? thr_cur : -CUDART_INF_F;
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (life) {
+        unsigned long long ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        long long* o = p.trace + 512 + (blockIdx.x == 0 ? 0 : 4);
+        o[0] = clock64() - life_clk; o[1] = (long long)(ns1 - life_ns); o[2] = t_end - t_beg; o[3] = blockIdx.x;
+    }
     cluster_sync_all();                        // neither CTA may exit (or free TMEM) while the other can still signal / write it
     if (warp == 2) {
         tc_fence_after();
@@ -478,25 +575,31 @@ __device__ __forceinline__ float dot_seq(const float* __restrict__ a, const floa
 }
 __device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
 
-// Stage 2: one warp per query row.  Rescore the nsplit*cand candidates exactly, order them by (score desc,
-// index asc), apply thr / top_k, and prove that no dropped column could belong to the answer.
+// Stage 2: one warp per query row.  Every candidate is a column triple {c, c+1, c+2} (two columns when c % 32 == 30, the
+// last triple of a 32-column chunk).  Rescore all their columns exactly, order them by (score desc, index asc), apply
+// thr / top_k, and prove that no dropped column could belong to the answer.
 __global__ void __launch_bounds__(256) simknn_rescore_kernel(
-    const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int nq, int m_total, int nsplit, int top_k, float thr,
-    float eps, const float* __restrict__ cand_val, const int* __restrict__ cand_idx, const float* __restrict__ cand_min,
+    const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int nq, int n, int q_offset, int remove_self, int m_total,
+    int nsplit, int top_k, float thr, float eps, const int* __restrict__ cand_idx, const float* __restrict__ cand_min,
     int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out, int* __restrict__ fb_rows, int* __restrict__ n_fallback) {
     extern __shared__ float sm2[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sc = sm2 + (size_t)warp * 2 * m_total;
-    int* id = reinterpret_cast<int*>(sc + m_total);
+    const int m3 = 3 * m_total;
+    float* sc = sm2 + (size_t)warp * 2 * m3;
+    int* id = reinterpret_cast<int*>(sc + m3);
     for (int row = blockIdx.x * 8 + warp; row < nq; row += gridDim.x * 8) {
         const float* a = xq + (int64_t)row * ld32;
+        const int self_col = remove_self ? q_offset + row : -1;
         int nvalid = 0;
-        for (int m0 = 0; m0 < m_total; m0 += 32) {
+        for (int m0 = 0; m0 < m3; m0 += 32) {
             const int m = m0 + lane;
             int j = -1; float s = -CUDART_INF_F;
-            if (m < m_total) {
-                j = __ldg(cand_idx + (size_t)row * m_total + m);
-                if (j >= 0) s = dot_seq(a, xall + (int64_t)j * ld32, d4);
+            if (m < m3) {
+                const int base = __ldg(cand_idx + (size_t)row * m_total + m / 3), e = m % 3;
+                if (base >= 0 && (e < 2 || (base & 31) != 30) && base + e < n && base + e != self_col) {
+                    j = base + e;
+                    s = dot_seq(a, xall + (int64_t)j * ld32, d4);
+                }
                 sc[m] = s; id[m] = j;
             }
             nvalid += __popc(__ballot_sync(0xffffffffu, j >= 0 && s >= thr));
@@ -504,14 +607,14 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
         __syncwarp();
         const int cnt = min(nvalid, top_k);
         float kth = thr;                                            // cut value: k-th exact score, or thr if fewer than k qualify
-        for (int m0 = 0; m0 < m_total; m0 += 32) {
+        for (int m0 = 0; m0 < m3; m0 += 32) {
             const int m = m0 + lane;
             int rank = 0x7fffffff; float s = 0.f; int j = -1;
-            if (m < m_total) {
+            if (m < m3) {
                 s = sc[m]; j = id[m];
                 if (j >= 0 && s >= thr) {
                     rank = 0;
-                    for (int o = 0; o < m_total; ++o) rank += (id[o] >= 0 && better(sc[o], id[o], s, j)) ? 1 : 0;
+                    for (int o = 0; o < m3; ++o) rank += (id[o] >= 0 && better(sc[o], id[o], s, j)) ? 1 : 0;
                 }
             }
             if (rank < top_k) {
@@ -735,7 +838,7 @@ struct Plan {
     int ew, stages, cand, nsplit, kblocks, ksteps_last, tiles;
     int seed_stride, seed_q;      // 0 = no seed pass
     size_t smem;
-    int lists() const { return nsplit * ew; }
+    int lists() const { return nsplit; }          // one candidate list per (row, column split)
 };
 
 // Smallest q with P(Binomial(top_k, 1/stride) >= q) <= tol: the chance that q of a row's true top_k landed in the sample.
@@ -753,7 +856,9 @@ static int seed_quantile(int top_k, int stride, double tol) {
 }
 
 static size_t smem_bytes(int ew, int kblocks, int stages, int cand) {
-    return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)ew * cand * BM * 8 + BM * 4 + 8 * (2 * kMaxStages + 5) + 16;
+    (void)ew;
+    return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)cand * BM * 8 + BM * 12 + 16 + kQueue * 68 + 16 +
+           8 * (2 * kMaxStages + 5) + 16;
 }
 
 static int env_int(const char* name, int lo, int hi) {       // tuning overrides for experiments
@@ -763,15 +868,14 @@ static int env_int(const char* name, int lo, int hi) {       // tuning overrides
     return (v >= lo && v <= hi) ? v : 0;
 }
 
-// Candidate slots per list.  Every list keeps its best `cand` FP16 scores; stage 2 proves a row only if its k-th exact
-// score clears every list's drop bound by the FP16 error, so cand - top_k is the number of near-cut columns one column
-// slice may hold before the row has to go to the exact scan.
+// Candidate slots per row list.  The list keeps the row's best `cand` FP16 scores; stage 2 proves a row only if its k-th
+// exact score clears the list's drop bound by the FP16 error, so cand - top_k is the number of near-cut columns a row may
+// have before it has to go to the exact scan.
 static int cand_for(int top_k, int ew) {
+    (void)ew;
     const int o = env_int("SNG_KNN_CAND", top_k, 128);
     if (o) return o;
-    int c = top_k + (ew >= 4 ? 4 : (ew == 2 ? 10 : 16));
-    if (c < 14) c = 14;
-    return (c + 1) / 2 * 2;
+    return (top_k + 22 + 1) / 2 * 2;
 }
 
 // top_k > 0: derive cand from top_k;  top_k == 0: use the explicit `cand` (stage-1 test entry point)
@@ -788,7 +892,7 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     for (int pass = 0; pass < 2 && !pl->ew; ++pass) {
         for (int ew = force_ew ? force_ew : ew_pref; ew >= 1 && !pl->ew; ew >>= 1) {
             const int c = top_k > 0 ? cand_for(top_k, ew) : cand;
-            if (ew * c <= kMaxCandTotal) {
+            if (c <= kMaxCandTotal) {
                 int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
                 if (env_int("SNG_KNN_STAGES", 2, kMaxStages)) want = env_int("SNG_KNN_STAGES", 2, kMaxStages);
                 for (int st = want; st >= (pass ? 2 : 3); --st) {
@@ -807,7 +911,7 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     int ns = (int)((3ll * sms + ctas - 1) / ctas);
     if (ns > 8) ns = 8;
     if (ns > pl->tiles) ns = pl->tiles;
-    while (ns > 1 && ns * pl->ew * pl->cand > kMaxCandTotal) --ns;
+    while (ns > 1 && ns * pl->cand > kMaxCandTotal) --ns;
     if (ns < 1) ns = 1;
     pl->nsplit = ns;
     // threshold seeding: only for full builds (top_k known) that sweep many tiles with one list set per row
@@ -845,15 +949,15 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
     p.nq = (int)nq; p.n = (int)n_db; p.q_offset = (int)q_offset;
     p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = seed_pass ? 0 : pl.cand;
     p.nsplit = seed_pass ? 1 : pl.nsplit; p.tiles_total = (int)((n_db + BN - 1) / BN); p.thr_lo = thr_lo; p.remove_self = remove_self;
-    p.debug = env_int("SNG_KNN_DEBUG", 1, 7);
+    p.debug = env_int("SNG_KNN_DEBUG", 1, 63);
     p.issuers = env_int("SNG_KNN_ISSUERS", 1, 2) ? env_int("SNG_KNN_ISSUERS", 1, 2) : (pl.kblocks <= 3 ? 2 : 1);
     p.cand_val = cand_val; p.cand_idx = cand_idx; p.cand_min = cand_min;
     p.seeds = seed_pass ? nullptr : seeds; p.seed_out = seed_out; p.seed_q = pl.seed_q; p.seed_stride = pl.seed_stride > 0 ? pl.seed_stride : 1;
     dim3 grid((unsigned)(2 * ((nq + 2 * BM - 1) / (2 * BM))), (unsigned)p.nsplit);        // x: CTA pairs (cluster of 2), y: column splits
     p.trace = nullptr;
     if (getenv("SNG_KNN_TRACE") && !seed_pass) {              // debugging aid only: allocates, synchronises and prints
-        cudaMalloc(&p.trace, 64 * 4 * sizeof(long long));
-        cudaMemset(p.trace, 0, 64 * 4 * sizeof(long long));
+        cudaMalloc(&p.trace, (64 * 8 + 16) * sizeof(long long));
+        cudaMemset(p.trace, 0, (64 * 8 + 16) * sizeof(long long));
     }
     cudaError_t e;
     if (seed_pass) e = pl.ew == 4 ? launch_ew<4, true>(grid, pl.smem, st, mq, mdb, p)
@@ -864,13 +968,21 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
                         : launch_ew<1, false>(grid, pl.smem, st, mq, mdb, p);
     if (e != cudaSuccess) { cudaGetLastError(); set_error("simknn stage 1: cudaFuncSetAttribute(%zu B smem): %s", pl.smem, cudaGetErrorString(e)); return SNG_ERR_CUDA; }
     if (p.trace) {
-        long long h[64 * 4];
+        long long h[64 * 8 + 16];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
         cudaFree(p.trace);
-        fprintf(stderr, "tile  mma:tempty_ok  mma:issued  epi:tfull_ok  epi:released   (cycles since tile 0's tempty_ok)\n");
+        fprintf(stderr, "tile  mma:tempty_ok  full0_ok  mmas0_issued  commit0_done  mma:issued  epi:tfull_ok  epi:released   (cycles since tile 0's tempty_ok)\n");
         for (int t = 0; t < 64; ++t)
-            fprintf(stderr, "%4d %10lld %10lld %10lld %10lld\n", t, h[4 * t] - h[0], h[4 * t + 1] - h[0], h[4 * t + 2] - h[0], h[4 * t + 3] - h[0]);
+            fprintf(stderr, "%4d %10lld %10lld %10lld %10lld %10lld %10lld %10lld\n", t, h[8 * t] - h[0], h[8 * t + 4] - h[0], h[8 * t + 5] - h[0],
+                    h[8 * t + 6] - h[0], h[8 * t + 1] - h[0], h[8 * t + 2] - h[0], h[8 * t + 3] - h[0]);
+        fprintf(stderr, "CTA 0 warp 4: %lld warp-chunks, %lld slow-path events, %lld pushes (%lld %lld %lld); "
+                "event cycles: mean %.0f max %lld\n", h[525], h[520], h[521], h[522], h[523], h[524], (double)h[526] / (double)(h[520] > 0 ? h[520] : 1), h[527]);
+        for (int c = 0; c < 2; ++c) {
+            const long long* o = h + 512 + 4 * c;
+            if (o[1] > 0) fprintf(stderr, "CTA %lld lifetime: %lld cycles, %lld ns -> %.0f MHz, %lld tiles, %.0f cycles/tile\n", o[3], o[0], o[1],
+                                  1e3 * (double)o[0] / (double)o[1], o[2], (double)o[0] / (double)(o[2] > 0 ? o[2] : 1));
+        }
     }
     return check_launch(seed_pass ? "simknn seed pass" : "simknn stage 1");
 }
@@ -979,8 +1091,9 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     const int d4 = (int)((d + 3) / 4);
     {
         const int blocks = (int)((nq + 7) / 8 < (int64_t)sm_count() * 8 ? (nq + 7) / 8 : (int64_t)sm_count() * 8);
-        simknn_rescore_kernel<<<blocks > 0 ? blocks : 1, 256, (size_t)8 * 2 * m_total * 4, st>>>(
-            xq32, xall32, ld32, d4, (int)nq, m_total, pl.lists(), top_k, thr, kScoreEps, cand_val, cand_idx, cand_min, idx, sim, cnt, fb_rows, n_fallback);
+        simknn_rescore_kernel<<<blocks > 0 ? blocks : 1, 256, (size_t)8 * 2 * 3 * m_total * 4, st>>>(
+            xq32, xall32, ld32, d4, (int)nq, (int)n, (int)q_offset, remove_self, m_total, pl.lists(), top_k, thr, kScoreEps, cand_idx, cand_min,
+            idx, sim, cnt, fb_rows, n_fallback);
         if (int rc = check_launch("simknn stage 2")) return rc;
     }
     const int fb_grid = (sm_count() > 0 ? sm_count() : 148) * 4;

@@ -95,7 +95,7 @@ def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_
     xf, xh = normalize_operands(x)
     n, d = x.shape
     dev = x.device
-    slots = 512                                              # lists * cand never exceeds this (kMaxCandTotal)
+    slots = 192                                              # lists * cand never exceeds this (kMaxCandTotal)
     ci = torch.empty(n * slots, dtype=torch.int32, device=dev)
     cv = torch.empty(n * slots, dtype=torch.float32, device=dev)
     cm = torch.empty(n * 64, dtype=torch.float32, device=dev)
