@@ -160,6 +160,57 @@ struct Stage1Params {
     long long* trace;             // SNG_KNN_TRACE: [64 tiles][8] clock64 stamps of cluster 0's leader CTA, else nullptr
 };
 
+// MMA issue loop of the SPLIT (four 128-column accumulator stages) mode for issuer W of NI, kblocks <= 2.  W / NI are compile
+// time so that every address, descriptor and ring index below is provably warp-uniform and stays in uniform registers: on a
+// busy SM the issuer's dependent instruction chain, not the tensor pipe, sets the tile period (SNG_KNN_TRACE).
+template <int W, int NI>
+__device__ __forceinline__ void issue_split(const Stage1Params& p, uint32_t base, uint32_t a_off, uint32_t b_off, uint32_t bar_full, uint32_t bar_empty,
+                                            uint32_t bar_tfull, uint32_t bar_tempty, int t_beg, int t_end, bool issuer, int lane) {
+    constexpr uint32_t kIdescHalf = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint64_t adesc0 = make_smem_desc(base + a_off);
+    const uint64_t bdesc0 = make_smem_desc(base + b_off);
+    const int kb2 = p.kblocks == 2;                          // second K block present
+    const int ks0 = kb2 ? 4 : p.ksteps_last;                 // K steps of block 0
+    const int ks1 = kb2 ? p.ksteps_last : 0;                 // K steps of block 1
+    const int nst = p.stages, step = NI * p.kblocks;
+    int st0 = (W * p.kblocks) % nst;                         // ring slot of this tile's K block 0
+    uint32_t ph0 = (uint32_t)((W * p.kblocks) / nst) & 1u;
+    for (int tt = W; tt < t_end - t_beg; tt += NI) {
+        int st1 = st0 + 1; uint32_t ph1 = ph0;
+        if (st1 == nst) { st1 = 0; ph1 ^= 1u; }
+        const uint32_t acc_phase = (uint32_t)(tt >> 1) & 1u;
+        const int acc0 = 2 * (tt & 1);
+        const uint64_t b0 = bdesc0 + (uint64_t)(st0 * (kTileBytes >> 4)), b1 = bdesc0 + (uint64_t)(st1 * (kTileBytes >> 4));
+        mbar_wait(bar_full + 8 * st0, ph0);
+        if (kb2) mbar_wait(bar_full + 8 * st1, ph1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar_tempty + 8 * (acc0 + h), acc_phase ^ 1);
+            tc_fence_after();
+            if (h == 0 && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 0] = clock64();
+            const uint32_t tmem_d = (uint32_t)((acc0 + h) * 128);
+            const uint64_t hb = (uint64_t)(h * (kTileBytes >> 5));                       // + 64 rows x 128 B
+            if (issuer) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    if (ks < ks0) umma_f16_pair(tmem_d, adesc0 + (uint64_t)(ks * 2), b0 + hb + (uint64_t)(ks * 2), kIdescHalf, ks != 0 ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    if (ks < ks1) umma_f16_pair(tmem_d, adesc0 + (uint64_t)((kTileBytes >> 4) + ks * 2), b1 + hb + (uint64_t)(ks * 2), kIdescHalf, 1u);
+                if (h == 1) {                                                            // both halves read: free the B stage(s)
+                    umma_commit_pair(bar_empty + 8 * st0);
+                    if (kb2) umma_commit_pair(bar_empty + 8 * st1);
+                }
+                umma_commit_pair(bar_tfull + 8 * (acc0 + h));
+            }
+            __syncwarp();
+        }
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 1] = clock64();
+        st0 += step;
+        while (st0 >= nst) { st0 -= nst; ph0 ^= 1u; }
+    }
+}
+
 // EW = epilogue warps per TMEM lane quarter; every epilogue thread owns one query row x (256/EW) columns of each tile
 // and its own candidate list; the EW threads of a row share one pruning threshold.
 //
@@ -174,6 +225,11 @@ template <int EW, bool SEED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNonEpiThreads + 128 * EW, 1)
 simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const Stage1Params p) {
     constexpr int CPT = BN / EW;                                  // columns per thread per tile
+    // SPLIT (EW == 4, i.e. small K): a 256-column tile is computed as two N = 128 halves into FOUR 128-column accumulator
+    // stages.  With only two stages, the hand-back of a stage (tcgen05.commit -> epilogue loads -> remote arrive -> issuer)
+    // sits on the critical path of every tile and any late epilogue warp stalls the tensor pipe; with four, each issuer owns
+    // two stages and a stage is not needed again for a whole tile period after it was drained.
+    constexpr bool SPLIT = (EW == 4);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -200,9 +256,9 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t bar_full = base + bar_off;                       // [kMaxStages]  leader only: B K-block landed in both CTAs
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;           // [kMaxStages]  per CTA: MMAs that read the stage retired
     const uint32_t bar_a = bar_empty + 8 * kMaxStages;              // [1]           leader only: both A blocks landed
-    const uint32_t bar_tfull = bar_a + 8;                           // [2]           per CTA: accumulator stage complete
-    const uint32_t bar_tempty = bar_tfull + 16;                     // [2]           leader only: both CTAs drained the stage
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 8 * (2 * kMaxStages + 5));
+    const uint32_t bar_tfull = bar_a + 8;                           // [4]           per CTA: accumulator stage complete
+    const uint32_t bar_tempty = bar_tfull + 32;                     // [4]           leader only: both CTAs drained the stage
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bar_off + 8 * (2 * kMaxStages + 9));
 
     const int row0 = (int)blockIdx.x * BM;                          // blockIdx.x = 2 * pair + rank
     const int t_beg = (int)(((long long)p.tiles_total * blockIdx.y) / p.nsplit);
@@ -211,7 +267,8 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_a, 2);
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 2 * 4 * EW); }
+        // SPLIT: four 128-column accumulator stages, each drained by 8 warps per CTA; else two 256-column stages, 4*EW warps each
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, SPLIT ? 16 : 2 * 4 * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -305,6 +362,11 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             int stage = 0; uint32_t phase = 0;
             auto advance = [&](int steps) { for (int i = 0; i < steps; ++i) if (++stage == p.stages) { stage = 0; phase ^= 1; } };
             advance(w * p.kblocks);
+            if constexpr (SPLIT) {
+                if (p.issuers == 1) issue_split<0, 1>(p, base, a_off, b_off, bar_full, bar_empty, bar_tfull, bar_tempty, t_beg, t_end, issuer, lane);
+                else if (warp == 1) issue_split<0, 2>(p, base, a_off, b_off, bar_full, bar_empty, bar_tfull, bar_tempty, t_beg, t_end, issuer, lane);
+                else issue_split<1, 2>(p, base, a_off, b_off, bar_full, bar_empty, bar_tfull, bar_tempty, t_beg, t_end, issuer, lane);
+            } else {
             for (int t = t_beg + w; t < t_end; t += p.issuers) {
                 const int acc = (t - t_beg) & 1;
                 const uint32_t acc_phase = (uint32_t)((t - t_beg) >> 1) & 1u;
@@ -315,8 +377,6 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0 && kb == 0;
-                    if (trm) p.trace[(t - t_beg) * 8 + 4] = clock64();
                     const int ksteps = (kb == p.kblocks - 1) ? p.ksteps_last : (BK / kUmmaK);
                     // descriptors count 16-byte units: one 16 KiB tile = 1024 units, one K step (32 B) = 2 units
                     const uint64_t adesc = adesc0 + (uint64_t)(kb * (kTileBytes >> 4));
@@ -324,9 +384,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     if (issuer) {
                         for (int ks = 0; ks < ksteps; ++ks)
                             umma_f16_pair(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), kIdesc, (kb | ks) != 0 ? 1u : 0u);
-                        if (trm) p.trace[(t - t_beg) * 8 + 5] = clock64();
                         umma_commit_pair(bar_empty + 8 * stage);        // frees this B stage in both CTAs when the MMAs retire
-                        if (trm) p.trace[(t - t_beg) * 8 + 6] = clock64();
                         if (kb == p.kblocks - 1) umma_commit_pair(bar_tfull + 8 * acc);   // accumulator of tile t complete (both CTAs)
                     }
                     __syncwarp();
@@ -334,6 +392,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 }
                 if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 8 + 1] = clock64();
                 advance((p.issuers - 1) * p.kblocks);                   // the other issuer's tile
+            }
             }
         }
     } else if (warp == 3) {
@@ -488,16 +547,21 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
         };
 
-        int acc = 0; uint32_t acc_phase = 0;
         uint32_t va[32], vb[32];
+        // columns of the tile this thread owns: [tile_col, tile_col + CPT) -- SPLIT: 64 columns of half h = slice & 1, taken from
+        // CTA (slice >> 1)'s staged rows, i.e. accumulator columns [64 (slice >> 1), +64) of stage 2 * (tile parity) + h
+        const int tile_col = SPLIT ? 128 * (slice >> 1) + 64 * (slice & 1) : slice * CPT;
         for (int t = t_beg; t < t_end; ++t) {
+            const int tt = t - t_beg;
+            const int acc = SPLIT ? 2 * (tt & 1) + (slice & 1) : (tt & 1);
+            const uint32_t acc_phase = (uint32_t)(tt >> 1) & 1u;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && threadIdx.x == kNonEpiThreads;
             if (tr) p.trace[(t - t_beg) * 8 + 2] = clock64();
             if (!SEED) thr_cur = fmaxf(thr_cur, row_thr[r]);
-            const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * CPT);
-            const int col0 = t * BN + slice * CPT;
+            const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(SPLIT ? acc * 128 + (slice >> 1) * 64 : acc * BN + slice * CPT);
+            const int col0 = t * BN + tile_col;
             const bool odd = (t & 1) != 0;
             if (CPT == 64) {
                 // both loads in flight at once; the accumulator stage goes back to the MMA warp before any processing
@@ -530,14 +594,13 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     process(vb, col0 + (c + 1) * 32, c + 1, odd);
                 }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (SEED) {
             if (grow < p.nq) {
                 // group id of sample column cs = ((cs >> 8) & 1) * 8 + ((cs & 255) >> 5)  (tile parity, chunk of the tile)
 #pragma unroll
                 for (int i = 0; i < 2 * CT; ++i)
-                    p.seed_out[(size_t)grow * kSeedGroups + (i / CT) * 8 + slice * CT + (i % CT)] = gmax[i];
+                    p.seed_out[(size_t)grow * kSeedGroups + (i / CT) * 8 + (tile_col >> 5) + (i % CT)] = gmax[i];
             }
         } else {
             __syncwarp();
@@ -858,7 +921,7 @@ static int seed_quantile(int top_k, int stride, double tol) {
 static size_t smem_bytes(int ew, int kblocks, int stages, int cand) {
     (void)ew;
     return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)cand * BM * 8 + BM * 12 + 16 + kQueue * 68 + 16 +
-           8 * (2 * kMaxStages + 5) + 16;
+           8 * (2 * kMaxStages + 9) + 16;
 }
 
 static int env_int(const char* name, int lo, int hi) {       // tuning overrides for experiments
@@ -972,7 +1035,7 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
         cudaStreamSynchronize(st);
         cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost);
         cudaFree(p.trace);
-        fprintf(stderr, "tile  mma:tempty_ok  full0_ok  mmas0_issued  commit0_done  mma:issued  epi:tfull_ok  epi:released   (cycles since tile 0's tempty_ok)\n");
+        fprintf(stderr, "tile  mma:tempty_ok  [4]  [5]  [6]  mma:issued  epi:tfull_ok  epi:released   (cycles since tile 0's tempty_ok; split mode: [4] = half 0 issued, [5] = half 1 stage free)\n");
         for (int t = 0; t < 64; ++t)
             fprintf(stderr, "%4d %10lld %10lld %10lld %10lld %10lld %10lld %10lld\n", t, h[8 * t] - h[0], h[8 * t + 4] - h[0], h[8 * t + 5] - h[0],
                     h[8 * t + 6] - h[0], h[8 * t + 1] - h[0], h[8 * t + 2] - h[0], h[8 * t + 3] - h[0]);
