@@ -9,6 +9,7 @@
 #include "sng_common.cuh"
 #include <cuda_fp16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace sng {
 
@@ -196,6 +197,154 @@ __global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
             const float invd = 1.0f / (float)max(end - beg, 1);
             *reinterpret_cast<float4*>(out + (int64_t)row * ldo + q * 4) = scale4(acc, invd);
         }
+    }
+}
+
+// K2 forward, selection variant (top_k <= 32).  One warp per target row, 32 in-edges per chunk.  A group of G = C/4 lanes
+// fetches one source row per step with one 128-bit load per lane (32/G full rows per warp step, G steps per chunk), and
+// the G partial dot products a lane then holds are reduced ACROSS its group with a transposing butterfly (G-1 shuffles
+// instead of G log2 G), which leaves every lane with the finished score of exactly one edge -- the edge whose source id
+// and 1/norm it loaded in the first place.  The running top-k lives in registers (lane t = rank t).  The first chunk is
+// ranked by top_k rounds of a one-instruction warp max; later chunks only insert the candidates that beat the k-th score.
+// The <= top_k winners are re-gathered at the end (L1 hits), so nothing of a chunk has to stay live across chunks.
+template <int G, bool PF, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) edge_topk_sel_fwd_kernel(
+    const float* __restrict__ h, const float* __restrict__ inv_r, int n, int row_offset, int c, int ldh, const int* __restrict__ rowptr,
+    const int* __restrict__ col, int top_k, float thr, float* __restrict__ out, int ldo,
+    int* __restrict__ sel_src, float* __restrict__ sel_w, int* __restrict__ sel_cnt) {
+    constexpr int EPW = 32 / G;                 // edges per warp step
+    constexpr int UB = G < 8 ? G : 8;           // steps whose loads are issued together
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G;
+    const int my_e = q * EPW + grp;             // the edge of a chunk this lane owns: fetched at step q by group grp
+    const bool ch_ok = q * 4 < c;
+    const float* hb = h + (ch_ok ? q * 4 : 0);  // lanes beyond the channel count read channel 0 and contribute zeros
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // The row's metadata (rowptr pair, first chunk of source ids) is fetched one row ahead, so the dependent chain of a row
+    // is just gather -> select -> re-gather instead of rowptr -> col -> gather -> ...
+    const int stride = gridDim.x * kWarpsPerBlock;
+    int row = blockIdx.x * kWarpsPerBlock + warp;
+    int beg = 0, end = 0, jl0 = 0;
+    if (row < n) {
+        beg = __ldg(rowptr + row); end = __ldg(rowptr + row + 1);
+        jl0 = my_e < end - beg ? __ldg(col + beg + my_e) : row_offset + row;
+    }
+    for (; row < n; row += stride) {
+        const int grow = row_offset + row;
+        const int nrow = row + stride;
+        int nbeg = 0, nend = 0, njl = 0;
+        if (PF && nrow < n) { nbeg = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1); }
+        float4 ni = scale4(ldg4(hb + (int64_t)grow * ldh), __ldg(inv_r + grow));     // target row, normalised
+        if (!ch_ok) ni = z4;
+        float ls = 0.f; int lj = -1;            // rank `lane` of the running top-k
+        int cnt = 0; float kth = -CUDART_INF_F; // entries in the list; score of rank top_k-1 once full
+
+        for (int base = beg; base < end; base += 32) {
+            const int nchunk = min(32, end - base);
+            const bool has = my_e < nchunk;
+            const int jl = base == beg ? jl0 : (has ? __ldg(col + base + my_e) : grow);   // missing edges read the target row itself
+            const float irl = __ldg(inv_r + jl);
+            float d[G];
+#pragma unroll
+            for (int u0 = 0; u0 < G; u0 += UB) {
+                float4 v[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int j = __shfl_sync(0xffffffffu, jl, grp * G + u0 + u);     // owner of edge (u0+u)*EPW + grp
+                    v[u] = (u0 + u) * EPW < nchunk ? ldg4(hb + (int64_t)j * ldh) : z4;
+                }
+                if (PF && u0 == 0 && base == beg && nrow < n)                              // next row's source ids, behind this row's gathers
+                    njl = my_e < nend - nbeg ? __ldg(col + nbeg + my_e) : row_offset + nrow;
+#pragma unroll
+                for (int u = 0; u < UB; ++u) d[u0 + u] = dot4(ni, v[u]);
+            }
+            // transposing reduction over the group: lane q ends up with sum over the group of d[q]
+#pragma unroll
+            for (int o = G / 2; o >= 1; o >>= 1) {
+                const bool up = (q & o) != 0;
+#pragma unroll
+                for (int i = 0; i < o; ++i) {
+                    const float send = up ? d[i] : d[i + o];
+                    const float keep = up ? d[i + o] : d[i];
+                    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            const float my_s = d[0] * irl + 0.0f;                                    // + 0: -0 becomes +0, equal scores get equal keys
+            const bool cand = has && my_s >= thr && (cnt < top_k || my_s > kth);
+            const unsigned ub = __float_as_uint(my_s);
+            unsigned key = cand ? ((ub & 0x80000000u) ? ~ub : (ub | 0x80000000u)) : 0u;   // order-preserving image; 0 = not a candidate
+            if (cnt == 0) {
+                // empty list (the row's first, usually only, chunk): candidates come out in rank order, so rank t goes to lane t
+                int t = 0;
+                for (; t < top_k; ++t) {
+                    const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+                    if (mx == 0u) break;
+                    const unsigned m = __ballot_sync(0xffffffffu, key == mx);
+                    int w = __ffs(m) - 1;
+                    if (m & (m - 1)) {                                               // exact tie: the lowest edge position wins
+                        const unsigned emin = __reduce_min_sync(0xffffffffu, key == mx ? (unsigned)my_e : 64u);
+                        w = __ffs(__ballot_sync(0xffffffffu, key == mx && (unsigned)my_e == emin)) - 1;
+                    }
+                    const float sw = __shfl_sync(0xffffffffu, my_s, w);
+                    const int jw = __shfl_sync(0xffffffffu, jl, w);
+                    if (lane == w) key = 0u;
+                    if (lane == t) { ls = sw; lj = jw; }
+                }
+                cnt = t;
+                if (cnt == top_k) kth = __shfl_sync(0xffffffffu, ls, top_k - 1);
+                continue;
+            }
+            while (true) {
+                const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+                if (mx == 0u) break;
+                unsigned m = __ballot_sync(0xffffffffu, key == mx);
+                int w = __ffs(m) - 1;
+                if (m & (m - 1)) {                                                   // exact tie: the lowest edge position wins
+                    const unsigned emin = __reduce_min_sync(0xffffffffu, key == mx ? (unsigned)my_e : 64u);
+                    w = __ffs(__ballot_sync(0xffffffffu, key == mx && (unsigned)my_e == emin)) - 1;
+                }
+                const float sw = __shfl_sync(0xffffffffu, my_s, w);
+                const int jw = __shfl_sync(0xffffffffu, jl, w);
+                if (lane == w) key = 0u;
+                // rank of the newcomer: list entries with score >= sw stay in front (earlier positions win ties)
+                const int pos = __popc(__ballot_sync(0xffffffffu, lane < cnt && ls >= sw));
+                if (pos >= top_k) break;                                            // nothing that remains can enter either
+                const float us = __shfl_up_sync(0xffffffffu, ls, 1);
+                const int uj = __shfl_up_sync(0xffffffffu, lj, 1);
+                if (lane > pos) { ls = us; lj = uj; }
+                if (lane == pos) { ls = sw; lj = jw; }
+                cnt = min(cnt + 1, top_k);
+                if (cnt == top_k) kth = __shfl_sync(0xffffffffu, ls, top_k - 1);
+                if (cnt == top_k) key = (my_s > kth) ? key : 0u;                     // candidates the new k-th score rules out
+            }
+        }
+        // weighted sum of the winners' rows (re-gathered: they were loaded moments ago)
+        float4 acc = z4;
+        for (int st = 0; st < cnt; st += EPW) {
+            const int t = min(st + grp, cnt - 1);                                    // clamp: the duplicate gets weight 0
+            const float w = __shfl_sync(0xffffffffu, ls, t);
+            const int j = __shfl_sync(0xffffffffu, lj, t);
+            fma4(acc, st + grp < cnt ? w : 0.f, ldg4(hb + (int64_t)j * ldh));
+        }
+        if (lane < top_k) {
+            sel_src[(int64_t)row * top_k + lane] = lane < cnt ? lj : -1;
+            sel_w[(int64_t)row * top_k + lane] = lane < cnt ? ls : 0.f;
+        }
+        if (lane == 0) sel_cnt[row] = cnt;
+        acc.x = cross_group_sum<G>(acc.x); acc.y = cross_group_sum<G>(acc.y);
+        acc.z = cross_group_sum<G>(acc.z); acc.w = cross_group_sum<G>(acc.w);
+        if (grp == 0 && ch_ok) {
+            const float invd = 1.0f / (float)max(end - beg, 1);
+            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + q * 4) = scale4(acc, invd);
+        }
+        if (PF) {
+            if (beg == end && nrow < n) njl = my_e < nend - nbeg ? __ldg(col + nbeg + my_e) : row_offset + nrow;   // (empty row: no chunk ran)
+        } else if (nrow < n) {
+            nbeg = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1);
+            njl = my_e < nend - nbeg ? __ldg(col + nbeg + my_e) : row_offset + nrow;
+        }
+        beg = nbeg; end = nend; jl0 = njl;
     }
 }
 
@@ -485,7 +634,12 @@ extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n_total, int64_t n,
     cudaStream_t st = (cudaStream_t)stream;
     row_inv_norm_kernel<<<grid_for_rows(n_total, kWarpsPerBlock), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm);
     SNG_DISPATCH_G(c,
-        if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
+        if (top_k > 0 && top_k <= 32 && !getenv("SNG_K2_OLD")) {
+            // (PF = next-row metadata prefetch costs 16 registers, i.e. a resident block per SM, and measured no gain: off)
+            constexpr int MB = G >= 16 ? 2 : (G == 8 ? 4 : 6);
+            edge_topk_sel_fwd_kernel<G, false, MB><<<grid, kThreads, 0, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
+        }
+        else if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
         else edge_topk_agg_fwd_kernel<G, true><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, 0, thr, out, (int)ldo, nullptr, nullptr, nullptr));
     return check_launch("sng_edge_topk_agg_fwd");
 }
