@@ -176,17 +176,15 @@ __device__ __forceinline__ void issue_split(const Stage1Params& p, uint32_t base
     int st0 = (W * p.kblocks) % nst;                         // ring slot of this tile's K block 0
     uint32_t ph0 = (uint32_t)((W * p.kblocks) / nst) & 1u;
     for (int tt = W; tt < t_end - t_beg; tt += NI) {
-        int st1 = st0 + 1; uint32_t ph1 = ph0;
-        if (st1 == nst) { st1 = 0; ph1 ^= 1u; }
+        const int st1 = st0 + 1;                             // same ring lap: stages % kblocks == 0
         const uint32_t acc_phase = (uint32_t)(tt >> 1) & 1u;
         const int acc0 = 2 * (tt & 1);
         const uint64_t b0 = bdesc0 + (uint64_t)(st0 * (kTileBytes >> 4)), b1 = bdesc0 + (uint64_t)(st1 * (kTileBytes >> 4));
-        mbar_wait(bar_full + 8 * st0, ph0);
-        if (kb2) mbar_wait(bar_full + 8 * st1, ph1);
+        mbar_wait(bar_full + 8 * st0, ph0);                  // every K block of the tile landed (one barrier per tile)
+        mbar_wait(bar_tempty + 8 * (tt & 1), acc_phase ^ 1); // both accumulator halves of this tile parity drained
+        tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            mbar_wait(bar_tempty + 8 * (acc0 + h), acc_phase ^ 1);
-            tc_fence_after();
             if (h == 0 && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 0] = clock64();
             const uint32_t tmem_d = (uint32_t)((acc0 + h) * 128);
             const uint64_t hb = (uint64_t)(h * (kTileBytes >> 5));                       // + 64 rows x 128 B
@@ -197,10 +195,7 @@ __device__ __forceinline__ void issue_split(const Stage1Params& p, uint32_t base
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                     if (ks < ks1) umma_f16_pair(tmem_d, adesc0 + (uint64_t)((kTileBytes >> 4) + ks * 2), b1 + hb + (uint64_t)(ks * 2), kIdescHalf, 1u);
-                if (h == 1) {                                                            // both halves read: free the B stage(s)
-                    umma_commit_pair(bar_empty + 8 * st0);
-                    if (kb2) umma_commit_pair(bar_empty + 8 * st1);
-                }
+                if (h == 1) umma_commit_pair(bar_empty + 8 * st0);                       // both halves read: free the tile's B slots
                 umma_commit_pair(bar_tfull + 8 * (acc0 + h));
             }
             __syncwarp();
@@ -267,8 +262,9 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_a, 2);
-        // SPLIT: four 128-column accumulator stages, each drained by 8 warps per CTA; else two 256-column stages, 4*EW warps each
-        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, SPLIT ? 16 : 2 * 4 * EW); }
+        // SPLIT: four 128-column accumulator stages handed back in PAIRS (tempty[tile parity], all 16 warps of both CTAs);
+        // else two 256-column stages, 4*EW warps per CTA each
+        for (int s = 0; s < 4; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, SPLIT ? 32 : 2 * 4 * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -331,6 +327,23 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         int stage = 0; uint32_t phase = 0;
         for (int t = t_beg; t < t_end; ++t) {
             const int brow = t * BN + (int)rank * 128;              // this CTA stages its half of the tile's database rows
+            if constexpr (SPLIT) {
+                // all K blocks of a tile share the barriers of the tile's first ring slot (stages % kblocks == 0): the issuers
+                // pay one wait and one commit per tile instead of one per K block
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                if (issuer) {
+                    if (!(p.debug & 4)) {
+                        for (int kb = 0; kb < p.kblocks; ++kb)
+                            tma_load_2d_pair(base + b_off + (uint32_t)(stage + kb) * kTileBytes, &map_db, (bar_full + 8 * stage) & kPeerMask, kb * BK, brow);
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)p.kblocks * kTileBytes);
+                        else mbar_arrive_cluster(bar_full + 8 * stage, 0);
+                    } else {
+                        mbar_arrive_cluster(bar_full + 8 * stage, 0);
+                    }
+                }
+                stage += p.kblocks;
+                if (stage >= p.stages) { stage = 0; phase ^= 1; }
+            } else {
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (issuer) {
@@ -343,6 +356,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     }
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
             }
         }
     } else if (warp == 1 || warp == 2) {
@@ -572,7 +586,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * (SPLIT ? (tt & 1) : acc), 0);
                 if (tr) p.trace[(t - t_beg) * 8 + 3] = clock64();
                 process(va, col0, 0, odd);
                 process(vb, col0 + 32, CT > 1 ? 1 : 0, odd);
@@ -952,6 +966,7 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     pl->ew = 0;
     // small K: the epilogue (TMEM reads) paces the kernel -> 16 epilogue warps; large K: the MMAs do -> fewer, deeper B ring
     const int ew_pref = d16 <= 128 ? 4 : (d16 <= 320 ? 2 : 1);
+    if (force_ew == 4 && pl->kblocks > 2) force_ew = 2;        // EW = 4 is the split-N mode, built for at most two K blocks
     for (int pass = 0; pass < 2 && !pl->ew; ++pass) {
         for (int ew = force_ew ? force_ew : ew_pref; ew >= 1 && !pl->ew; ew >>= 1) {
             const int c = top_k > 0 ? cand_for(top_k, ew) : cand;
@@ -959,6 +974,7 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
                 int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
                 if (env_int("SNG_KNN_STAGES", 2, kMaxStages)) want = env_int("SNG_KNN_STAGES", 2, kMaxStages);
                 for (int st = want; st >= (pass ? 2 : 3); --st) {
+                    if (ew == 4 && st % pl->kblocks != 0) continue;      // split mode: a tile's K blocks share one ring lap
                     const size_t sz = smem_bytes(ew, pl->kblocks, st, c);
                     if (sz <= kMaxSmem) { pl->ew = ew; pl->stages = st; pl->smem = sz; pl->cand = c; break; }
                 }
