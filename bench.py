@@ -254,7 +254,7 @@ def run_ours(args):
                 "peak_source": pk["src"] + " (sustained bf16/fp16 dense)", "kernel_ms": ms_k1, "algorithmic_flops_per_launch": flops,
                 "share_of_step": ms_k1 / ms, "seed_pass_ms": ms_seed, "plan": plan}
 
-    # ---- SNGNN++ epoch + aggregation kernels on the pokec-shaped graph (rank 0 reports; replicas at N>1) ------
+    # ---- SNGNN++ epoch (row-sharded at N>1) + aggregation kernels alone on the pokec-shaped graph ----------------
     extras = {}
     if not args.skip_epoch:
         torch.cuda.empty_cache()
@@ -268,29 +268,45 @@ def run_ours(args):
         Ep = g.num_edges
         hid = 32
         torch.manual_seed(2)
-        model = M.SNGNN_Plus_Plus(Fd, hid, C, N, 2, k, thr, 0.5, 1, 0.5).to(dev)
+        model = M.SNGNN_Plus_Plus(Fd, hid, C, N, 2, k, thr, 0.5, 1, 0.0 if world > 1 else 0.5).to(dev)
         opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=5e-4)
         data = synth.GraphData(x, ei)
         import torch.nn.functional as F
 
+        from sngnn_b200 import dist as D
+        x_loc, y_loc = x[lo:hi].contiguous(), y[lo:hi]
+
+        def forward():                                        # world > 1: row-sharded forward (replicated parameters)
+            if world == 1:
+                return model(data)
+            return D.sharded_forward(model, x_loc, ei, N)
+
         def epoch():                                          # R: train.py:136-138 = train step + val + test forwards
             model.train()
             opt.zero_grad()
-            loss = F.nll_loss(model(data), y)
+            if world == 1:
+                loss = F.nll_loss(forward(), y)
+            else:
+                loss = F.nll_loss(forward(), y_loc, reduction="sum") / N
             loss.backward()
+            D.allreduce_grads(model.parameters())
             opt.step()
             model.eval()
             with torch.no_grad():
-                model(data)
-                model(data)
+                forward()
+                forward()
 
         def fwd_only():
             model.eval()
             with torch.no_grad():
-                model(data)
+                forward()
 
-        ep_ms = timed(epoch, 5, 2)
-        fw_ms = timed(fwd_only, 5, 1)
+        ep_ms = timed(epoch, 5, 3, barrier)
+        fw_ms = timed(fwd_only, 5, 1, barrier)
+        te = torch.tensor([ep_ms, fw_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ep_ms, fw_ms = float(te[0]), float(te[1])
         # fused aggregation kernels alone, C = 32
         h = torch.randn(N, hid, device=dev)
         gg = torch.randn(N, hid, device=dev)
@@ -306,7 +322,7 @@ def run_ours(args):
 
         def k2_bwd():
             dval.zero_(); dnrm.zero_()
-            _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(gg), N, hid, hid, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss),
+            _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(gg), N, N, 0, hid, hid, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss),
                                                _C.ptr(sw), _C.ptr(sc), _C.ptr(g.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh),
                                                _C.stream()), "sng_edge_agg_bwd")
 
@@ -316,7 +332,8 @@ def run_ours(args):
         bytes_bwd = nsel * (3 * 4 * hid + 16) + 3 * N * 4 * hid + 2 * N * 4 * hid   # + the two accumulator memsets
         extras = {"epoch_ms": ep_ms, "forward_ms": fw_ms, "graph_prep_ms": prep_ms,
                   "epoch_config": f"SNGNN_Plus_Plus 2 layers hidden {hid} top_k={k} thr={thr} init_beta=0.5 on {args.workload}-shape graph "
-                                  f"({Ep} edges after loop processing); epoch = fwd+loss+bwd+Adam + 2 eval forwards (R train.py:136-138)",
+                                  f"({Ep} edges after loop processing); epoch = fwd+loss+bwd+Adam + 2 eval forwards (R train.py:136-138)" +
+                                  (f"; rows sharded over {world} ranks: all-gather of h per layer, reduce-scatter of dL/dh, all-reduce of parameter gradients" if world > 1 else ""),
                   "agg": {"fwd_ms": k2_ms, "fwd_gbs": bytes_fwd / (k2_ms * 1e-3) / 1e9, "fwd_frac_hbm": bytes_fwd / (k2_ms * 1e-3) / 1e9 / pk["hbm"],
                           "bwd_ms": k2b_ms, "bwd_gbs": bytes_bwd / (k2b_ms * 1e-3) / 1e9, "bwd_frac_hbm": bytes_bwd / (k2b_ms * 1e-3) / 1e9 / pk["hbm"],
                           "algorithmic_bytes_fwd": bytes_fwd, "algorithmic_bytes_bwd": bytes_bwd, "selected_edges": nsel, "channels": hid}}

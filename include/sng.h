@@ -82,12 +82,16 @@ SNG_API int sng_edge_topk_agg_fwd(const float* h, int64_t n_total, int64_t n, in
                           float* inv_norm, void* stream);
 
 /* K2b backward of the above w.r.t. h (closed form of SURVEY.md §3.4).
- * Pass 1 scatters into the two zero-initialised accumulators dval, dnrm [n, c] (float atomics);
- * pass 2 writes dh = dval + (dnrm - n (n . dnrm)) / r.   `g` = dL/dout [n,c].
+ * Pass 1 scatters into the two zero-initialised accumulators dval, dnrm [n_total, c] (float atomics);
+ * pass 2 writes dh [n_total, c] = dval + (dnrm - n (n . dnrm)) / r.   `g` = dL/dout [n, c].
  * top_k > 0: uses the saved selection lists (inv_denom[i] = 1/max(deg_i,1));
- * top_k <= 0: iterates the CSR (every edge selected).  inv_norm [n] = the array the forward filled
- * (or sng_rownorm_f32's inv_norm output for selection lists that did not come from the edge forward). */
-SNG_API int sng_edge_agg_bwd(const float* h, const float* inv_norm, const float* g, int64_t n, int64_t c, int64_t ld,
+ * top_k <= 0: iterates the CSR (every edge selected).  inv_norm [n_total] = the array the forward filled
+ * (or sng_rownorm_f32's inv_norm output for selection lists that did not come from the edge forward).
+ * Row sharding: the call covers target rows [row_offset, row_offset + n) of `h` (all n_total nodes); g, the lists, inv_denom
+ * and rowptr are local to the shard.  dh is then this shard's CONTRIBUTION to dL/dh of every node -- the map
+ * (dval, dnrm) -> dh is linear, so the per-shard results simply add (reduce-scatter across ranks). */
+SNG_API int sng_edge_agg_bwd(const float* h, const float* inv_norm, const float* g, int64_t n_total, int64_t n, int64_t row_offset,
+                     int64_t c, int64_t ld,
                      const int32_t* rowptr, const int32_t* col,
                      int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_cnt,
                      const float* inv_denom,

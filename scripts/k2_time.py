@@ -28,7 +28,7 @@ dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
 _, _, inv_norm = SF.rownorm(h, want_f32=False, want_inv=True)
 def bwd():
     dval.zero_(); dnrm.zero_()
-    _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(gg), N, C, C, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss), _C.ptr(sw),
+    _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(gg), N, N, 0, C, C, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss), _C.ptr(sw),
                                        _C.ptr(sc), _C.ptr(g.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()), "bwd")
 ms_b = timed(bwd)
 Ep, nsel = g.num_edges, int(sc.sum())

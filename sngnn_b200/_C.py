@@ -19,7 +19,7 @@ SIGNATURES = {
     "sng_device_info": (_I32, [_P, _P, _P]),
     "sng_rownorm_f32": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P]),
     "sng_edge_topk_agg_fwd": (_I32, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _F32, _P, _I64, _P, _P, _P, _P, _P]),
-    "sng_edge_agg_bwd": (_I32, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sng_edge_agg_bwd": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sng_list_agg_fwd": (_I32, [_P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "sng_spmm_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "sng_pp_fuse_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(kThreads) list_agg_fwd_kernel(
 // ------------------------------------------------------------------------------------------ K2b backward
 template <int G, bool SELECT_ALL>
 __global__ void __launch_bounds__(kThreads) edge_agg_bwd_scatter_kernel(
-    const float* __restrict__ h, const float* __restrict__ inv_r, const float* __restrict__ g, int n, int c, int64_t ld, const int* __restrict__ rowptr,
+    const float* __restrict__ h, const float* __restrict__ inv_r, const float* __restrict__ g, int n, int row_offset, int c, int64_t ld, const int* __restrict__ rowptr,
     const int* __restrict__ col, int top_k, const int* __restrict__ sel_src, const float* __restrict__ sel_w,
     const int* __restrict__ sel_cnt, const float* __restrict__ inv_denom, float* __restrict__ dval, float* __restrict__ dnrm) {
     constexpr int EPW = 32 / G;
@@ -400,8 +400,9 @@ __global__ void __launch_bounds__(kThreads) edge_agg_bwd_scatter_kernel(
             invd = __ldg(inv_denom + row);
         }
         if (cnt == 0) continue;
-        const float4 hi = ch_ok ? ldg4(h + (int64_t)row * ld + c4) : z4;
-        const float4 ni = scale4(hi, __ldg(inv_r + row));
+        const int grow = row_offset + row;                       // h / inv_r / dval / dnrm hold all nodes, g and the lists are shard-local
+        const float4 hi = ch_ok ? ldg4(h + (int64_t)grow * ld + c4) : z4;
+        const float4 ni = scale4(hi, __ldg(inv_r + grow));
         const float4 gs = ch_ok ? scale4(ldg4(g + (int64_t)row * ld + c4), invd) : z4;     // g_i / deg_i
         float4 dni = z4;
         for (int st = 0; st < cnt; st += EPW * U) {
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) edge_agg_bwd_scatter_kernel(
         }
         dni.x = cross_group_sum<G>(dni.x); dni.y = cross_group_sum<G>(dni.y);
         dni.z = cross_group_sum<G>(dni.z); dni.w = cross_group_sum<G>(dni.w);
-        if (grp == 0 && ch_ok) atomicAdd(reinterpret_cast<float4*>(dnrm + (int64_t)row * ld + c4), dni);
+        if (grp == 0 && ch_ok) atomicAdd(reinterpret_cast<float4*>(dnrm + (int64_t)grow * ld + c4), dni);
     }
 }
 
@@ -655,19 +656,19 @@ extern "C" int sng_list_agg_fwd(const float* h, int64_t n_rows, int64_t c, int64
     return check_launch("sng_list_agg_fwd");
 }
 
-extern "C" int sng_edge_agg_bwd(const float* h, const float* inv_norm, const float* g, int64_t n, int64_t c, int64_t ld, const int32_t* rowptr,
-                                const int32_t* col, int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_cnt,
+extern "C" int sng_edge_agg_bwd(const float* h, const float* inv_norm, const float* g, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ld,
+                                const int32_t* rowptr, const int32_t* col, int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_cnt,
                                 const float* inv_denom, float* dval, float* dnrm, float* dh, void* stream) {
-    if (int rc = check_rows("sng_edge_agg_bwd", n, c, ld)) return rc;
+    if (int rc = check_rows("sng_edge_agg_bwd", n_total, c, ld)) return rc;
     SNG_REQUIRE(h && inv_norm && g && dval && dnrm && dh, "sng_edge_agg_bwd: null pointer");
+    SNG_REQUIRE(n >= 0 && row_offset >= 0 && row_offset + n <= n_total, "sng_edge_agg_bwd: bad n / row_offset / n_total");
     SNG_REQUIRE(top_k > 0 ? (sel_src && sel_w && sel_cnt && inv_denom) : (rowptr && col), "sng_edge_agg_bwd: missing selection list / CSR");
-    if (n == 0) return SNG_OK;
-    const int grid = grid_for_rows(n, kWarpsPerBlock);
+    if (n_total == 0) return SNG_OK;
     cudaStream_t st = (cudaStream_t)stream;
     SNG_DISPATCH_G(c,
-        if (top_k > 0) edge_agg_bwd_scatter_kernel<G, false><<<grid, kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)c, ld, rowptr, col, top_k, sel_src, sel_w, sel_cnt, inv_denom, dval, dnrm);
-        else edge_agg_bwd_scatter_kernel<G, true><<<grid, kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)c, ld, rowptr, col, 0, nullptr, nullptr, nullptr, nullptr, dval, dnrm);
-        norm_bwd_finish_kernel<G><<<grid_for_rows(n, kWarpsPerBlock * (32 / G)), kThreads, 0, st>>>(h, inv_norm, (int)n, (int)c, ld, dval, dnrm, dh));
+        if (n > 0 && top_k > 0) edge_agg_bwd_scatter_kernel<G, false><<<grid_for_rows(n, kWarpsPerBlock), kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)row_offset, (int)c, ld, rowptr, col, top_k, sel_src, sel_w, sel_cnt, inv_denom, dval, dnrm);
+        else if (n > 0) edge_agg_bwd_scatter_kernel<G, true><<<grid_for_rows(n, kWarpsPerBlock), kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)row_offset, (int)c, ld, rowptr, col, 0, nullptr, nullptr, nullptr, nullptr, dval, dnrm);
+        norm_bwd_finish_kernel<G><<<grid_for_rows(n_total, kWarpsPerBlock * (32 / G)), kThreads, 0, st>>>(h, inv_norm, (int)n_total, (int)c, ld, dval, dnrm, dh));
     return check_launch("sng_edge_agg_bwd");
 }
 

@@ -69,8 +69,7 @@ def build_knn_sharded(x_local, n, top_k, thr=-1.0, remove_self=True, normalize=N
 
 
 def edge_agg_forward_sharded(h_local, graph, top_k=None, thr=None, agg=None):
-    """out_1 rows [lo, hi) from the all-gathered h (forward only; the sharded backward needs a reduce-scatter of
-    dL/dh and is not implemented yet -- DESIGN.md §multi-GPU)."""
+    """out_1 rows [lo, hi) from the all-gathered h, forward only (no autograd; see `edge_agg_sharded` for training)."""
     ws, rank = world()
     n = graph.n
     lo, hi = shard_bounds(n, ws, rank)
@@ -80,3 +79,148 @@ def edge_agg_forward_sharded(h_local, graph, top_k=None, thr=None, agg=None):
         from . import functional as SF
         agg = SF.edge_topk_agg_rows
     return agg(h_all, shard, lo, top_k, thr)
+
+
+# ------------------------------------------------------------------------------------------ training: sharded forward + backward
+def _reduce_scatter_rows(full, n):
+    """Sum `full` [ws*R, ld] (R = rows_per_rank) over ranks and return this rank's rows.  NCCL: reduce_scatter_tensor;
+    backends without it (gloo on CPU, used by the tests): all_reduce + slice."""
+    ws, rank = world()
+    r = rows_per_rank(n, ws)
+    lo, hi = shard_bounds(n, ws, rank)
+    if dist.get_backend() == "nccl":
+        out = torch.empty(r, full.size(1), dtype=full.dtype, device=full.device)
+        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM)
+        return out[: hi - lo]
+    dist.all_reduce(full, op=dist.ReduceOp.SUM)
+    return full[lo:hi]
+
+
+class AllGatherRows(torch.autograd.Function):
+    """h_all [n, C] = concatenation of every rank's row shard; backward = reduce-scatter (sum) of dL/dh_all -- the one
+    exchange of the sharded backward: a rank's targets gather from, and so send gradient to, any source row."""
+
+    @staticmethod
+    def forward(ctx, local, n):
+        ctx.n = n
+        return all_gather_rows(local.contiguous(), n)
+
+    @staticmethod
+    def backward(ctx, g_all):
+        ws, _ = world()
+        n = ctx.n
+        if ws == 1:
+            return g_all, None
+        r = rows_per_rank(n, ws)
+        full = g_all.new_zeros(ws * r, g_all.size(1))
+        full[:n].copy_(g_all)
+        return _reduce_scatter_rows(full, n).contiguous(), None
+
+
+def edge_agg_sharded(h_local, graph, top_k=None, thr=None, agg=None):
+    """Differentiable out_1 rows [lo, hi): all-gather h (autograd-aware), then K2 on the shard; its backward produces the
+    shard's contribution to dL/dh of every node, which AllGatherRows.backward reduce-scatters.
+    `agg(h_all, shard, row_offset, top_k, thr)` defaults to the CUDA kernels (functional.ShardedEdgeTopkAgg); the gloo tests
+    inject a differentiable CPU oracle."""
+    ws, rank = world()
+    n = graph.n
+    lo, hi = shard_bounds(n, ws, rank)
+    h_all = AllGatherRows.apply(h_local, n)
+    shard = graph.row_slice(lo, hi)
+    if agg is None:
+        from . import functional as SF
+        agg = SF.ShardedEdgeTopkAgg.apply
+    return agg(h_all, shard, lo, top_k, thr), shard
+
+
+def pp_fuse_sharded(out1_local, w_weight, w_bias, beta, bias, shard, n, lo, fuse=None):
+    """SNGNN++ fusion on a row shard: out rows [lo, hi) = beta * (A[lo:hi] @ W^T + b_w) + (1 - beta) * out_1 (+ bias), with
+    the replicated parameter W^T [n, C] gathered over the shard's out-neighbours.  The parameter gradients this produces
+    are PARTIAL (this rank's rows only), like every other parameter gradient of a sharded step: `allreduce_grads` sums them.
+    `fuse` defaults to functional.PPFuse on the shard's by-source CSR (its backward needs g0 of ALL rows for dL/dW^T rows
+    [lo, hi), so that variant all-gathers g0); the gloo tests inject a differentiable dense CPU version."""
+    if fuse is not None:
+        return fuse(out1_local, w_weight, w_bias, beta, bias, shard, n, lo)
+    return _ShardedPPFuse.apply(out1_local, w_weight, w_bias, beta, bias, shard, n, lo)
+
+
+class _ShardedPPFuse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out1, w_weight, w_bias, beta, bias, shard, n, lo):
+        import torch.nn.functional as F
+        from . import _C, functional as SF
+        out1 = SF._check_h(out1)
+        nl, cp = out1.shape
+        c = w_weight.size(0)
+        wt = F.pad(w_weight.detach(), (0, 0, 0, cp - c)).t().contiguous()        # [n, Cp], replicated
+        bw = F.pad(w_bias.detach(), (0, cp - c)).contiguous()
+        bb = None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous()
+        out0, out = torch.empty_like(out1), torch.empty_like(out1)
+        if nl:
+            _C.check(_C.lib().sng_pp_fuse_fwd(_C.ptr(wt), nl, cp, cp, _C.ptr(shard.rowptr_out), _C.ptr(shard.col_out), _C.ptr(bw),
+                                              _C.ptr(beta), _C.ptr(out1), _C.ptr(bb), _C.ptr(out0), _C.ptr(out), _C.stream()), "sng_pp_fuse_fwd")
+        ctx.shard, ctx.c, ctx.n, ctx.lo, ctx.has_bias = shard, c, n, lo, bias is not None
+        ctx.save_for_backward(out0, out1, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _C, functional as SF
+        out0, out1, beta = ctx.saved_tensors
+        shard, c, n, lo = ctx.shard, ctx.c, ctx.n, ctx.lo
+        nl, cp = out1.shape
+        g = g.contiguous()
+        dbeta = torch.zeros(1, dtype=torch.float32, device=g.device)
+        if nl:
+            _C.check(_C.lib().sng_pp_beta_grad(_C.ptr(out0), _C.ptr(out1), _C.ptr(g), g.numel(), _C.ptr(dbeta), _C.stream()), "sng_pp_beta_grad")
+        g0 = g * beta
+        # dL/dW^T rows [lo, hi): row t gathers g0 over the (shifted) sources of t's in-edges -- any row of g0
+        g0_all = all_gather_rows(g0.contiguous(), n)
+        dwt = g.new_zeros(n, cp)
+        if nl:
+            dwt[lo:lo + nl] = SF.spmm(g0_all.contiguous(), shard.rowptr_in, shard.col_in_shift, nl)
+        dbias = g.sum(0)[:c] if ctx.has_bias else None
+        return g - g0, dwt[:, :c].t(), g0.sum(0)[:c], dbeta, dbias, None, None, None
+
+
+def allreduce_grads(params):
+    """Sum the (partial, per-shard) parameter gradients over ranks: every parameter is replicated, every rank holds the
+    gradient contribution of its own rows."""
+    ws, _ = world()
+    if ws == 1:
+        return
+    for p in params:
+        if p.grad is not None:
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+
+
+def sharded_forward(model, x_local, edge_index, n, agg=None, fuse=None):
+    """Row-sharded forward of an SNGNN / SNGNN_Plus / SNGNN_Plus_Plus model (replicated parameters): this rank holds the
+    feature rows [lo, hi) and returns the log-probabilities of those rows.  Mirrors _SNStack.forward / the conv forwards of
+    models.py (R: models/models.py:76-86,116-137,233-242,322-329) with the aggregation and the ++ fusion replaced by their
+    sharded forms.  BatchNorm needs statistics over all nodes and is not supported here (the reference default is bn=False)."""
+    import torch.nn.functional as F
+    from . import graph as G, models as M
+    if getattr(model, "bn", False):
+        raise NotImplementedError("sharded_forward: bn=True needs cross-rank batch statistics")
+    ws, rank = world()
+    lo, hi = shard_bounds(n, ws, rank)
+    x = x_local
+    convs = list(model.lins)
+    for i, conv in enumerate(convs):
+        base = type(conv) is M.SNConv
+        plus_plus = isinstance(conv, M.SNConv_plus_plus)
+        g = G.prepare(edge_index, n, remove_self_loops=False if base else bool(conv.is_remove_self_loops), structural=plus_plus)
+        h = conv._hidden(x)
+        out, shard = edge_agg_sharded(h, g, None if base else conv.top_k, None if base else conv.thr, agg=agg)
+        if plus_plus:
+            out = pp_fuse_sharded(out, conv.w.weight, conv.w.bias, conv.beta, conv.bias, shard, n, lo, fuse=fuse)
+            out = out[:, :conv.lin.out_features]
+        else:
+            out = out[:, :conv.lin.out_features]
+            if conv.bias is not None:
+                out = out + conv.bias
+        if i < len(convs) - 1:
+            out = model.dropout(F.relu(out))
+        x = out
+    return F.log_softmax(x, dim=1)

@@ -68,7 +68,7 @@ class EdgeTopkAgg(torch.autograd.Function):
         dval = torch.zeros_like(h)
         dnrm = torch.zeros_like(h)
         dh = torch.empty_like(h)
-        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
+        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, n, 0, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
                                            _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(graph.inv_deg),
                                            _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
                  "sng_edge_agg_bwd")
@@ -79,19 +79,51 @@ def edge_topk_agg_rows(h_all, shard, row_offset, top_k=None, thr=None):
     """Forward-only K2 on a row shard: targets [row_offset, row_offset + shard.n) of `h_all` (all nodes, e.g. after an
     all-gather), `shard` = PreparedGraph.row_slice(lo, hi).  Returns (out [shard.n, C], sel_src, sel_w, sel_cnt)."""
     h_all = _check_h(h_all)
+    out, sel_src, sel_w, sel_cnt, _ = _edge_fwd_rows(h_all, shard, int(row_offset), int(top_k) if top_k is not None else 0, thr)
+    return out, sel_src, sel_w, sel_cnt
+
+
+class ShardedEdgeTopkAgg(torch.autograd.Function):
+    """K2 / K2b on a ROW SHARD: forward computes out_1 for target rows [row_offset, row_offset + shard.n) from `h_all` (all
+    nodes); backward returns this shard's contribution to dL/dh_all [N, C] -- contributions of different shards add
+    (the caller reduce-scatters them, see dist.AllGatherRows)."""
+
+    @staticmethod
+    def forward(ctx, h_all, shard, row_offset, top_k, thr):
+        h_all = _check_h(h_all)
+        k = int(top_k) if top_k is not None else 0
+        out, sel_src, sel_w, sel_cnt, inv_norm = _edge_fwd_rows(h_all, shard, int(row_offset), k, thr)
+        ctx.shard, ctx.k, ctx.row_offset = shard, k, int(row_offset)
+        ctx.save_for_backward(h_all, sel_src, sel_w, sel_cnt, inv_norm)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h_all, sel_src, sel_w, sel_cnt, inv_norm = ctx.saved_tensors
+        shard, k = ctx.shard, ctx.k
+        n_total, c = h_all.shape
+        g = g.contiguous()
+        dval, dnrm, dh = torch.zeros_like(h_all), torch.zeros_like(h_all), torch.empty_like(h_all)
+        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h_all), _C.ptr(inv_norm), _C.ptr(g), n_total, shard.n, ctx.row_offset, c, c,
+                                           _C.ptr(shard.rowptr_in), _C.ptr(shard.col_in), k, _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt),
+                                           _C.ptr(shard.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()), "sng_edge_agg_bwd")
+        return dh, None, None, None, None
+
+
+def _edge_fwd_rows(h_all, shard, row_offset, k, thr):
     c = h_all.size(1)
     n = shard.n
-    k = int(top_k) if top_k is not None else 0
-    out = torch.empty(n, c, dtype=h_all.dtype, device=h_all.device)
-    sel_src = torch.empty(n, max(k, 1), dtype=torch.int32, device=h_all.device) if k > 0 else None
-    sel_w = torch.empty(n, max(k, 1), dtype=torch.float32, device=h_all.device) if k > 0 else None
-    sel_cnt = torch.empty(n, dtype=torch.int32, device=h_all.device) if k > 0 else None
-    inv_norm = torch.empty(h_all.size(0), dtype=torch.float32, device=h_all.device)
-    _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h_all), h_all.size(0), n, int(row_offset), c, c, _C.ptr(shard.rowptr_in),
+    dev = h_all.device
+    out = torch.empty(n, c, dtype=h_all.dtype, device=dev)
+    sel_src = torch.empty(n, max(k, 1), dtype=torch.int32, device=dev) if k > 0 else None
+    sel_w = torch.empty(n, max(k, 1), dtype=torch.float32, device=dev) if k > 0 else None
+    sel_cnt = torch.empty(n, dtype=torch.int32, device=dev) if k > 0 else None
+    inv_norm = torch.empty(h_all.size(0), dtype=torch.float32, device=dev)
+    _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h_all), h_all.size(0), n, row_offset, c, c, _C.ptr(shard.rowptr_in),
                                             _C.ptr(shard.col_in), k, float(thr if thr is not None else 0.0), _C.ptr(out), c,
                                             _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(inv_norm), _C.stream()),
              "sng_edge_topk_agg_fwd")
-    return out, sel_src, sel_w, sel_cnt
+    return out, sel_src, sel_w, sel_cnt, inv_norm
 
 
 def edge_topk_agg(h, graph, top_k=None, thr=None, return_selection=False):
@@ -123,7 +155,7 @@ class ListAgg(torch.autograd.Function):
         g = g.contiguous()
         dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
         _, _, inv_norm = rownorm(h, want_f32=False, want_inv=True)
-        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, c, c, None, None, idx.size(1), _C.ptr(idx), _C.ptr(sim),
+        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, n, 0, c, c, None, None, idx.size(1), _C.ptr(idx), _C.ptr(sim),
                                            _C.ptr(cnt), _C.ptr(inv_denom), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
                  "sng_edge_agg_bwd")
         return dh, None, None, None, None

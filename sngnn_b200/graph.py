@@ -23,11 +23,16 @@ _CACHE_MAX = 8
 
 class PreparedGraph:
     __slots__ = ("n", "num_edges", "rowptr_in", "col_in", "inv_deg", "src_shift", "rowptr_out", "col_out",
-                 "col_in_shift", "dst_sorted")
+                 "col_in_shift", "dst_sorted", "_shards")
 
     def row_slice(self, lo, hi):
-        """Row-sharded view (targets [lo, hi)) for multi-GPU aggregation: rowptr rebased to 0."""
-        g = PreparedGraph()
+        """Row-sharded view (targets [lo, hi)) for multi-GPU aggregation: rowptr rebased to 0.  Cached per (lo, hi)."""
+        cache = getattr(self, "_shards", None)
+        if cache is None:
+            cache = self._shards = {}
+        if (lo, hi) in cache:
+            return cache[(lo, hi)]
+        g = cache[(lo, hi)] = PreparedGraph()
         g.n = hi - lo
         b, e = int(self.rowptr_in[lo]), int(self.rowptr_in[hi])
         g.num_edges = e - b
@@ -37,6 +42,10 @@ class PreparedGraph:
         g.src_shift = self.src_shift
         g.col_in_shift = None if self.col_in_shift is None else self.col_in_shift[b:e].contiguous()
         g.rowptr_out = g.col_out = g.dst_sorted = None
+        if self.rowptr_out is not None:                      # by-(shifted-)source CSR rows [lo, hi) for out_0 = A @ W^T
+            bo, eo = int(self.rowptr_out[lo]), int(self.rowptr_out[hi])
+            g.rowptr_out = (self.rowptr_out[lo:hi + 1] - bo).contiguous()
+            g.col_out = self.col_out[bo:eo].contiguous()
         return g
 
 

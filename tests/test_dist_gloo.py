@@ -100,3 +100,72 @@ def test_shard_bounds_cover_everything():
             b = [D.shard_bounds(n, ws, r) for r in range(ws)]
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(ws - 1))
+
+
+def _train_worker(rank, ws, port, kind, n, ret):
+    """Sharded forward + backward of a replicated-parameter model == the unsharded oracle (rows and parameter gradients)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    import torch.nn.functional as F
+    from sngnn_b200 import dist as D, synth
+    import sngnn_b200.models as M
+    from oracle import sn_ref
+    fd, hid, ncls, k, thr = 10, 8, 3, 3, 0.0
+    x = synth.make_features(n, fd, "clustered", seed=1).double()
+    ei = synth.make_graph(n, 5 * n, seed=2, hub_offset=2.0)
+    y = synth.make_labels(n, ncls, seed=3)
+    torch.manual_seed(7)                                         # same replicated parameters on every rank
+    if kind == "SNGNN":
+        model = M.SNGNN(fd, hid, ncls, 2)
+        model.dropout = torch.nn.Dropout(0.0)
+    elif kind == "SNGNN_Plus":
+        model = M.SNGNN_Plus(fd, hid, ncls, n, 2, k, thr, 1, 0.0)
+    else:
+        model = M.SNGNN_Plus_Plus(fd, hid, ncls, n, 2, k, thr, 0.5, 1, 0.0)
+    model = model.double().train()
+    lo, hi = D.shard_bounds(n, ws, rank)
+    rsl = False if kind == "SNGNN" else True
+    pe = sn_ref.process_edges(ei, n, rsl)
+
+    def agg(h_all, shard, row_offset, top_k, th):              # differentiable CPU oracle of K2 on the shard's rows
+        return sn_ref.sn_aggregate(h_all, pe, top_k, th)[row_offset:row_offset + shard.n]
+
+    def fuse(out1, w_w, w_b, beta, bias, shard, nn_, lo_):      # differentiable CPU oracle of K4 on the shard's rows
+        out0 = sn_ref.structural_term(pe, w_w, w_b, nn_)[lo_:lo_ + out1.size(0)]
+        out0 = F.pad(out0, (0, out1.size(1) - out0.size(1)))
+        out = beta * out0 + (1 - beta) * out1
+        return out if bias is None else out + F.pad(bias, (0, out1.size(1) - bias.numel()))
+
+    logp = D.sharded_forward(model, x[lo:hi].clone(), ei, n, agg=agg, fuse=fuse)
+    loss = F.nll_loss(logp, y[lo:hi], reduction="sum") / n     # local part of the full-batch mean
+    loss.backward()
+    D.allreduce_grads(model.parameters())
+
+    sd = {kk: v.detach().clone().requires_grad_(v.is_floating_point()) for kk, v in model.state_dict().items()}
+    ref = sn_ref.stack_forward(kind, sn_ref.params_from_state_dict(sd, 2), x, ei, top_k=k, thr=thr, remove_self_loops=rsl)
+    F.nll_loss(ref, y).backward()
+    assert torch.allclose(logp.detach(), ref.detach()[lo:hi], rtol=1e-9, atol=1e-11)
+    for name, p in model.named_parameters():
+        g_ref = sd[name].grad
+        assert p.grad is not None and torch.allclose(p.grad, g_ref, rtol=1e-8, atol=1e-11), (kind, name, (p.grad - g_ref).abs().max())
+    ret[rank] = True
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_training_step_world2_matches_unsharded_oracle():
+    """The N>1 training path: all-gather of h with a reduce-scatter backward, shard-local aggregation and
+    ++ fusion, all-reduce of the partial parameter gradients -- against the unsharded oracle, ragged shards included."""
+    ctx = mp.get_context("spawn")
+    for kind, n in (("SNGNN_Plus_Plus", 61), ("SNGNN_Plus", 40), ("SNGNN", 33)):
+        ret = ctx.Manager().dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_train_worker, args=(r, 2, port, kind, n, ret)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(180)
+            assert p.exitcode == 0, f"{kind}: worker exited with {p.exitcode}"
+        assert dict(ret) == {0: True, 1: True}
