@@ -237,10 +237,13 @@ def run_ours(args):
         seeds = simknn.seed_pass(xh[lo:hi], xh, Fd, plan["seed_stride"], ew)
         ms_seed = timed(lambda: simknn.seed_pass(xh[lo:hi], xh, Fd, plan["seed_stride"], ew), max(2, args.steps // 2), 1)
 
+    sweep_phase = torch.zeros(8, dtype=torch.int32, device=dev)
+
     def stage1_only():
+        sweep_phase.zero_()
         _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh[lo:]), _C.ptr(xh), ldh, nq, lo, N, Fd, cand, thr_lo, 1, _C.ptr(ci), _C.ptr(cv),
                                             _C.ptr(cm), ew, plan["nsplit"], ctypes.byref(ns), _C.ptr(seeds), plan["seed_q"],
-                                            plan["seed_stride"], _C.stream()), "sng_simknn_stage1")
+                                            plan["seed_stride"], _C.ptr(sweep_phase), _C.stream()), "sng_simknn_stage1")
 
     ms_k1 = timed(stage1_only, max(2, args.steps // 2), 1)
     flops = 2.0 * nq * N * Fd

@@ -174,13 +174,15 @@ SNG_API int sng_simknn_build(const uint16_t* xq_f16, const uint16_t* xall_f16, i
  * lane quarter.  force_ew in {0,1,2,4} picks the epilogue width (0 = auto), force_nsplit > 0 the number of column
  * splits; *lists_out receives lists (size the outputs for lists * cand <= 512 slots per row).
  * seeds (may be NULL) = output of sng_simknn_seed with the same seed_stride: every row then starts pruning at the
- * seed_q-th largest of its 16 group maxima instead of thr_lo. */
+ * seed_q-th largest of its 16 group maxima instead of thr_lo.
+ * sweep_phase (may be NULL) = [column splits] int32, zero-initialised by the caller: the CTAs of a launch use it to start
+ * their sweep over the database tiles where the other resident CTAs currently are, which keeps the tiles in L2. */
 SNG_API int sng_simknn_stage1(const uint16_t* xq_f16, const uint16_t* xall_f16, int64_t ldh,
                       int64_t nq, int64_t q_offset, int64_t n, int64_t d,
                       int cand, float thr_lo, int remove_self,
                       int32_t* cand_idx, float* cand_val, float* cand_min,
                       int force_ew, int force_nsplit, int* lists_out,
-                      const float* seeds, int seed_q, int seed_stride, void* stream);
+                      const float* seeds, int seed_q, int seed_stride, int32_t* sweep_phase, void* stream);
 
 /* Seed pass only (profiling / tests): the same tensor-core pipeline over every seed_stride-th database row with a
  * branch-free epilogue; seeds_out [nq, 16] = maxima of the row's FP16 scores over 16 disjoint groups of sampled columns

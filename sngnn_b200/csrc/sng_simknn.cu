@@ -157,6 +157,7 @@ struct Stage1Params {
     const float* seeds;           // [nq, kSeedGroups] group maxima over a 1/seed_stride column sample, or nullptr
     float* seed_out;              // SEED kernel only
     int seed_q, seed_stride;      // row threshold = seed_q-th largest group maximum; sample = every seed_stride-th column
+    int* phase;                   // [nsplit] sweep phase shared by all CTAs of a column split (see "Phase alignment"), or nullptr
     long long* trace;             // SNG_KNN_TRACE: [64 tiles][8] clock64 stamps of cluster 0's leader CTA, else nullptr
 };
 
@@ -258,6 +259,13 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int row0 = (int)blockIdx.x * BM;                          // blockIdx.x = 2 * pair + rank
     const int t_beg = (int)(((long long)p.tiles_total * blockIdx.y) / p.nsplit);
     const int t_end = (int)(((long long)p.tiles_total * (blockIdx.y + 1)) / p.nsplit);
+    const int T = t_end - t_beg;
+    // Phase alignment.  Every CTA sweeps all T tiles of its column split, but the database (261 MB FP16 at pokec scale) does
+    // not fit in L2 and CTAs of later waves start at arbitrary times: with every sweep starting at tile 0 the resident CTAs
+    // drift to random phases, the working set becomes the whole matrix and DRAM serves a third of the B traffic (ncu: 652 GB
+    // per build).  So a CTA starts its sweep at the tile the others are currently working on (a global counter the producers
+    // keep current) and wraps around: all resident CTAs stream the same few tiles and B is read from DRAM once per wave.
+    uint32_t* t0_slot = tmem_slot + 1;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 2); mbar_init(bar_empty + 8 * s, 1); }
@@ -304,12 +312,20 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         for (int i = lane; i < kQueue; i += 32) q_flag[i] = 0;
         if (lane == 0) { *q_head = 0u; *q_tail = 0u; *q_done = 0u; }
+        if (lane == 0 && rank == 0) {                                 // the pair's common starting tile, written to both CTAs
+            const uint32_t t0 = (p.phase != nullptr && T > 0) ? (uint32_t)(*reinterpret_cast<volatile int*>(p.phase + blockIdx.y)) % (uint32_t)T : 0u;
+            *t0_slot = t0;                                            // the peer reads it from here after the cluster barrier
+        }
     }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     if (*tmem_slot != 0u) __trap();            // the CTA owns the SM, so all 512 columns start at 0; addresses below assume it
+    int t_start;                               // first tile of this pair's sweep (leader's shared memory, read over DSMEM)
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %1, 0;\n\tld.shared::cluster.u32 %0, [ra];\n\t}"
+                 : "=r"(t_start) : "r"(smem_u32(t0_slot)) : "memory");
+    t_start += t_beg;
 
     long long life_clk = 0; unsigned long long life_ns = 0;
     const bool life = p.trace && threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2);
@@ -325,7 +341,8 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             else mbar_arrive_cluster(bar_a, 0);
         }
         int stage = 0; uint32_t phase = 0;
-        for (int t = t_beg; t < t_end; ++t) {
+        for (int tt = 0, t = t_start; tt < T; ++tt, t = (t + 1 == t_end) ? t_beg : t + 1) {
+            if (p.phase != nullptr && rank == 0 && (tt & 63) == 0 && issuer) p.phase[blockIdx.y] = t - t_beg;   // where this sweep is
             const int brow = t * BN + (int)rank * 128;              // this CTA stages its half of the tile's database rows
             if constexpr (SPLIT) {
                 // all K blocks of a tile share the barriers of the tile's first ring slot (stages % kblocks == 0): the issuers
@@ -381,12 +398,12 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 else if (warp == 1) issue_split<0, 2>(p, base, a_off, b_off, bar_full, bar_empty, bar_tfull, bar_tempty, t_beg, t_end, issuer, lane);
                 else issue_split<1, 2>(p, base, a_off, b_off, bar_full, bar_empty, bar_tfull, bar_tempty, t_beg, t_end, issuer, lane);
             } else {
-            for (int t = t_beg + w; t < t_end; t += p.issuers) {
-                const int acc = (t - t_beg) & 1;
-                const uint32_t acc_phase = (uint32_t)((t - t_beg) >> 1) & 1u;
+            for (int tt = w; tt < T; tt += p.issuers) {
+                const int acc = tt & 1;
+                const uint32_t acc_phase = (uint32_t)(tt >> 1) & 1u;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 8 + 0] = clock64();
+                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 0] = clock64();
                 const uint32_t tmem_d = (uint32_t)(acc * BN);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
@@ -404,7 +421,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     __syncwarp();
                     advance(1);
                 }
-                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && lane == 0) p.trace[(t - t_beg) * 8 + 1] = clock64();
+                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 1] = clock64();
                 advance((p.issuers - 1) * p.kblocks);                   // the other issuer's tile
             }
             }
@@ -428,7 +445,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     const unsigned done = *reinterpret_cast<volatile unsigned*>(q_done);
                     const unsigned head = *reinterpret_cast<volatile unsigned*>(q_head);
                     if (done == (unsigned)(4 * EW) && head == tail) break;
-                    __nanosleep(40);
+                    __nanosleep(200);
                     continue;
                 }
                 __threadfence_block();
@@ -565,14 +582,13 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // columns of the tile this thread owns: [tile_col, tile_col + CPT) -- SPLIT: 64 columns of half h = slice & 1, taken from
         // CTA (slice >> 1)'s staged rows, i.e. accumulator columns [64 (slice >> 1), +64) of stage 2 * (tile parity) + h
         const int tile_col = SPLIT ? 128 * (slice >> 1) + 64 * (slice & 1) : slice * CPT;
-        for (int t = t_beg; t < t_end; ++t) {
-            const int tt = t - t_beg;
+        for (int tt = 0, t = t_start; tt < T; ++tt, t = (t + 1 == t_end) ? t_beg : t + 1) {
             const int acc = SPLIT ? 2 * (tt & 1) + (slice & 1) : (tt & 1);
             const uint32_t acc_phase = (uint32_t)(tt >> 1) & 1u;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && t - t_beg < 64 && threadIdx.x == kNonEpiThreads;
-            if (tr) p.trace[(t - t_beg) * 8 + 2] = clock64();
+            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && threadIdx.x == kNonEpiThreads;
+            if (tr) p.trace[tt * 8 + 2] = clock64();
             if (!SEED) thr_cur = fmaxf(thr_cur, row_thr[r]);
             const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(SPLIT ? acc * 128 + (slice >> 1) * 64 : acc * BN + slice * CPT);
             const int col0 = t * BN + tile_col;
@@ -587,7 +603,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * (SPLIT ? (tt & 1) : acc), 0);
-                if (tr) p.trace[(t - t_beg) * 8 + 3] = clock64();
+                if (tr) p.trace[tt * 8 + 3] = clock64();
                 process(va, col0, 0, odd);
                 process(vb, col0 + 32, CT > 1 ? 1 : 0, odd);
             } else {
@@ -630,7 +646,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (life) {
         unsigned long long ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
         long long* o = p.trace + 512 + (blockIdx.x == 0 ? 0 : 4);
-        o[0] = clock64() - life_clk; o[1] = (long long)(ns1 - life_ns); o[2] = t_end - t_beg; o[3] = blockIdx.x;
+        o[0] = clock64() - life_clk; o[1] = (long long)(ns1 - life_ns); o[2] = T; o[3] = blockIdx.x;
     }
     cluster_sync_all();                        // neither CTA may exit (or free TMEM) while the other can still signal / write it
     if (warp == 2) {
@@ -1018,7 +1034,7 @@ static cudaError_t launch_ew(dim3 grid, size_t smem, cudaStream_t st, const CUte
 // seeds != nullptr && seed_out == nullptr: main pass starting from the seeded thresholds;  seed_out != nullptr: SEED pass.
 static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n,
                          float thr_lo, int remove_self, float* cand_val, int* cand_idx, float* cand_min, const float* seeds,
-                         float* seed_out, cudaStream_t st) {
+                         float* seed_out, int* phase, cudaStream_t st) {
     const bool seed_pass = seed_out != nullptr;
     const int64_t n_db = seed_pass ? (n + pl.seed_stride - 1) / pl.seed_stride : n;
     CUtensorMap mq, mdb;
@@ -1031,6 +1047,7 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
     p.debug = env_int("SNG_KNN_DEBUG", 1, 63);
     p.issuers = env_int("SNG_KNN_ISSUERS", 1, 2) ? env_int("SNG_KNN_ISSUERS", 1, 2) : (pl.kblocks <= 3 ? 2 : 1);
     p.cand_val = cand_val; p.cand_idx = cand_idx; p.cand_min = cand_min;
+    p.phase = seed_pass ? nullptr : phase;
     p.seeds = seed_pass ? nullptr : seeds; p.seed_out = seed_out; p.seed_q = pl.seed_q; p.seed_stride = pl.seed_stride > 0 ? pl.seed_stride : 1;
     dim3 grid((unsigned)(2 * ((nq + 2 * BM - 1) / (2 * BM))), (unsigned)p.nsplit);        // x: CTA pairs (cluster of 2), y: column splits
     p.trace = nullptr;
@@ -1093,7 +1110,7 @@ extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, i
     const size_t slots = (size_t)nq * pl.lists() * pl.cand;
     const size_t part = (size_t)kFbWaveRows * ((n + kChunk - 1) / kChunk) * top_k;
     return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + 2 * align256(part * 4) +
-           align256((size_t)nq * kSeedGroups * 4) + 1024;
+           align256((size_t)nq * kSeedGroups * 4) + 256 + 1024;
 }
 
 // The launch plan sng_simknn_build uses for this shape: out[0..7] = epilogue warps per lane quarter, candidate slots per list,
@@ -1116,13 +1133,13 @@ extern "C" int sng_simknn_seed(const uint16_t* xq, const uint16_t* xall, int64_t
     Plan pl;
     if (int rc = make_plan(&pl, nq, n, d, 0, 8, force_ew)) return rc;
     pl.seed_stride = seed_stride; pl.seed_q = 1;
-    return launch_stage1(pl, xq, xall, ldb, nq, 0, n, -3.0e38f, 0, nullptr, nullptr, nullptr, nullptr, seeds_out, (cudaStream_t)stream);
+    return launch_stage1(pl, xq, xall, ldb, nq, 0, n, -3.0e38f, 0, nullptr, nullptr, nullptr, nullptr, seeds_out, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n, int64_t d,
                                  int cand, float thr_lo, int remove_self, int32_t* cand_idx, float* cand_val, float* cand_min,
                                  int force_ew, int force_nsplit, int* lists_out, const float* seeds, int seed_q, int seed_stride,
-                                 void* stream) {
+                                 int32_t* sweep_phase, void* stream) {
     if (int rc = check_common("sng_simknn_stage1", xq, xall, ldb, nq, q_offset, n, d)) return rc;
     SNG_REQUIRE(cand >= 8 && cand <= 128 && cand_idx && cand_val && cand_min, "sng_simknn_stage1: bad cand / outputs");
     SNG_REQUIRE(force_ew == 0 || force_ew == 1 || force_ew == 2 || force_ew == 4, "sng_simknn_stage1: force_ew must be 0, 1, 2 or 4");
@@ -1134,7 +1151,7 @@ extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64
     SNG_REQUIRE(!seeds || (seed_q >= 1 && seed_q <= kSeedGroups - 2 && seed_stride >= 1),
                 "sng_simknn_stage1: seeds need 1 <= seed_q <= %d, seed_stride >= 1", kSeedGroups - 2);
     pl.seed_q = seeds ? seed_q : 0; pl.seed_stride = seeds ? seed_stride : 0;
-    return launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min, seeds, nullptr, (cudaStream_t)stream);
+    return launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min, seeds, nullptr, sweep_phase, (cudaStream_t)stream);
 }
 
 extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_t ldb, const float* xq32, const float* xall32, int64_t ld32,
@@ -1159,14 +1176,16 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     const size_t part = (size_t)kFbWaveRows * n_chunks * top_k;
     float* part_s = reinterpret_cast<float*>(w); w += align256(part * 4);
     int* part_i = reinterpret_cast<int*>(w); w += align256(part * 4);
-    float* seeds = reinterpret_cast<float*>(w);
+    float* seeds = reinterpret_cast<float*>(w); w += align256((size_t)nq * kSeedGroups * 4);
+    int* phase = reinterpret_cast<int*>(w);
+    if (cudaMemsetAsync(phase, 0, 8 * sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
     if (cudaMemsetAsync(n_fallback, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
     // approximate scores below thr - eps can never reach thr exactly
     const float thr_lo = thr - 1.01f * kScoreEps;
     if (pl.seed_stride > 0)
-        if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, nullptr, nullptr, nullptr, nullptr, seeds, st)) return rc;
+        if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, nullptr, nullptr, nullptr, nullptr, seeds, nullptr, st)) return rc;
     if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min,
-                               pl.seed_stride > 0 ? seeds : nullptr, nullptr, st)) return rc;
+                               pl.seed_stride > 0 ? seeds : nullptr, nullptr, getenv("SNG_KNN_NOPHASE") ? nullptr : phase, st)) return rc;
     const int d4 = (int)((d + 3) / 4);
     {
         const int blocks = (int)((nq + 7) / 8 < (int64_t)sm_count() * 8 ? (nq + 7) / 8 : (int64_t)sm_count() * 8);

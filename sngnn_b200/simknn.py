@@ -103,7 +103,7 @@ def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_
     seeds = seed_pass(xh, xh, d, seed_stride, force_ew) if seed_stride > 0 else None
     _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh), _C.ptr(xh), xh.size(1), n, 0, n, d, cand, float(thr_lo), int(remove_self),
                                         _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), force_ew, force_nsplit, ctypes.byref(nl),
-                                        _C.ptr(seeds), int(seed_q), int(seed_stride), _C.stream()),
+                                        _C.ptr(seeds), int(seed_q), int(seed_stride), None, _C.stream()),
              "sng_simknn_stage1")
     s = nl.value
     return ci[: n * s * cand].reshape(n, s, cand), cv[: n * s * cand].reshape(n, s, cand), cm[: n * s].reshape(n, s), xf, xh
