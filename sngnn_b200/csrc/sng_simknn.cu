@@ -38,6 +38,14 @@ constexpr int kMaxStages = 10;
 constexpr int kFallbackBlocks = 32;
 constexpr int kMaxCandTotal = 192;      // lists per row * cand <= this; stage 2 expands every candidate into 3 columns
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+// Instrumented builds (make EXTRA=-DSNG_KNN_INSTRUMENT): the SNG_KNN_DEBUG work-skipping modes and the SNG_KNN_TRACE
+// per-tile clock stamps used for the pipeline analysis in DESIGN.md.  Compiled out of the product library: the checks
+// sit in the per-tile loops of every role.
+#ifdef SNG_KNN_INSTRUMENT
+constexpr bool kInstr = true;
+#else
+constexpr bool kInstr = false;
+#endif
 #ifdef SNG_KNN_EVTRACE
 constexpr bool kEvTrace = true;          // per-event statistics in SNG_KNN_TRACE runs (costs local memory in the epilogue)
 #else
@@ -168,6 +176,7 @@ template <int W, int NI>
 __device__ __forceinline__ void issue_split(const Stage1Params& p, uint32_t base, uint32_t a_off, uint32_t b_off, uint32_t bar_full, uint32_t bar_empty,
                                             uint32_t bar_tfull, uint32_t bar_tempty, int t_beg, int t_end, bool issuer, int lane) {
     constexpr uint32_t kIdescHalf = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    long long* const trc = kInstr ? p.trace : nullptr;
     const uint64_t adesc0 = make_smem_desc(base + a_off);
     const uint64_t bdesc0 = make_smem_desc(base + b_off);
     const int kb2 = p.kblocks == 2;                          // second K block present
@@ -186,7 +195,7 @@ __device__ __forceinline__ void issue_split(const Stage1Params& p, uint32_t base
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            if (h == 0 && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 0] = clock64();
+            if (h == 0 && trc && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) trc[tt * 8 + 0] = clock64();
             const uint32_t tmem_d = (uint32_t)((acc0 + h) * 128);
             const uint64_t hb = (uint64_t)(h * (kTileBytes >> 5));                       // + 64 rows x 128 B
             if (issuer) {
@@ -201,7 +210,7 @@ __device__ __forceinline__ void issue_split(const Stage1Params& p, uint32_t base
             }
             __syncwarp();
         }
-        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 1] = clock64();
+        if (trc && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) trc[tt * 8 + 1] = clock64();
         st0 += step;
         while (st0 >= nst) { st0 -= nst; ph0 ^= 1u; }
     }
@@ -226,6 +235,8 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     // sits on the critical path of every tile and any late epilogue warp stalls the tensor pipe; with four, each issuer owns
     // two stages and a stage is not needed again for a whole tile period after it was drained.
     constexpr bool SPLIT = (EW == 4);
+    const int dbg = kInstr ? p.debug : 0;
+    long long* const trc = kInstr ? p.trace : nullptr;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -328,7 +339,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     t_start += t_beg;
 
     long long life_clk = 0; unsigned long long life_ns = 0;
-    const bool life = p.trace && threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2);
+    const bool life = trc && threadIdx.x == 0 && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 2);
     if (life) { life_clk = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(life_ns)); }
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs, whole warp, one lane issues)
@@ -349,7 +360,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 // pay one wait and one commit per tile instead of one per K block
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (issuer) {
-                    if (!(p.debug & 4)) {
+                    if (!(dbg & 4)) {
                         for (int kb = 0; kb < p.kblocks; ++kb)
                             tma_load_2d_pair(base + b_off + (uint32_t)(stage + kb) * kTileBytes, &map_db, (bar_full + 8 * stage) & kPeerMask, kb * BK, brow);
                         if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * (uint32_t)p.kblocks * kTileBytes);
@@ -364,7 +375,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             for (int kb = 0; kb < p.kblocks; ++kb) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (issuer) {
-                    if (!(p.debug & 4)) {
+                    if (!(dbg & 4)) {
                         tma_load_2d_pair(base + b_off + (uint32_t)stage * kTileBytes, &map_db, (bar_full + 8 * stage) & kPeerMask, kb * BK, brow);
                         if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * kTileBytes);
                         else mbar_arrive_cluster(bar_full + 8 * stage, 0);
@@ -403,7 +414,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 const uint32_t acc_phase = (uint32_t)(tt >> 1) & 1u;
                 mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 0] = clock64();
+                if (trc && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) trc[tt * 8 + 0] = clock64();
                 const uint32_t tmem_d = (uint32_t)(acc * BN);
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(bar_full + 8 * stage, phase);
@@ -421,7 +432,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     __syncwarp();
                     advance(1);
                 }
-                if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) p.trace[tt * 8 + 1] = clock64();
+                if (trc && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && lane == 0) trc[tt * 8 + 1] = clock64();
                 advance((p.issuers - 1) * p.kblocks);                   // the other issuer's tile
             }
             }
@@ -526,7 +537,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // was pruned with (cand_min) and stage 2 only accepts a row whose k-th exact score clears it.
         // `ci` = chunk index within the thread's tile slice (compile time after unrolling), `odd` = tile parity.
         auto process = [&](uint32_t (&v)[32], int col0, int ci, bool odd) {
-            if (p.debug & 1) { if (__uint_as_float(v[0] ^ v[31]) == 12345.678f) thr_cur = 0.f; return; }
+            if (dbg & 1) { if (__uint_as_float(v[0] ^ v[31]) == 12345.678f) thr_cur = 0.f; return; }
             float m[11];
             auto tree = [&]() {
 #pragma unroll
@@ -546,11 +557,11 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 gmax[CT + ci] = fmaxf(gmax[CT + ci], odd ? mx : -CUDART_INF_F);
                 return;
             }
-            const bool cnt_on = kEvTrace && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == kNonEpiThreads;
+            const bool cnt_on = kEvTrace && trc && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == kNonEpiThreads;
             if (cnt_on) ++ev_chunks;
             if (__any_sync(0xffffffffu, mx > thr_cur)) {           // rare slow path
                 const long long ev0 = cnt_on ? clock64() : 0;
-                if (p.debug & 8) return;
+                if (dbg & 8) return;
                 if ((unsigned)(self_col - col0) < 32u || col0 + 32 > n) {
                     // the chunk holds the row's own column, or columns beyond n (zero filled): once per row / last tile only
 #pragma unroll
@@ -587,15 +598,15 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const uint32_t acc_phase = (uint32_t)(tt >> 1) & 1u;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && threadIdx.x == kNonEpiThreads;
-            if (tr) p.trace[tt * 8 + 2] = clock64();
+            const bool tr = trc && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && threadIdx.x == kNonEpiThreads;
+            if (tr) trc[tt * 8 + 2] = clock64();
             if (!SEED) thr_cur = fmaxf(thr_cur, row_thr[r]);
             const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(SPLIT ? acc * 128 + (slice >> 1) * 64 : acc * BN + slice * CPT);
             const int col0 = t * BN + tile_col;
             const bool odd = (t & 1) != 0;
             if (CPT == 64) {
                 // both loads in flight at once; the accumulator stage goes back to the MMA warp before any processing
-                if (!(p.debug & 2)) {
+                if (!(dbg & 2)) {
                     tmem_ld32(taddr, va);
                     tmem_ld32(taddr + 32, vb);
                     tmem_ld_wait();
@@ -603,7 +614,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * (SPLIT ? (tt & 1) : acc), 0);
-                if (tr) p.trace[tt * 8 + 3] = clock64();
+                if (tr) trc[tt * 8 + 3] = clock64();
                 process(va, col0, 0, odd);
                 process(vb, col0 + 32, CT > 1 ? 1 : 0, odd);
             } else {
@@ -636,8 +647,8 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             __syncwarp();
             __threadfence_block();
             if (lane == 0) atomicAdd(q_done, 1u);                    // this warp will push nothing more
-            if (kEvTrace && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == kNonEpiThreads) {
-                p.trace[525] = ev_chunks; p.trace[520] = ev_n; p.trace[521] = ev_push; p.trace[526] = ev_cyc; p.trace[527] = ev_max;
+            if (kEvTrace && trc && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == kNonEpiThreads) {
+                trc[525] = ev_chunks; trc[520] = ev_n; trc[521] = ev_push; trc[526] = ev_cyc; trc[527] = ev_max;
             }
         }
     }
@@ -645,7 +656,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     __syncthreads();
     if (life) {
         unsigned long long ns1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
-        long long* o = p.trace + 512 + (blockIdx.x == 0 ? 0 : 4);
+        long long* o = trc + 512 + (blockIdx.x == 0 ? 0 : 4);
         o[0] = clock64() - life_clk; o[1] = (long long)(ns1 - life_ns); o[2] = T; o[3] = blockIdx.x;
     }
     cluster_sync_all();                        // neither CTA may exit (or free TMEM) while the other can still signal / write it
