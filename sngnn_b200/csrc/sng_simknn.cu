@@ -77,8 +77,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
     asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
                  ::"r"(bar), "r"(cta) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
 // Bounded wait: a protocol bug must trap (error returned to the caller) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     uint32_t done, polls = 0;
     unsigned long long t0 = 0;
     while (true) {
@@ -92,6 +98,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             else if (now - t0 > 4000000000ull) __trap();     // 4 s
         }
     }
+}
+// hot-loop form: one inline try (it suspends in hardware for a while), the bounded polling loop stays out of line
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 // TMA load issued by either CTA of the pair into its OWN shared memory; the bytes are credited to the LEADER's barrier
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1) {
