@@ -148,6 +148,23 @@ SNG_API int sng_class_sums_f64(const float* xhat, const int32_t* y, int64_t n, i
                        double* sums, double* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Graph preparation (once per edge_index; the reference redoes it every forward in Python/PyG:
+ * R: models/models.py:117-127 (++), :234-236 (+), :323 (base)).
+ *   edge_index [2, num_edges] int64 (row 0 = sources, row 1 = targets), n nodes.
+ *   N self loops are appended at the END; with remove_self_loops every src == dst edge is then dropped.
+ *   rowptr_in [n+1], col_in [num_edges + n capacity]: CSR by target, sources in original edge-position order (the
+ *   tie-break order of the selection); inv_deg [n] = 1/max(in-degree, 1).
+ *   structural != 0 (SNConv_plus_plus): rowptr_out [n+1], col_out [capacity] = CSR by (src - min src) holding the targets
+ *   (A of R: models.py:124-127), col_in_shift [capacity] = col_in - min src (its transpose, used by the backward).
+ *   info (device int32[2]) = {number of kept edges E', min src}.  Only the first E' entries of col_* are meaningful.
+ */
+SNG_API size_t sng_graph_prepare_workspace_bytes(int64_t num_edges, int64_t n);
+SNG_API int sng_graph_prepare(const int64_t* edge_index, int64_t num_edges, int64_t n, int remove_self_loops, int structural,
+                      int32_t* rowptr_in, int32_t* col_in, float* inv_deg,
+                      int32_t* rowptr_out, int32_t* col_out, int32_t* col_in_shift,
+                      int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K1  all-pairs similarity-kNN builder (tcgen05 / TMA / TMEM), never materialising the N x N matrix.
  *   xq_f16  [nq , ldh]  normalised query rows  (FP16, zero padded, ldh % 8 == 0, ldh >= 16*ceil(d/16), 16-byte aligned)
  *   xall_f16[n  , ldh]  normalised database rows

@@ -11,7 +11,8 @@ int32 CSR arrays the kernels consume:
   * CSR by SHIFTED SOURCE (`rowptr_out`, `col_out`): out-neighbours t of node (src - min src), for
     out_0 = A @ W^T (R: :124-130);  `col_in_shift = col_in - min(src)` serves its transpose in backward.
 
-Pure torch (works on CPU tensors too, which is what the host-logic tests use); the sort is stable.
+CUDA `edge_index`: one call of `sng_graph_prepare` (stable radix sort by target / source, include/sng.h).  CPU tensors
+(the host-logic and gloo tests): the same construction in torch, with a stable argsort.
 """
 import weakref
 
@@ -82,6 +83,12 @@ def prepare(edge_index, num_nodes, remove_self_loops, structural=False, processe
         raise ValueError("edge_index refers to a node id >= num_nodes")
     if num_nodes >= 2 ** 31 or edge_index.size(1) + num_nodes >= 2 ** 31:
         raise ValueError("graph too large for int32 CSR")
+    if edge_index.is_cuda and not processed:
+        g = _prepare_cuda(edge_index, int(num_nodes), bool(remove_self_loops), bool(structural))
+        if len(_CACHE) >= _CACHE_MAX:
+            _CACHE.pop(next(iter(_CACHE)))
+        _CACHE[key] = (weakref.ref(edge_index), g)
+        return g
     ei = edge_index if processed else process_edges(edge_index, num_nodes, remove_self_loops)
     src, dst = ei[0], ei[1]
     g = PreparedGraph()
@@ -101,6 +108,42 @@ def prepare(edge_index, num_nodes, remove_self_loops, structural=False, processe
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = (weakref.ref(edge_index), g)
+    return g
+
+
+def _prepare_cuda(edge_index, n, remove_self_loops, structural):
+    from . import _C
+    lib = _C.lib()
+    ei = edge_index.contiguous()
+    if ei.dtype != torch.int64:
+        ei = ei.long()
+    e = ei.size(1)
+    dev = ei.device
+    cap = e + n
+    g = PreparedGraph()
+    g.n = n
+    rowptr_in = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    col_in = torch.empty(cap, dtype=torch.int32, device=dev)
+    g.inv_deg = torch.empty(n, dtype=torch.float32, device=dev)
+    rowptr_out = torch.empty(n + 1, dtype=torch.int32, device=dev) if structural else None
+    col_out = torch.empty(cap, dtype=torch.int32, device=dev) if structural else None
+    col_in_shift = torch.empty(cap, dtype=torch.int32, device=dev) if structural else None
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    wbytes = lib.sng_graph_prepare_workspace_bytes(e, n)
+    if wbytes == 0:
+        raise ValueError("graph too large for int32 CSR")
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    _C.check(lib.sng_graph_prepare(_C.ptr(ei), e, n, int(remove_self_loops), int(structural), _C.ptr(rowptr_in), _C.ptr(col_in),
+                                   _C.ptr(g.inv_deg), _C.ptr(rowptr_out), _C.ptr(col_out), _C.ptr(col_in_shift), _C.ptr(info),
+                                   _C.ptr(ws), wbytes, _C.stream()), "sng_graph_prepare")
+    kept, shift = (int(v) for v in info.tolist())               # one sync: the arrays are narrowed to the kept edges
+    g.num_edges = kept
+    g.rowptr_in, g.col_in = rowptr_in, col_in[:kept]
+    g.src_shift = shift if structural else 0
+    g.rowptr_out = rowptr_out
+    g.col_out = col_out[:kept] if structural else None
+    g.col_in_shift = col_in_shift[:kept] if structural else None
+    g.dst_sorted = None
     return g
 
 

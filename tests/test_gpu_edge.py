@@ -153,3 +153,30 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError):
         SF.edge_topk_agg(torch.randn(2, 4, device=DEV), g, 65, 0.0)     # top_k > SNG_MAX_TOPK
     assert "top_k" in _C.last_error()
+
+
+@pytest.mark.parametrize("n,e,rsl,structural,sym", [(5000, 60000, True, True, True), (5000, 60000, False, True, False),
+                                                    (300, 0, True, True, False), (4097, 9000, False, False, True), (70000, 900000, True, True, True)])
+def test_graph_prepare_cuda_equals_torch(n, e, rsl, structural, sym):
+    """sng_graph_prepare (stable radix sort on the GPU) == the torch construction (stable argsort) of graph.py on the CPU:
+    identical CSR arrays, i.e. identical in-edge POSITION order, which is the tie-break order of the selection rule."""
+    from sngnn_b200 import synth, graph as G
+    if e:
+        ei = synth.make_graph(n, e, seed=n, symmetric=sym, hub_offset=3.0)
+        extra = torch.tensor([[5, 9, 9, 7], [5, 9, 2, 7]])                       # pre-existing loops and a duplicate-prone edge
+        ei = torch.cat([ei, extra, ei[:, :50]], dim=1)                           # duplicates are kept (SURVEY.md appendix A.1)
+        ei = ei[:, torch.randperm(ei.size(1), generator=torch.Generator().manual_seed(1))]   # not sorted: position order matters
+        if structural:
+            ei = ei[:, ei[0] >= 3]                                               # min(src) = 3: the shift quirk of R models.py:125
+    else:
+        ei = torch.zeros(2, 0, dtype=torch.long)
+    G.clear_cache()
+    ref = G.prepare(ei, n, rsl, structural=structural)
+    got = G.prepare(ei.to(DEV), n, rsl, structural=structural)
+    assert got.num_edges == ref.num_edges and got.n == ref.n and got.src_shift == ref.src_shift
+    for name in ("rowptr_in", "col_in", "rowptr_out", "col_out", "col_in_shift"):
+        a, b = getattr(got, name), getattr(ref, name)
+        assert (a is None) == (b is None), name
+        if a is not None:
+            assert torch.equal(a.cpu(), b), name
+    torch.testing.assert_close(got.inv_deg.cpu(), ref.inv_deg, rtol=1e-6, atol=0)
