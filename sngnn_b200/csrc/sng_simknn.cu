@@ -83,6 +83,14 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t cta) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(cta));
+    return ra;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // Bounded wait: a protocol bug must trap (error returned to the caller) instead of hanging the GPU.
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     uint32_t done, polls = 0;
@@ -603,15 +611,22 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // columns of the tile this thread owns: [tile_col, tile_col + CPT) -- SPLIT: 64 columns of half h = slice & 1, taken from
         // CTA (slice >> 1)'s staged rows, i.e. accumulator columns [64 (slice >> 1), +64) of stage 2 * (tile parity) + h
         const int tile_col = SPLIT ? 128 * (slice >> 1) + 64 * (slice & 1) : slice * CPT;
+        // loop-invariant addresses, pinned in registers (the per-tile loop is issue-bound; left alone the compiler re-derives
+        // them from threadIdx every tile to save registers): TMEM address / accumulator-full barrier of the EVEN tiles, the
+        // leader's hand-back barrier; odd tiles are a constant away
+        uint32_t taddr_e = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(SPLIT ? (slice & 1) * 128 + (slice >> 1) * 64 : slice * CPT);
+        uint32_t bar_tf_e = bar_tfull + 8u * (SPLIT ? (uint32_t)(slice & 1) : 0u);
+        uint32_t bar_te_e = mapa_cluster(bar_tempty, 0);
         for (int tt = 0, t = t_start; tt < T; ++tt, t = (t + 1 == t_end) ? t_beg : t + 1) {
-            const int acc = SPLIT ? 2 * (tt & 1) + (slice & 1) : (tt & 1);
+            asm volatile("" : "+r"(taddr_e), "+r"(bar_tf_e), "+r"(bar_te_e));
+            const uint32_t par = (uint32_t)tt & 1u;
             const uint32_t acc_phase = (uint32_t)(tt >> 1) & 1u;
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            mbar_wait(bar_tf_e + par * (SPLIT ? 16u : 8u), acc_phase);
             tc_fence_after();
             const bool tr = trc && blockIdx.x == 0 && blockIdx.y == 0 && tt < 64 && threadIdx.x == kNonEpiThreads;
             if (tr) trc[tt * 8 + 2] = clock64();
             if (!SEED) thr_cur = fmaxf(thr_cur, row_thr[r]);
-            const uint32_t taddr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(SPLIT ? acc * 128 + (slice >> 1) * 64 : acc * BN + slice * CPT);
+            const uint32_t taddr = taddr_e + par * (uint32_t)(SPLIT ? 256 : BN);
             const int col0 = t * BN + tile_col;
             const bool odd = (t & 1) != 0;
             if (CPT == 64) {
@@ -623,7 +638,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * (SPLIT ? (tt & 1) : acc), 0);
+                if (lane == 0) mbar_arrive_remote(bar_te_e + 8u * par);
                 if (tr) trc[tt * 8 + 3] = clock64();
                 process(va, col0, 0, odd);
                 process(vb, col0 + 32, CT > 1 ? 1 : 0, odd);
@@ -640,7 +655,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                         // every load of this accumulator stage has landed: hand the stage back to the leader's MMA warp
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+                        if (lane == 0) mbar_arrive_remote(bar_te_e + 8u * par);
                     }
                     process(vb, col0 + (c + 1) * 32, c + 1, odd);
                 }
@@ -1035,11 +1050,19 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     // (the seed pass is never column-split, so with many splits it would cost as much as the main pass)
     const bool forced = env_int("SNG_KNN_SEED_S", 2, 256) != 0;
     if (top_k > 0 && (ns <= 2 || forced) && !getenv("SNG_KNN_NOSEED")) {
-        int stride = env_int("SNG_KNN_SEED_S", 2, 256);
-        if (!stride) stride = 16;
-        int q = env_int("SNG_KNN_SEED_Q", 1, kSeedGroups - 2);
-        if (!q) q = seed_quantile(top_k, stride, 2e-5);
-        if (pl->tiles / stride >= 32 && q <= kSeedGroups - 4) { pl->seed_stride = stride; pl->seed_q = q; }
+        if (forced) {
+            const int stride = env_int("SNG_KNN_SEED_S", 2, 256);
+            int q = env_int("SNG_KNN_SEED_Q", 1, kSeedGroups - 2);
+            if (!q) q = seed_quantile(top_k, stride, 2e-5);
+            if (pl->tiles / stride >= 8 && q <= kSeedGroups - 4) { pl->seed_stride = stride; pl->seed_q = q; }
+        } else {
+            // sample 1/16 of the columns when there are plenty, more of them for small databases; a large top_k needs a
+            // sparser sample for the quantile to stay inside the 16 groups
+            for (int stride = pl->tiles >= 512 ? 16 : (pl->tiles / 32 > 4 ? pl->tiles / 32 : 4); stride <= 64 && !pl->seed_stride; stride *= 2) {
+                const int q = seed_quantile(top_k, stride, 2e-5);
+                if (pl->tiles / stride >= 8 && q <= kSeedGroups - 4) { pl->seed_stride = stride; pl->seed_q = q; }
+            }
+        }
     }
     return SNG_OK;
 }

@@ -150,7 +150,8 @@ def test_seed_pass_group_maxima(n, d, stride, ew):
 
 
 @pytest.mark.parametrize("n,d,k,thr,rs,kind,stride,q", [(20000, 65, 10, -1.0, True, "normal", 2, 0), (20000, 65, 10, 0.5, True, "clustered", 2, 0),
-                                                         (36000, 128, 5, -1.0, False, "clustered", 4, 0), (20000, 40, 10, -1.0, True, "normal", 2, 1)])
+                                                         (36000, 128, 5, -1.0, False, "clustered", 4, 0), (20000, 40, 10, -1.0, True, "normal", 2, 1),
+                                                         (24000, 200, 10, 0.2, True, "clustered", 2, 0), (70000, 300, 50, -1.0, True, "clustered", 32, 0)])
 def test_seeded_build_matches_oracle(n, d, k, thr, rs, kind, stride, q, monkeypatch):
     """Full build with threshold seeding switched on (SNG_KNN_SEED_S shrinks the stride so it engages at test sizes;
     q = 1 makes the seeded threshold far too aggressive, so the proof must send many rows to the exact scan)."""
@@ -173,3 +174,19 @@ def test_seeded_build_matches_oracle(n, d, k, thr, rs, kind, stride, q, monkeypa
     assert check_tie_order(idx, sim, cnt)
     if q == 1:
         assert int(nfb) > 0
+
+
+@pytest.mark.parametrize("n,d,k", [(40000, 65, 10), (20000, 128, 50), (9000, 65, 10)])
+def test_default_plan_build_matches_oracle(n, d, k):
+    """The plan the library picks by itself (seed stride / quantile adapted to the database size and top_k)."""
+    from sngnn_b200 import simknn
+    x = _features(n, d, "clustered", seed=3 * n + d)
+    plan = simknn.build_plan(n, n, d, k)
+    idx, sim, cnt, nfb = simknn.build_knn(x.to(DEV), k, 0.0, True, return_fallback=True)
+    torch.cuda.synchronize()
+    rows = 1200
+    idx_ref, sim_ref, cnt_ref = _oracle(x, k, 0.0, True, 0, rows)
+    res = compare_lists(idx[:rows], cnt[:rows], idx_ref, cnt_ref, _score64(x), 0.0)
+    print(f"default plan n={n} d={d} k={k} plan={plan}: {res} fallback_rows={int(nfb)}")
+    assert res["out_of_band"] == 0, res
+    assert check_tie_order(idx, sim, cnt)
