@@ -263,11 +263,15 @@ def run_ours(args):
         torch.cuda.empty_cache()
         ei = synth.make_graph(N, E, seed=1, device=dev, symmetric=True)
         y = synth.make_labels(N, C, seed=2, device=dev)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        g = G.prepare(ei, N, True, structural=True)
-        torch.cuda.synchronize()
-        prep_ms = (time.perf_counter() - t0) * 1e3
+        prep = []
+        for _ in range(3):                                    # first call pays cudaMalloc of the sort workspace; report the warm one
+            G.clear_cache()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g = G.prepare(ei, N, True, structural=True)
+            torch.cuda.synchronize()
+            prep.append((time.perf_counter() - t0) * 1e3)
+        prep_ms = min(prep)
         Ep = g.num_edges
         hid = 32
         torch.manual_seed(2)
@@ -333,7 +337,7 @@ def run_ours(args):
         nsel = int(sc.sum())
         bytes_fwd = Ep * (4 * hid + 4) + N * (8 * hid + 8) + 8 * N * k
         bytes_bwd = nsel * (3 * 4 * hid + 16) + 3 * N * 4 * hid + 2 * N * 4 * hid   # + the two accumulator memsets
-        extras = {"epoch_ms": ep_ms, "forward_ms": fw_ms, "graph_prep_ms": prep_ms,
+        extras = {"epoch_ms": ep_ms, "forward_ms": fw_ms, "graph_prep_ms": prep_ms, "graph_prep_first_call_ms": prep[0],
                   "epoch_config": f"SNGNN_Plus_Plus 2 layers hidden {hid} top_k={k} thr={thr} init_beta=0.5 on {args.workload}-shape graph "
                                   f"({Ep} edges after loop processing); epoch = fwd+loss+bwd+Adam + 2 eval forwards (R train.py:136-138)" +
                                   (f"; rows sharded over {world} ranks: all-gather of h per layer, reduce-scatter of dL/dh, all-reduce of parameter gradients" if world > 1 else ""),
