@@ -219,7 +219,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     idx, sim, cnt, nfb = out["r"]
-    n_fallback = int(nfb)
+    n_fallback, n_retry = int(nfb[0]), int(nfb[1])
 
     # ---- the dominant kernel alone (roofline): tensor-core main pass on this rank's rows, launched exactly as the
     # build launches it (same plan; thresholds seeded by the seed pass, which is timed separately) ---------------
@@ -358,6 +358,7 @@ def run_ours(args):
         parity = compare_lists(idx[:rows], cnt[:rows], iref, cref, lambda r, j: (n64[r] * n64[j]).sum(-1), thr)
         parity["rows_checked"] = rows
         parity["fallback_rows"] = n_fallback
+        parity["retry_rows"] = n_retry
         if not args.skip_cpu and world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             cpu_rows = min(args.cpu_rows, N)
@@ -378,10 +379,10 @@ def run_ours(args):
                            "features": args.features, "l2": "inputs larger than L2 (x-hat f16 %.0f MB, f32 %.0f MB)" % (N * ldh * 2 / 1e6, N * ld32 * 4 / 1e6),
                            "parallelism": f"row-shard x{world}" + (" + NCCL all-gather of x-hat" if world > 1 else "")},
                 "e2e": {"value": pairs / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-                "gpu_launches": (12 + (1 if plan["seed_stride"] > 0 else 0)) * args.steps,
+                "gpu_launches": (15 + (1 if plan["seed_stride"] > 0 else 0)) * args.steps,
                 "kernels_per_step": ["rownorm_kernel"] + (["simknn_stage1_kernel<seed>"] if plan["seed_stride"] > 0 else []) +
-                                    ["simknn_stage1_kernel", "simknn_rescore_kernel", "4 x (simknn_fb_scan_kernel, simknn_fb_merge_kernel)",
-                                     "simknn_fb_stream_kernel"],
+                                    ["simknn_stage1_kernel", "simknn_rescore_kernel", "simknn_retry_gather_kernel", "simknn_stage1_kernel (retry)",
+                                     "simknn_rescore_kernel (retry)", "4 x (simknn_fb_scan_kernel, simknn_fb_merge_kernel)", "simknn_fb_stream_kernel"],
                 "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
         line.update(extras)
         print(json.dumps(line))

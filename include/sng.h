@@ -173,8 +173,10 @@ SNG_API int sng_graph_prepare(const int64_t* edge_index, int64_t num_edges, int6
  * Stage 2 rescores them in FP32 (xq_f32 / xall_f32, leading dim ld32 % 4 == 0, zero padded), orders them by
  * (sim desc, index asc), applies thr / top_k and PROVES exactness: a row whose k-th exact score is not clear
  * of the best possible score of any dropped column is flagged and recomputed by an exact FP32 scan (stage 3).
+ * Rows stage 2 cannot prove first get a RETRY pass (a second, unseeded tensor-core pass over just those rows with long
+ * candidate lists); only rows that fail that proof too reach stage 3.
  * Outputs: idx [nq, top_k] int32 (-1 padded), sim [nq, top_k], cnt [nq]; n_fallback (device int32) counts
- * rows that needed stage 3.
+ * rows that needed stage 3, n_retry (device int32, may be NULL) rows that needed the retry pass.
  * Replaces (as "the reference rule on the complete graph") the selection of
  * R: models/models.py:145-156 and the blocked X X^T of R: SimGFAToolbox/dense.py:17-27.
  */
@@ -183,7 +185,7 @@ SNG_API int sng_simknn_build(const uint16_t* xq_f16, const uint16_t* xall_f16, i
                      const float* xq_f32, const float* xall_f32, int64_t ld32,
                      int64_t nq, int64_t q_offset, int64_t n, int64_t d,
                      int top_k, float thr, int remove_self,
-                     int32_t* idx, float* sim, int32_t* cnt, int32_t* n_fallback,
+                     int32_t* idx, float* sim, int32_t* cnt, int32_t* n_fallback, int32_t* n_retry,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stage 1 only (profiling / tests): cand_idx / cand_val [nq, lists, cand], cand_min [nq, lists] (upper bound of every

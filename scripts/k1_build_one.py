@@ -7,4 +7,4 @@ N, Fd, E, C = synth.SHAPES[sys.argv[1] if len(sys.argv) > 1 else "pokec"]
 x = synth.make_features(N, Fd, "clustered", seed=0, device="cuda", zscore=True)
 idx, sim, cnt, nfb = simknn.build_knn(x, 10, 0.0, True, return_fallback=True)
 torch.cuda.synchronize()
-print("ok", int(nfb), simknn.build_plan(N, N, Fd, 10))
+print("ok", int(nfb[0]), simknn.build_plan(N, N, Fd, 10))

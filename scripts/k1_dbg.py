@@ -11,4 +11,4 @@ print("stage1 ok", n, d, ew, round(time.time() - t, 3), "lists", ci.shape, "fill
 t = time.time()
 idx, sim, cnt, nfb = simknn.build_knn(x, 10, -1.0, True, return_fallback=True)
 torch.cuda.synchronize()
-print("build ok", round(time.time() - t, 3), "fallback", int(nfb), "cnt min", int(cnt.min()), flush=True)
+print("build ok", round(time.time() - t, 3), "fallback", int(nfb[0]), "cnt min", int(cnt.min()), flush=True)

@@ -31,7 +31,7 @@ SIGNATURES = {
     "sng_graph_prepare": (_I32, [_P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sng_simknn_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),
     "sng_simknn_build": (_I32, [_P, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, _I32, _F32, _I32,
-                                _P, _P, _P, _P, _P, _SZ, _P]),
+                                _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sng_simknn_stage1": (_I32, [_P, _P, _I64, _I64, _I64, _I64, _I64, _I32, _F32, _I32, _P, _P, _P, _I32, _I32, _P,
                                  _P, _I32, _I32, _P, _P]),
     "sng_simknn_seed": (_I32, [_P, _P, _I64, _I64, _I64, _I64, _I32, _I32, _P, _P]),

@@ -183,6 +183,8 @@ struct Stage1Params {
     const float* seeds;           // [nq, kSeedGroups] group maxima over a 1/seed_stride column sample, or nullptr
     float* seed_out;              // SEED kernel only
     int seed_q, seed_stride;      // row threshold = seed_q-th largest group maximum; sample = every seed_stride-th column
+    const int* nq_dev;            // retry pass: number of query rows actually present (device), or nullptr
+    const int* row_ids;           // retry pass: global row id (minus q_offset) of query row r, or nullptr (= r)
     int* phase;                   // [nsplit] sweep phase shared by all CTAs of a column split (see "Phase alignment"), or nullptr
     long long* trace;             // SNG_KNN_TRACE: [64 tiles][8] clock64 stamps of cluster 0's leader CTA, else nullptr
 };
@@ -255,6 +257,9 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     constexpr bool SPLIT = (EW == 4);
     const int dbg = kInstr ? p.debug : 0;
     long long* const trc = kInstr ? p.trace : nullptr;
+    // retry pass: the grid is sized for the maximum, the number of rows lives on the device; idle pairs leave together
+    const int nq_eff = p.nq_dev ? min(__ldg(p.nq_dev), p.nq) : p.nq;
+    if ((int)(blockIdx.x >> 1) * 2 * BM >= nq_eff) return;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -310,7 +315,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int i = lane; i < BM; i += 32) {
             float tau = p.thr_lo;
             const int grow = row0 + i;
-            if (!SEED && p.seeds != nullptr && grow < p.nq) {
+            if (!SEED && p.seeds != nullptr && grow < nq_eff) {
                 float g[kSeedGroups];
 #pragma unroll
                 for (int j = 0; j < kSeedGroups / 4; ++j) {
@@ -524,7 +529,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const int lists = p.nsplit;
             for (int i = lane; i < BM * L; i += 32) {
                 const int r = i / L, sl = i - r * L, grow = row0 + r;
-                if (grow < p.nq) {
+                if (grow < nq_eff) {
                     const size_t o = ((size_t)grow * lists + blockIdx.y) * L + sl;
                     const bool ok = sl < list_cnt[r];
                     p.cand_val[o] = ok ? list_val[sl * BM + r] : -CUDART_INF_F;
@@ -534,7 +539,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             for (int r = lane; r < BM; r += 32) {
                 const int grow = row0 + r;
                 // bound on everything dropped for this row: the final threshold (seed, evictions and filtered columns included)
-                if (grow < p.nq) p.cand_min[(size_t)grow * lists + blockIdx.y] = row_thr[r] > p.thr_lo ? row_thr[r] : -CUDART_INF_F;
+                if (grow < nq_eff) p.cand_min[(size_t)grow * lists + blockIdx.y] = row_thr[r] > p.thr_lo ? row_thr[r] : -CUDART_INF_F;
             }
         }
     } else if (warp >= 4) {
@@ -543,7 +548,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int quarter = warp & 3, slice = (warp - 4) >> 2;
         const int r = quarter * 32 + lane;                        // row within the CTA == TMEM lane
         const int grow = row0 + r;
-        const int self_col = p.remove_self ? (p.q_offset + grow) : -1;
+        const int self_col = p.remove_self ? p.q_offset + ((p.row_ids && grow < nq_eff) ? __ldg(p.row_ids + grow) : grow) : -1;
         const int n = p.n;
         float thr_cur = p.thr_lo;                                  // the row's pruning threshold as last read from shared memory
         long long ev_chunks = 0, ev_n = 0, ev_cyc = 0, ev_max = 0, ev_push = 0;   // SNG_KNN_TRACE statistics of warp 4 of CTA 0
@@ -662,7 +667,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
         }
         if (SEED) {
-            if (grow < p.nq) {
+            if (grow < nq_eff) {
                 // group id of sample column cs = ((cs >> 8) & 1) * 8 + ((cs & 255) >> 5)  (tile parity, chunk of the tile)
 #pragma unroll
                 for (int i = 0; i < 2 * CT; ++i)
@@ -710,13 +715,17 @@ __device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) { ret
 __global__ void __launch_bounds__(256) simknn_rescore_kernel(
     const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int nq, int n, int q_offset, int remove_self, int m_total,
     int nsplit, int top_k, float thr, float eps, const int* __restrict__ cand_idx, const float* __restrict__ cand_min,
-    int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out, int* __restrict__ fb_rows, int* __restrict__ n_fallback) {
+    int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out, int* __restrict__ fb_rows, int* __restrict__ n_fallback,
+    const int* __restrict__ nq_dev, const int* __restrict__ row_map) {
     extern __shared__ float sm2[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m3 = 3 * m_total;
     float* sc = sm2 + (size_t)warp * 2 * m3;
     int* id = reinterpret_cast<int*>(sc + m3);
-    for (int row = blockIdx.x * 8 + warp; row < nq; row += gridDim.x * 8) {
+    if (nq_dev) nq = min(nq, __ldg(nq_dev));
+    // retry pass: candidate lists are indexed by f, everything else by the row f stands for
+    for (int f = blockIdx.x * 8 + warp; f < nq; f += gridDim.x * 8) {
+        const int row = row_map ? __ldg(row_map + f) : f;
         const float* a = xq + (int64_t)row * ld32;
         const int self_col = remove_self ? q_offset + row : -1;
         int nvalid = 0;
@@ -724,7 +733,7 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
             const int m = m0 + lane;
             int j = -1; float s = -CUDART_INF_F;
             if (m < m3) {
-                const int base = __ldg(cand_idx + (size_t)row * m_total + m / 3), e = m % 3;
+                const int base = __ldg(cand_idx + (size_t)f * m_total + m / 3), e = m % 3;
                 if (base >= 0 && (e < 2 || (base & 31) != 30) && base + e < n && base + e != self_col) {
                     j = base + e;
                     s = dot_seq(a, xall + (int64_t)j * ld32, d4);
@@ -755,7 +764,7 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
         }
         for (int t = cnt + lane; t < top_k; t += 32) { idx_out[(size_t)row * top_k + t] = -1; sim_out[(size_t)row * top_k + t] = 0.f; }
         float bound = -CUDART_INF_F;                                 // best exact score any DROPPED column may have
-        for (int s0 = lane; s0 < nsplit; s0 += 32) bound = fmaxf(bound, __ldg(cand_min + (size_t)row * nsplit + s0) + eps);
+        for (int s0 = lane; s0 < nsplit; s0 += 32) bound = fmaxf(bound, __ldg(cand_min + (size_t)f * nsplit + s0) + eps);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
         if (lane == 0) {
@@ -764,6 +773,24 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
         }
         __syncwarp();
     }
+}
+
+// Retry pass, step 1: compact the FP16 rows of the first kRetryRows flagged query rows into one matrix (the TMA operand of
+// the second tensor-core pass); flagged rows beyond that go straight to the exact-scan list.
+constexpr int kRetryRows = 4096;
+__global__ void __launch_bounds__(256) simknn_retry_gather_kernel(const uint16_t* __restrict__ xq, int64_t ldb, const int* __restrict__ fb_rows,
+                                                                 const int* __restrict__ n_fb, uint16_t* __restrict__ xq_retry,
+                                                                 int* __restrict__ fb2_rows, int* __restrict__ n_fb2) {
+    const int nfb = *n_fb;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+    const int64_t vec = ldb / 8;                                             // 16-byte chunks per row (ldb % 8 == 0)
+    for (int f = w; f < min(nfb, kRetryRows); f += nw) {
+        const uint4* src = reinterpret_cast<const uint4*>(xq + (int64_t)fb_rows[f] * ldb);
+        uint4* dst = reinterpret_cast<uint4*>(xq_retry + (int64_t)f * ldb);
+        for (int64_t i = lane; i < vec; i += 32) dst[i] = src[i];
+    }
+    for (int f = kRetryRows + w * 32 + lane; f < nfb; f += nw * 32) fb2_rows[atomicAdd(n_fb2, 1)] = fb_rows[f];
 }
 
 // Stage 3 (parallel form): work item = (flagged row f, chunk of kChunk columns).  Scan: exact scores of the chunk in
@@ -1078,7 +1105,7 @@ static cudaError_t launch_ew(dim3 grid, size_t smem, cudaStream_t st, const CUte
 // seeds != nullptr && seed_out == nullptr: main pass starting from the seeded thresholds;  seed_out != nullptr: SEED pass.
 static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xall, int64_t ldb, int64_t nq, int64_t q_offset, int64_t n,
                          float thr_lo, int remove_self, float* cand_val, int* cand_idx, float* cand_min, const float* seeds,
-                         float* seed_out, int* phase, cudaStream_t st) {
+                         float* seed_out, int* phase, cudaStream_t st, const int* nq_dev = nullptr, const int* row_ids = nullptr) {
     const bool seed_pass = seed_out != nullptr;
     const int64_t n_db = seed_pass ? (n + pl.seed_stride - 1) / pl.seed_stride : n;
     CUtensorMap mq, mdb;
@@ -1092,6 +1119,7 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
     p.issuers = env_int("SNG_KNN_ISSUERS", 1, 2) ? env_int("SNG_KNN_ISSUERS", 1, 2) : (pl.kblocks <= 3 ? 2 : 1);
     p.cand_val = cand_val; p.cand_idx = cand_idx; p.cand_min = cand_min;
     p.phase = seed_pass ? nullptr : phase;
+    p.nq_dev = nq_dev; p.row_ids = row_ids;
     p.seeds = seed_pass ? nullptr : seeds; p.seed_out = seed_out; p.seed_q = pl.seed_q; p.seed_stride = pl.seed_stride > 0 ? pl.seed_stride : 1;
     dim3 grid((unsigned)(2 * ((nq + 2 * BM - 1) / (2 * BM))), (unsigned)p.nsplit);        // x: CTA pairs (cluster of 2), y: column splits
     p.trace = nullptr;
@@ -1154,7 +1182,9 @@ extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, i
     const size_t slots = (size_t)nq * pl.lists() * pl.cand;
     const size_t part = (size_t)kFbWaveRows * ((n + kChunk - 1) / kChunk) * top_k;
     return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + 2 * align256(part * 4) +
-           align256((size_t)nq * kSeedGroups * 4) + 256 + 1024;
+           align256((size_t)nq * kSeedGroups * 4) + 256 +
+           align256((size_t)kRetryRows * 1024 * 2) + 2 * align256((size_t)kRetryRows * kMaxCandTotal * 4) + align256((size_t)kRetryRows * 8 * 4) +
+           align256((size_t)nq * 4) + 256 + 1024;
 }
 
 // The launch plan sng_simknn_build uses for this shape: out[0..7] = epilogue warps per lane quarter, candidate slots per list,
@@ -1200,12 +1230,13 @@ extern "C" int sng_simknn_stage1(const uint16_t* xq, const uint16_t* xall, int64
 
 extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_t ldb, const float* xq32, const float* xall32, int64_t ld32,
                                 int64_t nq, int64_t q_offset, int64_t n, int64_t d, int top_k, float thr, int remove_self,
-                                int32_t* idx, float* sim, int32_t* cnt, int32_t* n_fallback, void* workspace, size_t workspace_bytes,
-                                void* stream) {
+                                int32_t* idx, float* sim, int32_t* cnt, int32_t* n_fallback, int32_t* n_retry, void* workspace,
+                                size_t workspace_bytes, void* stream) {
     if (int rc = check_common("sng_simknn_build", xq, xall, ldb, nq, q_offset, n, d)) return rc;
     SNG_REQUIRE(xq32 && xall32 && ld32 % 4 == 0 && ld32 >= d, "sng_simknn_build: FP32 rows must be padded to a multiple of 4 floats (ld32=%lld)", (long long)ld32);
     SNG_REQUIRE(top_k >= 1 && top_k <= SNG_KNN_MAX_TOPK, "sng_simknn_build: top_k=%d out of [1,%d]", top_k, SNG_KNN_MAX_TOPK);
     SNG_REQUIRE(idx && sim && cnt && n_fallback && workspace, "sng_simknn_build: null output / workspace");
+    SNG_REQUIRE(ldb <= 1024, "sng_simknn_build: ldb > 1024");
     if (workspace_bytes < sng_simknn_workspace_bytes(nq, n, d, top_k)) { set_error("sng_simknn_build: workspace too small (%zu < %zu)", workspace_bytes, sng_simknn_workspace_bytes(nq, n, d, top_k)); return SNG_ERR_WORKSPACE; }
     Plan pl;
     if (int rc = make_plan(&pl, nq, n, d, top_k, 0, 0)) return rc;
@@ -1221,8 +1252,29 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     float* part_s = reinterpret_cast<float*>(w); w += align256(part * 4);
     int* part_i = reinterpret_cast<int*>(w); w += align256(part * 4);
     float* seeds = reinterpret_cast<float*>(w); w += align256((size_t)nq * kSeedGroups * 4);
-    int* phase = reinterpret_cast<int*>(w);
+    int* phase = reinterpret_cast<int*>(w); w += 256;
+    // retry pass buffers
+    uint16_t* xq_retry = reinterpret_cast<uint16_t*>(w); w += align256((size_t)kRetryRows * 1024 * 2);
+    float* rcand_val = reinterpret_cast<float*>(w); w += align256((size_t)kRetryRows * kMaxCandTotal * 4);
+    int* rcand_idx = reinterpret_cast<int*>(w); w += align256((size_t)kRetryRows * kMaxCandTotal * 4);
+    float* rcand_min = reinterpret_cast<float*>(w); w += align256((size_t)kRetryRows * 8 * 4);
+    int* fb2_rows = reinterpret_cast<int*>(w); w += align256((size_t)nq * 4);
+    int* n_fb1 = reinterpret_cast<int*>(w);                          // rows stage 2 could not prove (device counter)
+    // retry plan (decided up front: it determines where stage 2 files the rows it cannot prove): the longest list that fits
+    Plan pr;
+    bool retry = false;
+    if (!getenv("SNG_KNN_NORETRY")) {
+        const int want = top_k + 32 <= 64 ? 64 : (top_k + 32 <= 96 ? 96 : 128);
+        for (int rcand = want; rcand >= top_k + 8 && !retry; rcand -= 16) {
+            if (make_plan(&pr, kRetryRows, n, d, 0, rcand, pl.ew) != SNG_OK || pr.ew != pl.ew) continue;
+            pr.seed_stride = pr.seed_q = 0;
+            pr.nsplit = kMaxCandTotal / rcand < pr.tiles ? kMaxCandTotal / rcand : pr.tiles;
+            if (pr.nsplit < 1) pr.nsplit = 1;
+            retry = true;
+        }
+    }
     if (cudaMemsetAsync(phase, 0, 8 * sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
+    if (cudaMemsetAsync(n_fb1, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
     if (cudaMemsetAsync(n_fallback, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
     // approximate scores below thr - eps can never reach thr exactly
     const float thr_lo = thr - 1.01f * kScoreEps;
@@ -1231,20 +1283,40 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min,
                                pl.seed_stride > 0 ? seeds : nullptr, nullptr, getenv("SNG_KNN_NOPHASE") ? nullptr : phase, st)) return rc;
     const int d4 = (int)((d + 3) / 4);
+    // stage 2 flags the rows it cannot prove: into the retry list when there is a retry pass, else straight into the scan list
+    int* flag_rows = retry ? fb_rows : fb2_rows;
+    int* flag_cnt = retry ? n_fb1 : n_fallback;
     {
         const int blocks = (int)((nq + 7) / 8 < (int64_t)sm_count() * 8 ? (nq + 7) / 8 : (int64_t)sm_count() * 8);
         simknn_rescore_kernel<<<blocks > 0 ? blocks : 1, 256, (size_t)8 * 2 * 3 * m_total * 4, st>>>(
             xq32, xall32, ld32, d4, (int)nq, (int)n, (int)q_offset, remove_self, m_total, pl.lists(), top_k, thr, kScoreEps, cand_idx, cand_min,
-            idx, sim, cnt, fb_rows, n_fallback);
+            idx, sim, cnt, flag_rows, flag_cnt, nullptr, nullptr);
         if (int rc = check_launch("simknn stage 2")) return rc;
+    }
+    if (retry) {
+        // Retry pass: the (few) unproven rows -- a seed threshold that hid a neighbour, or more near-cut columns than the list
+        // has slots -- go through the tensor cores once more as their own small query matrix, unseeded, with long lists and
+        // the column range split over many CTAs; only rows that fail this proof too reach the exact FP32 scan.
+        simknn_retry_gather_kernel<<<64, 256, 0, st>>>(xq, ldb, fb_rows, n_fb1, xq_retry, fb2_rows, n_fallback);
+        if (int rc = launch_stage1(pr, xq_retry, xall, ldb, kRetryRows, q_offset, n, thr_lo, remove_self, rcand_val, rcand_idx, rcand_min,
+                                   nullptr, nullptr, nullptr, st, n_fb1, fb_rows)) return rc;
+        const int mr = pr.lists() * pr.cand;
+        simknn_rescore_kernel<<<kRetryRows / 8, 256, (size_t)8 * 2 * 3 * mr * 4, st>>>(
+            xq32, xall32, ld32, d4, kRetryRows, (int)n, (int)q_offset, remove_self, mr, pr.lists(), top_k, thr, kScoreEps, rcand_idx, rcand_min,
+            idx, sim, cnt, fb2_rows, n_fallback, n_fb1, fb_rows);
+        if (int rc = check_launch("simknn retry pass")) return rc;
+    }
+    if (n_retry) {
+        if (cudaMemcpyAsync(n_retry, retry ? n_fb1 : n_fallback, sizeof(int), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return check_launch("sng_simknn_build n_retry");
     }
     const int fb_grid = (sm_count() > 0 ? sm_count() : 148) * 4;
     for (int wave = 0; wave < kFbWaves; ++wave) {
-        simknn_fb_scan_kernel<<<fb_grid, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb_rows, n_fallback,
+        simknn_fb_scan_kernel<<<fb_grid, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb2_rows, n_fallback,
                                                       wave, n_chunks, part_s, part_i);
-        simknn_fb_merge_kernel<<<fb_grid, 256, 0, st>>>(fb_rows, n_fallback, wave, n_chunks, top_k, part_s, part_i, idx, sim, cnt);
+        simknn_fb_merge_kernel<<<fb_grid, 256, 0, st>>>(fb2_rows, n_fallback, wave, n_chunks, top_k, part_s, part_i, idx, sim, cnt);
     }
-    simknn_fb_stream_kernel<<<fb_grid, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb_rows,
+    simknn_fb_stream_kernel<<<fb_grid, 256, 0, st>>>(xq32, xall32, ld32, d4, (int)n, (int)q_offset, top_k, thr, remove_self, fb2_rows,
                                                     n_fallback, kFbWaves * kFbWaveRows, idx, sim, cnt);
     return check_launch("simknn stage 3");
 }

@@ -30,7 +30,8 @@ def normalize_operands(x):
 
 
 def build_knn_normalized(xf, xh, d, top_k, thr, remove_self=True, q_lo=0, q_hi=None, return_fallback=False):
-    """K1 on already normalised operands (what a rank calls after the all-gather of x-hat)."""
+    """K1 on already normalised operands (what a rank calls after the all-gather of x-hat).  return_fallback adds a device
+    int32[2] = [rows that needed the exact scan, rows that needed the retry pass]."""
     n = xf.size(0)
     q_hi = n if q_hi is None else q_hi
     nq = q_hi - q_lo
@@ -40,14 +41,14 @@ def build_knn_normalized(xf, xh, d, top_k, thr, remove_self=True, q_lo=0, q_hi=N
     idx = torch.empty(nq, top_k, dtype=torch.int32, device=dev)
     sim = torch.empty(nq, top_k, dtype=torch.float32, device=dev)
     cnt = torch.empty(nq, dtype=torch.int32, device=dev)
-    nfb = torch.zeros(1, dtype=torch.int32, device=dev)
+    nfb = torch.zeros(2, dtype=torch.int32, device=dev)          # [rows that needed the exact scan, rows that needed the retry pass]
     wbytes = _C.lib().sng_simknn_workspace_bytes(nq, n, d, top_k)
     if wbytes == 0:
         raise RuntimeError(f"sng_simknn_workspace_bytes rejected nq={nq} n={n} d={d} top_k={top_k}: {_C.last_error()}")
     ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
     _C.check(_C.lib().sng_simknn_build(_C.ptr(xh[q_lo:]), _C.ptr(xh), xh.size(1), _C.ptr(xf[q_lo:]), _C.ptr(xf), xf.size(1),
                                        nq, q_lo, n, d, int(top_k), float(thr), int(bool(remove_self)),
-                                       _C.ptr(idx), _C.ptr(sim), _C.ptr(cnt), _C.ptr(nfb), _C.ptr(ws), wbytes, _C.stream()),
+                                       _C.ptr(idx), _C.ptr(sim), _C.ptr(cnt), _C.ptr(nfb), _C.ptr(nfb[1:]), _C.ptr(ws), wbytes, _C.stream()),
              "sng_simknn_build")
     if return_fallback:
         return idx, sim, cnt, nfb
