@@ -51,7 +51,7 @@ constexpr bool kEvTrace = true;          // per-event statistics in SNG_KNN_TRAC
 #else
 constexpr bool kEvTrace = false;
 #endif
-constexpr int kQueue = 256;             // hit queue entries per CTA (power of two); one entry = 64 bytes
+constexpr int kQueue = 256;             // hit queue entries per CTA (power of two; the plan may shrink it); one entry = 64 bytes
 constexpr int kSeedGroups = 16;         // disjoint column groups of the seed sample: (tile parity) x (32-column chunk of the tile)
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -171,6 +171,7 @@ struct Stage1Params {
     int kblocks, ksteps_last;     // K tiling: kblocks tiles of 64, the last one has ksteps_last MMA steps of 16
     int stages;                   // B ring depth (K blocks)
     int cand;                     // candidate slots per row list (L)
+    int qcap;                     // hit queue entries (power of two)
     int nsplit, tiles_total;      // 256-column tiles are split across gridDim.y cluster columns
     float thr_lo;                 // approximate scores <= thr_lo can never be selected
     int remove_self;
@@ -272,17 +273,18 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t list_off = b_off + (uint32_t)p.stages * kTileBytes;
     const uint32_t thr_off = list_off + (uint32_t)p.cand * BM * 8u;
     const uint32_t q_off = (thr_off + BM * 12u + 15u) & ~15u;         // row_thr, list_cnt, list_minpos; then the 16-byte aligned queue
-    const uint32_t bar_off = q_off + kQueue * 68u + 16u;             // entries (64 B), flags (4 B) + {q_head, q_tail, done}
+    const uint32_t qcap = (uint32_t)p.qcap;
+    const uint32_t bar_off = q_off + qcap * 68u + 16u;             // entries (64 B), flags (4 B) + {q_head, q_tail, done}
     float* list_val = reinterpret_cast<float*>(smem + list_off);
     int* list_idx = reinterpret_cast<int*>(smem + list_off + (size_t)p.cand * BM * 4);
     volatile float* row_thr = reinterpret_cast<volatile float*>(smem + thr_off);
     int* list_cnt = reinterpret_cast<int*>(smem + thr_off + BM * 4);
     int* list_minpos = reinterpret_cast<int*>(smem + thr_off + BM * 8);
     float4* q_ent = reinterpret_cast<float4*>(smem + q_off);         // entry e = q_ent[4e .. 4e+3]: 11 triple maxima, col0, row
-    volatile int* q_flag = reinterpret_cast<volatile int*>(smem + q_off + kQueue * 64);
-    unsigned* q_head = reinterpret_cast<unsigned*>(smem + q_off + kQueue * 68);
-    volatile unsigned* q_tail = reinterpret_cast<volatile unsigned*>(smem + q_off + kQueue * 68 + 4);
-    unsigned* q_done = reinterpret_cast<unsigned*>(smem + q_off + kQueue * 68 + 8);
+    volatile int* q_flag = reinterpret_cast<volatile int*>(smem + q_off + qcap * 64);
+    unsigned* q_head = reinterpret_cast<unsigned*>(smem + q_off + qcap * 68);
+    volatile unsigned* q_tail = reinterpret_cast<volatile unsigned*>(smem + q_off + qcap * 68 + 4);
+    unsigned* q_done = reinterpret_cast<unsigned*>(smem + q_off + qcap * 68 + 8);
     const uint32_t bar_full = base + bar_off;                       // [kMaxStages]  leader only: B K-block landed in both CTAs
     const uint32_t bar_empty = bar_full + 8 * kMaxStages;           // [kMaxStages]  per CTA: MMAs that read the stage retired
     const uint32_t bar_a = bar_empty + 8 * kMaxStages;              // [1]           leader only: both A blocks landed
@@ -344,7 +346,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             list_cnt[i] = 0;
             list_minpos[i] = 0;
         }
-        for (int i = lane; i < kQueue; i += 32) q_flag[i] = 0;
+        for (int i = lane; i < (int)qcap; i += 32) q_flag[i] = 0;
         if (lane == 0) { *q_head = 0u; *q_tail = 0u; *q_done = 0u; }
         if (lane == 0 && rank == 0) {                                 // the pair's common starting tile, written to both CTAs
             const uint32_t t0 = (p.phase != nullptr && T > 0) ? (uint32_t)(*reinterpret_cast<volatile int*>(p.phase + blockIdx.y)) % (uint32_t)T : 0u;
@@ -472,7 +474,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const int L = p.cand;
             unsigned tail = 0;
             while (true) {
-                const unsigned s = (tail + lane) & (kQueue - 1);
+                const unsigned s = (tail + lane) & (qcap - 1);
                 const unsigned ready = __ballot_sync(0xffffffffu, q_flag[s] != 0);
                 const int nr = ready == 0xffffffffu ? 32 : __ffs(~ready) - 1;       // leading published entries
                 if (nr == 0) {
@@ -593,8 +595,8 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 }
                 if (mx > thr_cur) {                                  // hit lanes only: dump the triple maxima for the list warp
                     const unsigned at = atomicAdd(q_head, 1u);
-                    while ((int)(at - *q_tail) >= kQueue) __nanosleep(20);           // queue full: wait for the list warp
-                    const unsigned s = at & (kQueue - 1);
+                    while ((int)(at - *q_tail) >= (int)qcap) __nanosleep(20);           // queue full: wait for the list warp
+                    const unsigned s = at & (qcap - 1);
                     q_ent[4 * s] = make_float4(m[0], m[1], m[2], m[3]);
                     q_ent[4 * s + 1] = make_float4(m[4], m[5], m[6], m[7]);
                     q_ent[4 * s + 2] = make_float4(m[8], m[9], m[10], __int_as_float(col0));
@@ -991,7 +993,7 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
 }
 
 struct Plan {
-    int ew, stages, cand, nsplit, kblocks, ksteps_last, tiles;
+    int ew, stages, cand, qcap, nsplit, kblocks, ksteps_last, tiles;
     int seed_stride, seed_q;      // 0 = no seed pass
     size_t smem;
     int lists() const { return nsplit; }          // one candidate list per (row, column split)
@@ -1011,9 +1013,9 @@ static int seed_quantile(int top_k, int stride, double tol) {
     return top_k + 1;
 }
 
-static size_t smem_bytes(int ew, int kblocks, int stages, int cand) {
+static size_t smem_bytes(int ew, int kblocks, int stages, int cand, int qcap) {
     (void)ew;
-    return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)cand * BM * 8 + BM * 12 + 16 + kQueue * 68 + 16 +
+    return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)cand * BM * 8 + BM * 12 + 16 + (size_t)qcap * 68 + 16 +
            8 * (2 * kMaxStages + 9) + 16;
 }
 
@@ -1027,11 +1029,10 @@ static int env_int(const char* name, int lo, int hi) {       // tuning overrides
 // Candidate slots per row list.  The list keeps the row's best `cand` FP16 scores; stage 2 proves a row only if its k-th
 // exact score clears the list's drop bound by the FP16 error, so cand - top_k is the number of near-cut columns a row may
 // have before it has to go to the exact scan.
-static int cand_for(int top_k, int ew) {
-    (void)ew;
+static int cand_for(int top_k, int margin) {
     const int o = env_int("SNG_KNN_CAND", top_k, 128);
     if (o) return o;
-    return (top_k + 22 + 1) / 2 * 2;
+    return (top_k + margin + 1) / 2 * 2;
 }
 
 // top_k > 0: derive cand from top_k;  top_k == 0: use the explicit `cand` (stage-1 test entry point)
@@ -1046,16 +1047,22 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     // small K: the epilogue (TMEM reads) paces the kernel -> 16 epilogue warps; large K: the MMAs do -> fewer, deeper B ring
     const int ew_pref = d16 <= 128 ? 4 : (d16 <= 320 ? 2 : 1);
     if (force_ew == 4 && pl->kblocks > 2) force_ew = 2;        // EW = 4 is the split-N mode, built for at most two K blocks
+    // Preference: a B ring of >= 3 stages first (pass 0), then the widest candidate margin, then the full hit queue.  Large
+    // d (A alone is 128 KB at d = 512) or large top_k trade the margin away: the retry pass catches the rows that costs.
+    static const int kMargins[] = {22, 14, 8, 4};
     for (int pass = 0; pass < 2 && !pl->ew; ++pass) {
         for (int ew = force_ew ? force_ew : ew_pref; ew >= 1 && !pl->ew; ew >>= 1) {
-            const int c = top_k > 0 ? cand_for(top_k, ew) : cand;
-            if (c <= kMaxCandTotal) {
-                int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
-                if (env_int("SNG_KNN_STAGES", 2, kMaxStages)) want = env_int("SNG_KNN_STAGES", 2, kMaxStages);
-                for (int st = want; st >= (pass ? 2 : 3); --st) {
-                    if (ew == 4 && st % pl->kblocks != 0) continue;      // split mode: a tile's K blocks share one ring lap
-                    const size_t sz = smem_bytes(ew, pl->kblocks, st, c);
-                    if (sz <= kMaxSmem) { pl->ew = ew; pl->stages = st; pl->smem = sz; pl->cand = c; break; }
+            for (int mi = 0; mi < (top_k > 0 ? 4 : 1) && !pl->ew; ++mi) {
+                const int c = top_k > 0 ? cand_for(top_k, kMargins[mi]) : cand;
+                if (c > kMaxCandTotal) continue;
+                for (int qc = kQueue; qc >= 64 && !pl->ew; qc /= 4) {
+                    int want = pl->kblocks * 4 < kMaxStages ? (pl->kblocks * 4 > 4 ? pl->kblocks * 4 : 4) : kMaxStages;
+                    if (env_int("SNG_KNN_STAGES", 2, kMaxStages)) want = env_int("SNG_KNN_STAGES", 2, kMaxStages);
+                    for (int st = want; st >= (pass ? 2 : 3); --st) {
+                        if (ew == 4 && st % pl->kblocks != 0) continue;      // split mode: a tile's K blocks share one ring lap
+                        const size_t sz = smem_bytes(ew, pl->kblocks, st, c, qc);
+                        if (sz <= kMaxSmem) { pl->ew = ew; pl->stages = st; pl->smem = sz; pl->cand = c; pl->qcap = qc; break; }
+                    }
                 }
             }
             if (force_ew) break;
@@ -1113,7 +1120,7 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
     if (int rc = make_map(&mdb, xall, n_db, ldb, seed_pass ? pl.seed_stride : 1)) return rc;
     Stage1Params p;
     p.nq = (int)nq; p.n = (int)n_db; p.q_offset = (int)q_offset;
-    p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = seed_pass ? 0 : pl.cand;
+    p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = seed_pass ? 0 : pl.cand; p.qcap = pl.qcap;
     p.nsplit = seed_pass ? 1 : pl.nsplit; p.tiles_total = (int)((n_db + BN - 1) / BN); p.thr_lo = thr_lo; p.remove_self = remove_self;
     p.debug = env_int("SNG_KNN_DEBUG", 1, 63);
     p.issuers = env_int("SNG_KNN_ISSUERS", 1, 2) ? env_int("SNG_KNN_ISSUERS", 1, 2) : (pl.kblocks <= 3 ? 2 : 1);

@@ -152,7 +152,7 @@ class _ShardedPPFuse(torch.autograd.Function):
         out1 = SF._check_h(out1)
         nl, cp = out1.shape
         c = w_weight.size(0)
-        wt = F.pad(w_weight.detach(), (0, 0, 0, cp - c)).t().contiguous()        # [n, Cp], replicated
+        wt = SF._transposed_padded(w_weight, cp)                                  # [n, Cp], replicated
         bw = F.pad(w_bias.detach(), (0, cp - c)).contiguous()
         bb = None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous()
         out0, out = torch.empty_like(out1), torch.empty_like(out1)

@@ -4,6 +4,8 @@ dense `lin` GEMM only; every sparse / selection / aggregation step is a libsng.s
 Channel padding: the edge kernels want 16-byte feature rows, so the layer output width C is padded to
 Cp = 4*ceil(C/4) by zero-padding the `lin` weights (zero columns change neither norms nor dot products).
 """
+import weakref
+
 import torch
 import torch.nn.functional as F
 
@@ -171,6 +173,25 @@ def spmm(x, rowptr, col, n_rows, val=None, rowscale=None, bias=None):
     return out
 
 
+_WT_CACHE = {}
+
+
+def _transposed_padded(w_weight, cp):
+    """W^T [N, Cp] (zero-padded channels) of the structural weight [C, N].  The transpose is a full copy of the parameter
+    (209 MB at pokec size), so it is kept until the parameter changes: the two evaluation forwards of an epoch reuse it."""
+    key = (id(w_weight), cp)
+    hit = _WT_CACHE.get(key)
+    # same tensor OBJECT (a freed parameter's address and version can be reused by the next model), unchanged since
+    if hit is not None and hit[0]() is w_weight and hit[1] == (w_weight._version, w_weight.data_ptr()):
+        return hit[2]
+    c = w_weight.size(0)
+    wt = F.pad(w_weight.detach(), (0, 0, 0, cp - c)).t().contiguous()
+    if len(_WT_CACHE) >= 8:
+        _WT_CACHE.pop(next(iter(_WT_CACHE)))
+    _WT_CACHE[key] = (weakref.ref(w_weight), (w_weight._version, w_weight.data_ptr()), wt)
+    return wt
+
+
 class PPFuse(torch.autograd.Function):
     """out = beta*(A @ W^T + b_w) + (1-beta)*out_1 (+bias)  --  R: models/models.py:124-136 (K4)."""
 
@@ -182,7 +203,7 @@ class PPFuse(torch.autograd.Function):
         if w_weight.size(1) != n:
             raise RuntimeError(f"w.weight is [{c},{w_weight.size(1)}] but the graph has {n} nodes "
                                "(R builds w = Linear(num_nodes, out_channels), models.py:95)")
-        wt = F.pad(w_weight.detach(), (0, 0, 0, cp - c)).t().contiguous()        # [N, Cp]
+        wt = _transposed_padded(w_weight, cp)                                     # [N, Cp]
         bw = F.pad(w_bias.detach(), (0, cp - c)).contiguous()
         bb = None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous()
         out0 = torch.empty_like(out1)

@@ -90,3 +90,22 @@ def test_module_surface_matches_reference_signatures():
     assert float(m.lins[0].beta) == 0.25 and m.lins[0].w.weight.shape == (4, 20)
     assert sorted(k for k in m.state_dict()) == sorted(
         [f"lins.{l}.{n}" for l in (0, 1) for n in ("beta", "lin.weight", "lin.bias", "w.weight", "w.bias")])
+
+
+def test_simknn_plan_is_host_logic():
+    """sng_simknn_plan needs no GPU: the launch plan of the build for the named shapes."""
+    from sngnn_b200 import simknn
+    p = simknn.build_plan(1632803, 1632803, 65, 10)                      # pokec: split mode, seeded 1/16 with the 6th of 16 group maxima
+    assert (p["ew"], p["kblocks"], p["nsplit"], p["seed_stride"], p["seed_q"], p["cand"]) == (4, 2, 1, 16, 6, 32), p
+    assert p["stages"] % p["kblocks"] == 0
+    p = simknn.build_plan(204101, 1632803, 65, 10)                       # one rank of an 8-GPU build: same plan
+    assert (p["ew"], p["nsplit"], p["seed_stride"]) == (4, 1, 16), p
+    p = simknn.build_plan(2923922, 2923922, 269, 10)                     # snap-patents: K = 272 -> two 256-column stages
+    assert (p["ew"], p["kblocks"], p["seed_stride"]) == (2, 5, 16), p
+    p = simknn.build_plan(100000, 100000, 512, 50)                       # sweep corner: A alone is 128 KB -> thinner margin, 2 stages
+    assert p["ew"] == 1 and 50 < p["cand"] <= 72 and p["stages"] >= 2 and p["seed_q"] <= 12, p
+    p = simknn.build_plan(2277, 2277, 2325 // 8, 10)                     # tiny database: column-split, unseeded
+    assert p["nsplit"] > 1 and p["seed_stride"] == 0, p
+    import pytest
+    with pytest.raises(RuntimeError):
+        simknn.build_plan(1000, 1000, 65, 1000)                          # top_k out of range -> loud error

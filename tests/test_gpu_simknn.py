@@ -176,7 +176,7 @@ def test_seeded_build_matches_oracle(n, d, k, thr, rs, kind, stride, q, monkeypa
         assert int(nfb[1]) > 0                                      # rows that needed the retry pass
 
 
-@pytest.mark.parametrize("n,d,k", [(40000, 65, 10), (20000, 128, 50), (9000, 65, 10)])
+@pytest.mark.parametrize("n,d,k", [(40000, 65, 10), (20000, 128, 50), (9000, 65, 10), (30000, 512, 50), (26000, 512, 10)])
 def test_default_plan_build_matches_oracle(n, d, k):
     """The plan the library picks by itself (seed stride / quantile adapted to the database size and top_k)."""
     from sngnn_b200 import simknn
