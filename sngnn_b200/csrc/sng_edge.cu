@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
 // and 1/norm it loaded in the first place.  The running top-k lives in registers (lane t = rank t).  The first chunk is
 // ranked by top_k rounds of a one-instruction warp max; later chunks only insert the candidates that beat the k-th score.
 // The <= top_k winners are re-gathered at the end (L1 hits), so nothing of a chunk has to stay live across chunks.
-template <int G, bool PF, int MINB>
+template <int G, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) edge_topk_sel_fwd_kernel(
     const float* __restrict__ h, const float* __restrict__ inv_r, int n, int row_offset, int c, int ldh, const int* __restrict__ rowptr,
     const int* __restrict__ col, int top_k, float thr, float* __restrict__ out, int ldo,
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(kThreads, MINB) edge_topk_sel_fwd_kernel(
     const float* hb = h + (ch_ok ? q * 4 : 0);  // lanes beyond the channel count read channel 0 and contribute zeros
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // The row's metadata (rowptr pair, first chunk of source ids) is fetched one row ahead, so the dependent chain of a row
-    // is just gather -> select -> re-gather instead of rowptr -> col -> gather -> ...
+    // The next row's metadata (rowptr pair, first chunk of source ids) is loaded at the END of a row, ahead of its use.
+    // (Fetching it a whole row ahead costs 16 registers -- one resident block per SM -- and measured no gain.)
     const int stride = gridDim.x * kWarpsPerBlock;
     int row = blockIdx.x * kWarpsPerBlock + warp;
     int beg = 0, end = 0, jl0 = 0;
@@ -234,7 +234,6 @@ __global__ void __launch_bounds__(kThreads, MINB) edge_topk_sel_fwd_kernel(
         const int grow = row_offset + row;
         const int nrow = row + stride;
         int nbeg = 0, nend = 0, njl = 0;
-        if (PF && nrow < n) { nbeg = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1); }
         float4 ni = scale4(ldg4(hb + (int64_t)grow * ldh), __ldg(inv_r + grow));     // target row, normalised
         if (!ch_ok) ni = z4;
         float ls = 0.f; int lj = -1;            // rank `lane` of the running top-k
@@ -254,8 +253,6 @@ __global__ void __launch_bounds__(kThreads, MINB) edge_topk_sel_fwd_kernel(
                     const int j = __shfl_sync(0xffffffffu, jl, grp * G + u0 + u);     // owner of edge (u0+u)*EPW + grp
                     v[u] = (u0 + u) * EPW < nchunk ? ldg4(hb + (int64_t)j * ldh) : z4;
                 }
-                if (PF && u0 == 0 && base == beg && nrow < n)                              // next row's source ids, behind this row's gathers
-                    njl = my_e < nend - nbeg ? __ldg(col + nbeg + my_e) : row_offset + nrow;
 #pragma unroll
                 for (int u = 0; u < UB; ++u) d[u0 + u] = dot4(ni, v[u]);
             }
@@ -338,9 +335,7 @@ __global__ void __launch_bounds__(kThreads, MINB) edge_topk_sel_fwd_kernel(
             const float invd = 1.0f / (float)max(end - beg, 1);
             *reinterpret_cast<float4*>(out + (int64_t)row * ldo + q * 4) = scale4(acc, invd);
         }
-        if (PF) {
-            if (beg == end && nrow < n) njl = my_e < nend - nbeg ? __ldg(col + nbeg + my_e) : row_offset + nrow;   // (empty row: no chunk ran)
-        } else if (nrow < n) {
+        if (nrow < n) {
             nbeg = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1);
             njl = my_e < nend - nbeg ? __ldg(col + nbeg + my_e) : row_offset + nrow;
         }
@@ -636,9 +631,8 @@ extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n_total, int64_t n,
     row_inv_norm_kernel<<<grid_for_rows(n_total, kWarpsPerBlock), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm);
     SNG_DISPATCH_G(c,
         if (top_k > 0 && top_k <= 32 && !getenv("SNG_K2_OLD")) {
-            // (PF = next-row metadata prefetch costs 16 registers, i.e. a resident block per SM, and measured no gain: off)
             constexpr int MB = G >= 16 ? 2 : (G == 8 ? 4 : 6);
-            edge_topk_sel_fwd_kernel<G, false, MB><<<grid, kThreads, 0, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
+            edge_topk_sel_fwd_kernel<G, MB><<<grid, kThreads, 0, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
         }
         else if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
         else edge_topk_agg_fwd_kernel<G, true><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, 0, thr, out, (int)ldo, nullptr, nullptr, nullptr));

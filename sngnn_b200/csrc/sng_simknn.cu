@@ -35,7 +35,6 @@ constexpr int kTileBytes = 128 * BK * 2;// 16 KiB: one K block of 128 rows (A bl
 constexpr int kUmmaK = 16;
 constexpr int kNonEpiThreads = 128;
 constexpr int kMaxStages = 10;
-constexpr int kFallbackBlocks = 32;
 constexpr int kMaxCandTotal = 192;      // lists per row * cand <= this; stage 2 expands every candidate into 3 columns
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 // Instrumented builds (make EXTRA=-DSNG_KNN_INSTRUMENT): the SNG_KNN_DEBUG work-skipping modes and the SNG_KNN_TRACE
@@ -779,7 +778,7 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
 
 // Retry pass, step 1: compact the FP16 rows of the first kRetryRows flagged query rows into one matrix (the TMA operand of
 // the second tensor-core pass); flagged rows beyond that go straight to the exact-scan list.
-constexpr int kRetryRows = 4096;
+constexpr int kRetryRows = 16384;          // capacity of the retry pass; flagged rows beyond it go to the exact scan
 __global__ void __launch_bounds__(256) simknn_retry_gather_kernel(const uint16_t* __restrict__ xq, int64_t ldb, const int* __restrict__ fb_rows,
                                                                  const int* __restrict__ n_fb, uint16_t* __restrict__ xq_retry,
                                                                  int* __restrict__ fb2_rows, int* __restrict__ n_fb2) {
