@@ -190,3 +190,20 @@ def test_default_plan_build_matches_oracle(n, d, k):
     print(f"default plan n={n} d={d} k={k} plan={plan}: {res} fallback_rows={int(nfb[0])} retry_rows={int(nfb[1])}")
     assert res["out_of_band"] == 0, res
     assert check_tie_order(idx, sim, cnt)
+
+
+def test_build_without_retry_pass_matches_oracle(monkeypatch):
+    """SNG_KNN_NORETRY: unproven rows go straight to the exact scan (the path every row took before the retry pass existed)."""
+    from sngnn_b200 import simknn
+    monkeypatch.setenv("SNG_KNN_NORETRY", "1")
+    monkeypatch.setenv("SNG_KNN_CAND", "12")                     # two spare slots only: many rows cannot be proven
+    n, d, k = 6000, 65, 10
+    x = _features(n, d, "clustered", seed=11)
+    idx, sim, cnt, nfb = simknn.build_knn(x.to(DEV), k, 0.0, True, return_fallback=True)
+    torch.cuda.synchronize()
+    idx_ref, sim_ref, cnt_ref = _oracle(x, k, 0.0, True)
+    res = compare_lists(idx, cnt, idx_ref, cnt_ref, _score64(x), 0.0)
+    print(f"no retry: {res} fallback_rows={int(nfb[0])}")
+    assert res["out_of_band"] == 0, res
+    assert int(nfb[0]) > 0 and int(nfb[0]) == int(nfb[1])
+    assert check_tie_order(idx, sim, cnt)
