@@ -715,7 +715,8 @@ __device__ __forceinline__ bool better(float sa, int ia, float sb, int ib) { ret
 // thr / top_k, and prove that no dropped column could belong to the answer.
 __global__ void __launch_bounds__(256) simknn_rescore_kernel(
     const float* __restrict__ xq, const float* __restrict__ xall, int64_t ld32, int d4, int nq, int n, int q_offset, int remove_self, int m_total,
-    int nsplit, int top_k, float thr, float eps, const int* __restrict__ cand_idx, const float* __restrict__ cand_min,
+    int nsplit, int top_k, float thr, float eps, const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+    const float* __restrict__ cand_min,
     int* __restrict__ idx_out, float* __restrict__ sim_out, int* __restrict__ cnt_out, int* __restrict__ fb_rows, int* __restrict__ n_fallback,
     const int* __restrict__ nq_dev, const int* __restrict__ row_map) {
     extern __shared__ float sm2[];
@@ -729,13 +730,33 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
         const int row = row_map ? __ldg(row_map + f) : f;
         const float* a = xq + (int64_t)row * ld32;
         const int self_col = remove_self ? q_offset + row : -1;
+        // Triples that cannot matter are not rescored.  Let t_k be the top_k-th largest triple maximum (FP16 scores).  The
+        // top_k largest triples each hold a column whose exact score is >= t_k - eps, so the top_k-th best exact score is
+        // too; every column of a triple whose maximum is < t_k - 2 eps scores < t_k - eps exactly: strictly below the cut.
+        for (int m = lane; m < m_total; m += 32)
+            sc[m] = __ldg(cand_idx + (size_t)f * m_total + m) >= 0 ? __ldg(cand_val + (size_t)f * m_total + m) : -CUDART_INF_F;
+        __syncwarp();
+        float tk = CUDART_INF_F; int ntrip = 0;
+        for (int m0 = 0; m0 < m_total; m0 += 32) {                    // fixed trip counts: rank of every maximum by counting
+            const int m = m0 + lane;
+            const float v = m < m_total ? sc[m] : -CUDART_INF_F;
+            int above = 0;
+            for (int o = 0; o < m_total; ++o) above += sc[o] > v ? 1 : 0;
+            if (v > -CUDART_INF_F && above < top_k) tk = fminf(tk, v);
+            ntrip += __popc(__ballot_sync(0xffffffffu, v > -CUDART_INF_F));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tk = fminf(tk, __shfl_xor_sync(0xffffffffu, tk, o));
+        const float cutoff = ntrip >= top_k ? tk - 2.0f * eps : -CUDART_INF_F;
+        __syncwarp();
         int nvalid = 0;
         for (int m0 = 0; m0 < m3; m0 += 32) {
             const int m = m0 + lane;
             int j = -1; float s = -CUDART_INF_F;
             if (m < m3) {
                 const int base = __ldg(cand_idx + (size_t)f * m_total + m / 3), e = m % 3;
-                if (base >= 0 && (e < 2 || (base & 31) != 30) && base + e < n && base + e != self_col) {
+                if (base >= 0 && __ldg(cand_val + (size_t)f * m_total + m / 3) >= cutoff && (e < 2 || (base & 31) != 30) && base + e < n &&
+                    base + e != self_col) {
                     j = base + e;
                     s = dot_seq(a, xall + (int64_t)j * ld32, d4);
                 }
@@ -1295,7 +1316,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     {
         const int blocks = (int)((nq + 7) / 8 < (int64_t)sm_count() * 8 ? (nq + 7) / 8 : (int64_t)sm_count() * 8);
         simknn_rescore_kernel<<<blocks > 0 ? blocks : 1, 256, (size_t)8 * 2 * 3 * m_total * 4, st>>>(
-            xq32, xall32, ld32, d4, (int)nq, (int)n, (int)q_offset, remove_self, m_total, pl.lists(), top_k, thr, kScoreEps, cand_idx, cand_min,
+            xq32, xall32, ld32, d4, (int)nq, (int)n, (int)q_offset, remove_self, m_total, pl.lists(), top_k, thr, kScoreEps, cand_val, cand_idx, cand_min,
             idx, sim, cnt, flag_rows, flag_cnt, nullptr, nullptr);
         if (int rc = check_launch("simknn stage 2")) return rc;
     }
@@ -1308,7 +1329,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
                                    nullptr, nullptr, nullptr, st, n_fb1, fb_rows)) return rc;
         const int mr = pr.lists() * pr.cand;
         simknn_rescore_kernel<<<kRetryRows / 8, 256, (size_t)8 * 2 * 3 * mr * 4, st>>>(
-            xq32, xall32, ld32, d4, kRetryRows, (int)n, (int)q_offset, remove_self, mr, pr.lists(), top_k, thr, kScoreEps, rcand_idx, rcand_min,
+            xq32, xall32, ld32, d4, kRetryRows, (int)n, (int)q_offset, remove_self, mr, pr.lists(), top_k, thr, kScoreEps, rcand_val, rcand_idx, rcand_min,
             idx, sim, cnt, fb2_rows, n_fallback, n_fb1, fb_rows);
         if (int rc = check_launch("simknn retry pass")) return rc;
     }
