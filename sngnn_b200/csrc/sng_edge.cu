@@ -581,6 +581,19 @@ static int grid_for_rows(int64_t rows, int rows_per_block) {
     return (int)(g < 1 ? 1 : g);
 }
 
+// Grid of a grid-stride row kernel = exactly the number of CTAs that are resident at once (SMs x occupancy of THIS kernel):
+// every CTA then gets the same share of rows and there is no partial second wave (a fixed 8 CTAs per SM left the gather
+// kernels, which fit 5-6, with a 1.3-1.6 wave launch whose tail ran on a half-empty GPU).
+template <typename Kernel>
+static int grid_resident(Kernel kernel, int64_t rows, int rows_per_block, size_t smem = 0, int threads = kThreads) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+    const int64_t need = (rows + rows_per_block - 1) / rows_per_block;
+    const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 1) * occ;
+    const int64_t g = need < cap ? need : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
 #define SNG_DISPATCH_G(cexpr, ...)                                              \
     switch (group_lanes(cexpr)) {                                               \
         case 1: { constexpr int G = 1; __VA_ARGS__; } break;                    \
@@ -608,7 +621,7 @@ extern "C" int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx
     SNG_REQUIRE(!xhat_f32 || (ld_f32 >= d && ld_f32 < (1ll << 30)), "sng_rownorm_f32: ld_f32 < d");
     SNG_REQUIRE(!xhat_f16 || (ld_f16 >= d && ld_f16 < (1ll << 30)), "sng_rownorm_f32: ld_f16 < d");
     if (n == 0) return SNG_OK;
-    rownorm_kernel<<<grid_for_rows(n, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
+    rownorm_kernel<<<grid_resident(rownorm_kernel, n, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(
         x, n, (int)d, ldx, xhat_f32, (int)ld_f32, reinterpret_cast<__half*>(xhat_f16), (int)ld_f16, inv_norm);
     return check_launch("sng_rownorm_f32");
 }
@@ -625,17 +638,16 @@ extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n_total, int64_t n,
     SNG_REQUIRE(top_k <= 0 || (sel_src && sel_w && sel_cnt), "sng_edge_topk_agg_fwd: selection outputs required when top_k>0");
     SNG_REQUIRE(top_k <= 0 || thr > -1.1f, "sng_edge_topk_agg_fwd: thr must be > -1.1 (knock-out sentinel of R models.py:153)");
     if (n == 0) return SNG_OK;
-    const int grid = grid_for_rows(n, kWarpsPerBlock);
     const size_t smem = (size_t)kWarpsPerBlock * 2 * (top_k > 0 ? top_k : 1) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    row_inv_norm_kernel<<<grid_for_rows(n_total, kWarpsPerBlock), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm);
+    row_inv_norm_kernel<<<grid_resident(row_inv_norm_kernel, n_total, kWarpsPerBlock), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm);
     SNG_DISPATCH_G(c,
         if (top_k > 0 && top_k <= 32 && !getenv("SNG_K2_OLD")) {
             constexpr int MB = G >= 16 ? 2 : (G == 8 ? 4 : 6);
-            edge_topk_sel_fwd_kernel<G, MB><<<grid, kThreads, 0, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
+            edge_topk_sel_fwd_kernel<G, MB><<<grid_resident(edge_topk_sel_fwd_kernel<G, MB>, n, kWarpsPerBlock), kThreads, 0, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
         }
-        else if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
-        else edge_topk_agg_fwd_kernel<G, true><<<grid, kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, 0, thr, out, (int)ldo, nullptr, nullptr, nullptr));
+        else if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid_resident(edge_topk_agg_fwd_kernel<G, false>, n, kWarpsPerBlock, smem), kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
+        else edge_topk_agg_fwd_kernel<G, true><<<grid_resident(edge_topk_agg_fwd_kernel<G, true>, n, kWarpsPerBlock, smem), kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, 0, thr, out, (int)ldo, nullptr, nullptr, nullptr));
     return check_launch("sng_edge_topk_agg_fwd");
 }
 
@@ -645,8 +657,7 @@ extern "C" int sng_list_agg_fwd(const float* h, int64_t n_rows, int64_t c, int64
     if (int rc = check_rows("sng_list_agg_fwd", n_rows, c, ldh)) return rc;
     SNG_REQUIRE(h && sel_src && sel_w && sel_cnt && out && list_k > 0 && ldo % 4 == 0 && ldo >= c, "sng_list_agg_fwd: bad arguments");
     if (n_rows == 0) return SNG_OK;
-    const int grid = grid_for_rows(n_rows, kWarpsPerBlock);
-    SNG_DISPATCH_G(c, list_agg_fwd_kernel<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(h, (int)n_rows, (int)c, ldh, list_k, sel_src, sel_w, sel_cnt, inv_denom, out, ldo));
+    SNG_DISPATCH_G(c, list_agg_fwd_kernel<G><<<grid_resident(list_agg_fwd_kernel<G>, n_rows, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(h, (int)n_rows, (int)c, ldh, list_k, sel_src, sel_w, sel_cnt, inv_denom, out, ldo));
     return check_launch("sng_list_agg_fwd");
 }
 
@@ -660,9 +671,9 @@ extern "C" int sng_edge_agg_bwd(const float* h, const float* inv_norm, const flo
     if (n_total == 0) return SNG_OK;
     cudaStream_t st = (cudaStream_t)stream;
     SNG_DISPATCH_G(c,
-        if (n > 0 && top_k > 0) edge_agg_bwd_scatter_kernel<G, false><<<grid_for_rows(n, kWarpsPerBlock), kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)row_offset, (int)c, ld, rowptr, col, top_k, sel_src, sel_w, sel_cnt, inv_denom, dval, dnrm);
-        else if (n > 0) edge_agg_bwd_scatter_kernel<G, true><<<grid_for_rows(n, kWarpsPerBlock), kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)row_offset, (int)c, ld, rowptr, col, 0, nullptr, nullptr, nullptr, nullptr, dval, dnrm);
-        norm_bwd_finish_kernel<G><<<grid_for_rows(n_total, kWarpsPerBlock * (32 / G)), kThreads, 0, st>>>(h, inv_norm, (int)n_total, (int)c, ld, dval, dnrm, dh));
+        if (n > 0 && top_k > 0) edge_agg_bwd_scatter_kernel<G, false><<<grid_resident(edge_agg_bwd_scatter_kernel<G, false>, n, kWarpsPerBlock), kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)row_offset, (int)c, ld, rowptr, col, top_k, sel_src, sel_w, sel_cnt, inv_denom, dval, dnrm);
+        else if (n > 0) edge_agg_bwd_scatter_kernel<G, true><<<grid_resident(edge_agg_bwd_scatter_kernel<G, true>, n, kWarpsPerBlock), kThreads, 0, st>>>(h, inv_norm, g, (int)n, (int)row_offset, (int)c, ld, rowptr, col, 0, nullptr, nullptr, nullptr, nullptr, dval, dnrm);
+        norm_bwd_finish_kernel<G><<<grid_resident(norm_bwd_finish_kernel<G>, n_total, kWarpsPerBlock * (32 / G)), kThreads, 0, st>>>(h, inv_norm, (int)n_total, (int)c, ld, dval, dnrm, dh));
     return check_launch("sng_edge_agg_bwd");
 }
 
@@ -671,8 +682,7 @@ extern "C" int sng_spmm_fwd(const float* x, int64_t n_rows, int64_t c, int64_t l
     if (int rc = check_rows("sng_spmm_fwd", n_rows, c, ldx)) return rc;
     SNG_REQUIRE(x && rowptr && col && out && ldo % 4 == 0 && ldo >= c, "sng_spmm_fwd: null pointer or bad ldo");
     if (n_rows == 0) return SNG_OK;
-    const int grid = grid_for_rows(n_rows, kWarpsPerBlock);
-    SNG_DISPATCH_G(c, spmm_fwd_kernel<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, (int)n_rows, (int)c, ldx, rowptr, col, val, rowscale, bias, out, ldo));
+    SNG_DISPATCH_G(c, spmm_fwd_kernel<G><<<grid_resident(spmm_fwd_kernel<G>, n_rows, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(x, (int)n_rows, (int)c, ldx, rowptr, col, val, rowscale, bias, out, ldo));
     return check_launch("sng_spmm_fwd");
 }
 
@@ -682,8 +692,7 @@ extern "C" int sng_pp_fuse_fwd(const float* wt, int64_t n, int64_t c, int64_t ld
     if (int rc = check_rows("sng_pp_fuse_fwd", n, c, ld)) return rc;
     SNG_REQUIRE(wt && rowptr_out && col_out && b_w && beta && out1 && out0 && out, "sng_pp_fuse_fwd: null pointer");
     if (n == 0) return SNG_OK;
-    const int grid = grid_for_rows(n, kWarpsPerBlock);
-    SNG_DISPATCH_G(c, pp_fuse_fwd_kernel<G><<<grid, kThreads, 0, (cudaStream_t)stream>>>(wt, (int)n, (int)c, ld, rowptr_out, col_out, b_w, beta, out1, bias, out0, out));
+    SNG_DISPATCH_G(c, pp_fuse_fwd_kernel<G><<<grid_resident(pp_fuse_fwd_kernel<G>, n, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(wt, (int)n, (int)c, ld, rowptr_out, col_out, b_w, beta, out1, bias, out0, out));
     return check_launch("sng_pp_fuse_fwd");
 }
 
@@ -699,7 +708,7 @@ extern "C" int sng_sddmm_dot(const float* xhat, int64_t n, int64_t d, int64_t ld
                              int64_t num_edges, float* s, void* stream) {
     SNG_REQUIRE(xhat && a && b && s && n >= 0 && d > 0 && ld >= d && num_edges >= 0, "sng_sddmm_dot: bad arguments");
     if (num_edges == 0) return SNG_OK;
-    sddmm_dot_kernel<<<grid_for_rows(num_edges, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(xhat, (int)d, ld, a, b, num_edges, s);
+    sddmm_dot_kernel<<<grid_resident(sddmm_dot_kernel, num_edges, kWarpsPerBlock), kThreads, 0, (cudaStream_t)stream>>>(xhat, (int)d, ld, a, b, num_edges, s);
     return check_launch("sng_sddmm_dot");
 }
 
