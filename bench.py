@@ -214,6 +214,18 @@ def run_ours(args):
     ms = timed(step_resident, args.steps, args.warmup, barrier)
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup - 2), barrier)
     clocks = sampler.stop() if rank == 0 else None
+    # phases of the resident step, timed separately (not part of `value`): K0 + all-gather of x-hat | the build call
+    ph = {}
+
+    def phase_a():
+        ph["ops"] = normalise_and_gather(x[lo:hi])
+
+    def phase_b():
+        xf_, xh_ = ph["ops"]
+        simknn.build_knn_normalized(xf_, xh_, Fd, k, thr, True, lo, hi)
+
+    ms_gather = timed(phase_a, 3, 1, barrier)
+    ms_build = timed(phase_b, 3, 1, barrier)
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -255,7 +267,8 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "simknn_stage1_kernel<%d,false> (main pass)" % ew, "achieved": achieved_tf, "peak": pk["tf_sust"],
                 "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sust"], "traffic": traffic,
                 "peak_source": pk["src"] + " (sustained bf16/fp16 dense)", "kernel_ms": ms_k1, "algorithmic_flops_per_launch": flops,
-                "share_of_step": ms_k1 / ms, "seed_pass_ms": ms_seed, "plan": plan}
+                "share_of_step": ms_k1 / ms, "seed_pass_ms": ms_seed, "plan": plan,
+                "phase_ms_rank0": {"normalise_and_allgather": ms_gather, "build_call": ms_build}}
 
     # ---- SNGNN++ epoch (row-sharded at N>1) + aggregation kernels alone on the pokec-shaped graph ----------------
     extras = {}

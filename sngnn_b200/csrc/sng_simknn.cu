@@ -316,14 +316,16 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int i = lane; i < BM; i += 32) {
             float tau = p.thr_lo;
             const int grow = row0 + i;
+            if (!SEED && grow >= nq_eff) tau = CUDART_INF_F;         // rows beyond the query matrix (TMA zero fill / stale retry slots) never hit
             if (!SEED && p.seeds != nullptr && grow < nq_eff) {
+                const int srow = p.row_ids ? __ldg(p.row_ids + grow) : grow;     // retry pass: the seeds belong to the original row
                 float g[kSeedGroups];
 #pragma unroll
                 for (int j = 0; j < kSeedGroups / 4; ++j) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.seeds + (size_t)grow * kSeedGroups) + j);
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.seeds + (size_t)srow * kSeedGroups) + j);
                     g[4 * j] = t4.x; g[4 * j + 1] = t4.y; g[4 * j + 2] = t4.z; g[4 * j + 3] = t4.w;
                 }
-                const int self = p.q_offset + grow;                  // the row itself may sit in the sample: drop its group
+                const int self = p.q_offset + srow;                  // the row itself may sit in the sample: drop its group
                 if (p.remove_self && self % p.seed_stride == 0) {
                     const int cs = self / p.seed_stride, sg = ((cs >> 8) & 1) * 8 + ((cs & 255) >> 5);
 #pragma unroll
@@ -1325,8 +1327,11 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
         // has slots -- go through the tensor cores once more as their own small query matrix, unseeded, with long lists and
         // the column range split over many CTAs; only rows that fail this proof too reach the exact FP32 scan.
         simknn_retry_gather_kernel<<<64, 256, 0, st>>>(xq, ldb, fb_rows, n_fb1, xq_retry, fb2_rows, n_fallback);
+        // seeded like the main pass but from a much lower quantile (10th..12th of the 16 group maxima instead of the 6th): it
+        // cannot hide a neighbour (that would take top_k of top_k in a 1/stride sample) and spares the lists the warm-up
+        if (pl.seed_stride > 0) { pr.seed_stride = pl.seed_stride; pr.seed_q = pl.seed_q + 4 < kSeedGroups - 4 ? pl.seed_q + 4 : kSeedGroups - 4; }
         if (int rc = launch_stage1(pr, xq_retry, xall, ldb, kRetryRows, q_offset, n, thr_lo, remove_self, rcand_val, rcand_idx, rcand_min,
-                                   nullptr, nullptr, nullptr, st, n_fb1, fb_rows)) return rc;
+                                   pl.seed_stride > 0 ? seeds : nullptr, nullptr, nullptr, st, n_fb1, fb_rows)) return rc;
         const int mr = pr.lists() * pr.cand;
         simknn_rescore_kernel<<<kRetryRows / 8, 256, (size_t)8 * 2 * 3 * mr * 4, st>>>(
             xq32, xall32, ld32, d4, kRetryRows, (int)n, (int)q_offset, remove_self, mr, pr.lists(), top_k, thr, kScoreEps, rcand_val, rcand_idx, rcand_min,
