@@ -169,12 +169,13 @@ SNG_API int sng_graph_prepare(const int64_t* edge_index, int64_t num_edges, int6
  *   xq_f16  [nq , ldh]  normalised query rows  (FP16, zero padded, ldh % 8 == 0, ldh >= 16*ceil(d/16), 16-byte aligned)
  *   xall_f16[n  , ldh]  normalised database rows
  *   query row r is global node q_offset + r (used for remove_self and for sharding by query rows)
- * Stage 1 (tensor cores) keeps, per query row, the `cand` best FP16-scored columns (cand >= top_k + margin).
- * Stage 2 rescores them in FP32 (xq_f32 / xall_f32, leading dim ld32 % 4 == 0, zero padded), orders them by
+ * Stage 1 (tensor cores; a seed pass over a column sample first sets every row's starting threshold) keeps, per query
+ * row, the `cand` best FP16-scored column TRIPLES {c, c+1, c+2} (two columns when c % 32 == 30), cand >= top_k + margin.
+ * Stage 2 rescores their columns in FP32 (xq_f32 / xall_f32, leading dim ld32 % 4 == 0, zero padded), orders them by
  * (sim desc, index asc), applies thr / top_k and PROVES exactness: a row whose k-th exact score is not clear
- * of the best possible score of any dropped column is flagged and recomputed by an exact FP32 scan (stage 3).
- * Rows stage 2 cannot prove first get a RETRY pass (a second, unseeded tensor-core pass over just those rows with long
- * candidate lists); only rows that fail that proof too reach stage 3.
+ * of the best possible score of any dropped column is flagged.
+ * Flagged rows first get a RETRY pass (a second tensor-core pass over just those rows, with long candidate lists and a
+ * much lower starting threshold); only rows that fail that proof too are recomputed by an exact FP32 scan (stage 3).
  * Outputs: idx [nq, top_k] int32 (-1 padded), sim [nq, top_k], cnt [nq]; n_fallback (device int32) counts
  * rows that needed stage 3, n_retry (device int32, may be NULL) rows that needed the retry pass.
  * Replaces (as "the reference rule on the complete graph") the selection of
@@ -188,10 +189,11 @@ SNG_API int sng_simknn_build(const uint16_t* xq_f16, const uint16_t* xall_f16, i
                      int32_t* idx, float* sim, int32_t* cnt, int32_t* n_fallback, int32_t* n_retry,
                      void* workspace, size_t workspace_bytes, void* stream);
 
-/* Stage 1 only (profiling / tests): cand_idx / cand_val [nq, lists, cand], cand_min [nq, lists] (upper bound of every
- * score that list dropped, -inf if it dropped nothing above thr_lo); lists = column splits x epilogue warps per TMEM
- * lane quarter.  force_ew in {0,1,2,4} picks the epilogue width (0 = auto), force_nsplit > 0 the number of column
- * splits; *lists_out receives lists (size the outputs for lists * cand <= 512 slots per row).
+/* Stage 1 only (profiling / tests): cand_idx [nq, lists, cand] = first column of a kept column triple (-1 = empty slot),
+ * cand_val = the triple's largest FP16 score, cand_min [nq, lists] = upper bound of every score that list dropped (-inf if
+ * it dropped nothing above thr_lo); lists = column splits (one list per row and split).  force_ew in {0,1,2,4} picks the
+ * epilogue warps per TMEM lane quarter (0 = auto; 4 = the four-accumulator split mode, K <= 128), force_nsplit > 0 the
+ * number of column splits; *lists_out receives lists (size the outputs for lists * cand <= 192 slots per row).
  * seeds (may be NULL) = output of sng_simknn_seed with the same seed_stride: every row then starts pruning at the
  * seed_q-th largest of its 16 group maxima instead of thr_lo.
  * sweep_phase (may be NULL) = [column splits] int32, zero-initialised by the caller: the CTAs of a launch use it to start
