@@ -6,15 +6,16 @@
 // scatter_max selection of R: models/models.py:145-156 and the blocked X X^T of
 // R: SimGFAToolbox/dense.py:17-27.
 //
-// Pipeline (one CTA = MB x 128 query rows against a range of 128-column tiles of the database):
-//   warp 0      TMA producer: A (query block, all of K) once; B column tiles through an S-stage ring
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=128, K=16, FP16 in, FP32 acc in TMEM)
-//   warp 2      TMEM allocator
-//   warps 4..   epilogue: thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time, 3-input max
-//               tree against the row's running threshold (the current worst kept candidate); hits go to a
-//               per-row candidate list in shared memory.  TMEM is double buffered so the epilogue of tile
-//               t overlaps the MMAs of tile t+1.
-// Stage 2 rescoring in FP32 + proof of exactness, stage 3 exact fallback: see the bottom of this file.
+// One build = seed pass -> main pass -> FP32 rescore + proof -> retry pass -> exact scan (see sng_simknn_build at the bottom).
+// Seed, main and retry pass are the same kernel.  A CTA pair (cluster of 2, cta_group::2) owns 256 query rows and sweeps
+// the database in 256-column tiles; one CTA per SM, 4 + 4*EW warps:
+//   warp 0      TMA producer: A (the CTA's 128 query rows, all of K) once; its half of every B tile through an S-stage ring
+//   warps 1-2   MMA issuers (leader CTA): tcgen05.mma.cta_group::2, FP16 in, FP32 accumulators in TMEM.  Small K (EW = 4):
+//               two N = 128 halves per tile into four 128-column stages, two issuers; else one N = 256 MMA chain, two stages
+//   warp 3      list warp: drains the hit queue into the per-row candidate lists (shared memory), owns the row thresholds
+//   warps 4..   epilogue: thread = one query row (TMEM lane); tcgen05.ld 32 columns at a time, 3-input-max tree against the
+//               row's pruning threshold; a chunk that beats it is handed to the list warp as 11 column-triple maxima
+// Why it looks like this (issue-bound, not tensor-bound, at small K) is measured in DESIGN.md §5 / profiles/README.md.
 //
 // Operands are FP16 (not BF16): unit-norm rows live in [-1,1] where FP16 has 3 more mantissa bits, so the
 // worst-case score error is 2^-10 instead of 2^-8 and the candidate margin needed for exact indices is 4x
@@ -236,8 +237,8 @@ __device__ __forceinline__ void issue_split(const Stage1Params& p, uint32_t base
     }
 }
 
-// EW = epilogue warps per TMEM lane quarter; every epilogue thread owns one query row x (256/EW) columns of each tile
-// and its own candidate list; the EW threads of a row share one pruning threshold.
+// EW = epilogue warps per TMEM lane quarter; every epilogue thread owns one query row x (256/EW) columns of each tile; the
+// EW threads of a row share the row's pruning threshold and (through the hit queue and the list warp) its candidate list.
 //
 // Seeding.  A list that starts from thr_lo inserts ~L ln(n/L) times, and every insert is a slow, divergent detour off the
 // max-tree fast path (ncu, pokec shape: 3/4 of all warp instructions).  So the build first runs this kernel in SEED mode
