@@ -109,3 +109,36 @@ def test_simknn_plan_is_host_logic():
     import pytest
     with pytest.raises(RuntimeError):
         simknn.build_plan(1000, 1000, 65, 1000)                          # top_k out of range -> loud error
+
+
+def test_transposed_weight_cache_is_keyed_by_tensor_identity():
+    """The cached W^T of the ++ fusion must follow the parameter object and its version, never a recycled address:
+    a freed model's parameter memory is routinely reused by the next model (regression: golden models run back to back)."""
+    import gc
+    from sngnn_b200 import functional as SF
+    SF._WT_CACHE.clear()
+    w = torch.nn.Parameter(torch.arange(6.0).reshape(2, 3))
+    a = SF._transposed_padded(w, 4)
+    assert a.shape == (3, 4) and torch.equal(a[:, :2], w.detach().t()) and a[:, 2:].abs().sum() == 0
+    assert SF._transposed_padded(w, 4) is a                               # unchanged parameter: reused
+    with torch.no_grad():
+        w.add_(1.0)                                                       # optimizer step: version bump
+    b = SF._transposed_padded(w, 4)
+    assert b is not a and torch.equal(b[:, :2], w.detach().t())
+    ptr = w.data_ptr()
+    del w, a, b
+    gc.collect()
+    for _ in range(8):                                                    # a new parameter, very likely at the old address
+        w2 = torch.nn.Parameter(torch.full((2, 3), 7.0))
+        got = SF._transposed_padded(w2, 4)
+        assert torch.equal(got[:, :2], w2.detach().t())
+        if w2.data_ptr() == ptr:
+            break
+
+
+def test_knn_to_csr_host_logic():
+    from sngnn_b200 import simknn
+    idx = torch.tensor([[4, 2, -1], [-1, -1, -1], [0, 1, 3]], dtype=torch.int32)
+    cnt = torch.tensor([2, 0, 3], dtype=torch.int32)
+    rowptr, col, flat = simknn.knn_to_csr(idx, cnt)
+    assert rowptr.tolist() == [0, 2, 2, 5] and col.tolist() == [4, 2, 0, 1, 3] and flat.tolist() == [0, 1, 6, 7, 8]
