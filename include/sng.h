@@ -60,30 +60,56 @@ SNG_API int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx,
                     float* inv_norm, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * K2  fused edge-restricted similarity / selection / mean aggregation (forward)
+ * K2 (+K4)  fused edge-restricted similarity / selection / mean aggregation, forward
  * replaces SNConv_plus(_plus).message + PyG propagate(aggr='mean')
  *   R: models/models.py:132,139-158 (++), :239,244-263 (+), :326,331-334 (base, top_k <= 0)
+ * and, when `wt` is given, the structural term and the beta blend of R: models/models.py:124-136 in the SAME pass.
  * For every target row i with in-edge list [rowptr[i], rowptr[i+1]) of CSR-by-target (sources in `col`,
  * kept in original edge-position order):
- *   s_e   = <h_i/r_i , h_j/r_j>,  r = max(||h||, 1e-12)
- *   S_i   = first min(top_k, deg) edges under (s desc, position asc), cut at the first s < thr
- *   out[i]= (1/max(deg_i,1)) * sum_{e in S_i} s_e * h[src_e]
- * Saved for backward (top_k > 0): sel_src [n,top_k] (source ids, rank order, -1 padded),
- * sel_w [n,top_k] (s_e), sel_cnt [n].  With top_k <= 0 those three may be NULL.
+ *   s_e    = <h_i/r_i , h_j/r_j>,  r = max(||h||, 1e-12)
+ *   S_i    = first min(top_k, deg) edges under (s desc, position asc), cut at the first s < thr
+ *   out_1[i] = (1/max(deg_i,1)) * sum_{e in S_i} s_e * h[src_e]
+ *   wt == NULL:  out = out_1
+ *   wt != NULL:  out_0[i] = sum_{e in-list of i} wt[src_e] + b_w ;  out = beta*out_0 + (1-beta)*out_1 (+ bias) ;
+ *                diff (may be NULL) = out_0 - out_1 = d out / d beta.  Only valid when the in-list of every node equals its
+ *                out-list (symmetric graph, src shift 0: info[2] of sng_graph_prepare); otherwise use sng_pp_fuse_fwd.
+ * Saved for backward (all may be NULL in inference): sel_src [n,top_k] (source ids, rank order, -1 padded),
+ * sel_w [n,top_k] (s_e), sel_cnt [n], sel_q [n,top_k] = tpos of the selected edges (needs tpos; input of sng_edge_bwd).
+ * Degree dispatch: rows_long / rows_hub = the long_rows lists of sng_graph_prepare (rows with 32 < deg <= 1024 / deg > 1024);
+ * n_long < 0 = lists unknown, one general kernel then runs every row.
  * Row sharding: the call covers target rows [row_offset, row_offset + n) of `h`, which holds ALL n_total nodes
- * (sources are arbitrary); rowptr / out / sel_* are local to the shard, `col` holds global source ids.
+ * (sources are arbitrary); rowptr / out / sel_* / rows_* are local to the shard, `col` holds global source ids.
  * inv_norm [n_total] is filled with 1/max(||h_i||, 1e-12) (a pre-pass of this call) and is an input of the backward.
  */
-SNG_API int sng_edge_topk_agg_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
-                          const int32_t* rowptr, const int32_t* col,
-                          int top_k, float thr,
-                          float* out, int64_t ldo,
-                          int32_t* sel_src, float* sel_w, int32_t* sel_cnt,
-                          float* inv_norm, void* stream);
+SNG_API int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
+                 const int32_t* rowptr, const int32_t* col, const int32_t* tpos,
+                 const int32_t* rows_long, int64_t n_long, const int32_t* rows_hub, int64_t n_hub,
+                 int top_k, float thr, float* out, int64_t ldo,
+                 int32_t* sel_src, float* sel_w, int32_t* sel_q, int32_t* sel_cnt, float* inv_norm,
+                 const float* wt, int64_t ldw, const float* b_w, const float* beta, const float* bias, float* diff,
+                 void* stream);
 
-/* K2b backward of the above w.r.t. h (closed form of SURVEY.md §3.4).
- * Pass 1 scatters into the two zero-initialised accumulators dval, dnrm [n_total, c] (float atomics);
- * pass 2 writes dh [n_total, c] = dval + (dnrm - n (n . dnrm)) / r.   `g` = dL/dout [n, c].
+/* K2b (+K4b) backward of the above w.r.t. h -- and, under the fused epilogue, w.r.t. wt and beta -- WITHOUT float atomics:
+ * two gather passes (by target, then by source through the transpose index tpos), every sum in a fixed order, so the
+ * result is bit-reproducible (closed form of SURVEY.md §3.4).  g = dL/dout [n, ldg] (dL/dout_1 when beta == NULL).
+ *   top_k > 0: uses the saved lists (sel_src, sel_w, sel_q, sel_cnt);  top_k <= 0: every edge of the CSR (col, tpos).
+ *   rowptr_out / col_out = CSR by (source - src_shift) of the same edges, num_edges of them.
+ *   beta != NULL: g is scaled by (1 - beta) for the aggregation; dbeta (may be NULL) = sum(diff * g) (needs diff, partials);
+ *                 dwt (may be NULL) [n, lddw] = beta * sum over out-edges (j -> i) of g_i = dL/dwt.
+ * Workspaces (caller-allocated, contents irrelevant): coef [2 * num_edges] floats, dn_target [n, ld], partials [SNG_PARTIALS].
+ * Output dh [n, ld] = dL/dh. */
+#define SNG_PARTIALS 4096
+SNG_API int sng_edge_bwd(const float* h, const float* inv_norm, const float* g, int64_t n, int64_t c, int64_t ld, int64_t ldg,
+                 const int32_t* rowptr, const int32_t* col, const int32_t* tpos,
+                 const int32_t* rowptr_out, const int32_t* col_out, int64_t src_shift, int64_t num_edges,
+                 int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_q, const int32_t* sel_cnt,
+                 const float* beta, const float* diff, int64_t lddiff, float* dbeta,
+                 float* coef, float* dn_target, float* partials, float* dh, float* dwt, int64_t lddw, void* stream);
+
+/* Scatter form of the backward (float atomics; used for row shards and for explicit neighbour lists, where no
+ * transpose index exists).
+ * Pass 1 scatters into the two zero-initialised accumulators dval, dnrm [n_total, c];
+ * pass 2 writes dh [n_total, c] = dval + (dnrm - n (n . dnrm)) / r.   `g` = dL/dout_1 [n, c].
  * top_k > 0: uses the saved selection lists (inv_denom[i] = 1/max(deg_i,1));
  * top_k <= 0: iterates the CSR (every edge selected).  inv_norm [n_total] = the array the forward filled
  * (or sng_rownorm_f32's inv_norm output for selection lists that did not come from the edge forward).
@@ -124,9 +150,9 @@ SNG_API int sng_pp_fuse_fwd(const float* wt, int64_t n, int64_t c, int64_t ld,
                     const float* b_w, const float* beta, const float* out1, const float* bias,
                     float* out0, float* out, void* stream);
 
-/* dbeta += sum((out0 - out1) * g); dbeta is a zero-initialised device scalar. */
+/* dbeta = sum((out0 - out1) * g), summed in a fixed order (bit-reproducible); partials = workspace of SNG_PARTIALS floats. */
 SNG_API int sng_pp_beta_grad(const float* out0, const float* out1, const float* g, int64_t numel,
-                     float* dbeta, void* stream);
+                     float* dbeta, float* partials, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SDDMM cosine at given edges: s[e] = <xhat[a[e]], xhat[b[e]]> (xhat already normalised, FP32).
@@ -154,14 +180,20 @@ SNG_API int sng_class_sums_f64(const float* xhat, const int32_t* y, int64_t n, i
  *   N self loops are appended at the END; with remove_self_loops every src == dst edge is then dropped.
  *   rowptr_in [n+1], col_in [num_edges + n capacity]: CSR by target, sources in original edge-position order (the
  *   tie-break order of the selection); inv_deg [n] = 1/max(in-degree, 1).
- *   structural != 0 (SNConv_plus_plus): rowptr_out [n+1], col_out [capacity] = CSR by (src - min src) holding the targets
- *   (A of R: models.py:124-127), col_in_shift [capacity] = col_in - min src (its transpose, used by the backward).
- *   info (device int32[2]) = {number of kept edges E', min src}.  Only the first E' entries of col_* are meaningful.
+ *   structural != 0: rowptr_out [n+1], col_out [capacity] = CSR by (src - min src) holding the targets
+ *   (A of R: models.py:124-127), col_in_shift [capacity] = col_in - min src (its transpose).
+ *   tpos [capacity] (may be NULL; needs structural) = position of by-target edge p in the by-source arrays (the transpose
+ *   index of sng_edge_bwd).  long_rows [n] (may be NULL): local ids of the rows with 32 < in-degree <= 1024 from the
+ *   front, of the rows with in-degree > 1024 from the back (the degree dispatch of sng_edge_fwd).
+ *   info (device int32[8]) = {number of kept edges E', min src, 1 if every in-list equals the out-list and min src == 0
+ *   (structural only), rows in (32, 1024], rows > 1024, max in-degree, 0, 0}.  Only the first E' entries of col_* / tpos
+ *   are meaningful.  The two stable sorts are cub::DeviceRadixSort (a library sort); everything else is kernels of this library.
  */
 SNG_API size_t sng_graph_prepare_workspace_bytes(int64_t num_edges, int64_t n);
 SNG_API int sng_graph_prepare(const int64_t* edge_index, int64_t num_edges, int64_t n, int remove_self_loops, int structural,
                       int32_t* rowptr_in, int32_t* col_in, float* inv_deg,
                       int32_t* rowptr_out, int32_t* col_out, int32_t* col_in_shift,
+                      int32_t* tpos, int32_t* long_rows,
                       int32_t* info, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -1,38 +1,78 @@
-"""K2 forward / backward timing on the pokec-shaped graph: python scripts/k2_time.py [C] [top_k]"""
+"""Times the edge-path kernels alone on the pokec-shaped graph (C = 32): fused / unfused forward (train + inference),
+deterministic backward, scatter backward.  python scripts/k2_time.py [shape] [C] [k]"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sngnn_b200 import synth, graph as G, functional as SF, _C
-C = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-k = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-N, Fd, E, _ = synth.SHAPES["pokec"]
+
+shape = sys.argv[1] if len(sys.argv) > 1 else "pokec"
+C = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 dev = "cuda"
+N, Fd, E, _ = synth.SHAPES[shape]
 ei = synth.make_graph(N, E, seed=1, device=dev, symmetric=True)
-g = G.prepare(ei, N, True, structural=True)
+g = G.prepare(ei, N, True)
+Ep = g.num_edges
 torch.manual_seed(0)
 h = torch.randn(N, C, device=dev)
 gg = torch.randn(N, C, device=dev)
-def timed(f, reps=10):
-    for _ in range(3): f()
+wt = torch.randn(N, C, device=dev)
+bw = torch.randn(C, device=dev); beta = torch.full((1,), 0.5, device=dev)
+fuse = (wt, bw, beta, None)
+
+
+def timed(fn, steps=10, warm=3):
+    for _ in range(warm): fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(reps): f()
+    for _ in range(steps): fn()
     b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps
-sel = {}
-def fwd(): sel["o"] = SF.EdgeTopkAgg.apply(h, g, k, 0.0)
-ms_f = timed(fwd)
-out, ss, sw, sc = sel["o"]
-dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
-_, _, inv_norm = SF.rownorm(h, want_f32=False, want_inv=True)
-def bwd():
+    return a.elapsed_time(b) / steps
+
+
+res = {"shape": shape, "N": N, "edges": Ep, "C": C, "k": k, "symmetric": g.symmetric, "n_long": int(g.rows_long.numel()),
+       "n_hub": int(g.rows_hub.numel()), "max_deg": g.max_deg}
+hbm = 6499.0
+b_plain = Ep * (4 * C + 4) + N * (8 * C + 8)
+res["fwd_infer_ms"] = timed(lambda: SF._edge_fwd(h, g, 0, k, 0.0, False))
+res["fwd_train_ms"] = timed(lambda: SF._edge_fwd(h, g, 0, k, 0.0, True, want_q=True))
+res["fwd_fused_infer_ms"] = timed(lambda: SF._edge_fwd(h, g, 0, k, 0.0, False, fuse))
+res["fwd_fused_train_ms"] = timed(lambda: SF._edge_fwd(h, g, 0, k, 0.0, True, fuse, want_q=True))
+res["fwd_infer_frac_hbm"] = b_plain / res["fwd_infer_ms"] / 1e6 / hbm
+res["fwd_train_frac_hbm"] = (b_plain + 8 * N * k) / res["fwd_train_ms"] / 1e6 / hbm
+res["fwd_fused_infer_frac_hbm"] = (b_plain + Ep * 4 * C) / res["fwd_fused_infer_ms"] / 1e6 / hbm
+saved = g.rows_long, g.rows_hub
+g.rows_long = g.rows_hub = None
+res["fwd_general_kernel_infer_ms"] = timed(lambda: SF._edge_fwd(h, g, 0, k, 0.0, False))
+g.rows_long, g.rows_hub = saved
+out, ss, sw, sq, sc, inv, diff = SF._edge_fwd(h, g, 0, k, 0.0, True, fuse, want_q=True)
+nsel = int(sc.sum())
+res["selected_edges"] = nsel
+coef = torch.empty(2 * Ep, device=dev); dnt = torch.empty_like(h); dh = torch.empty_like(h); dwt = torch.empty_like(h)
+part = torch.empty(_C.PARTIALS, device=dev); dbeta = torch.empty(1, device=dev)
+
+
+def bwd(fused):
+    _C.call("sng_edge_bwd", h, _C.ptr(h), _C.ptr(inv), _C.ptr(gg), N, C, C, C, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), _C.ptr(g.tpos),
+            _C.ptr(g.rowptr_out), _C.ptr(g.col_out), g.src_shift, Ep, k, _C.ptr(ss), _C.ptr(sw), _C.ptr(sq), _C.ptr(sc),
+            _C.ptr(beta if fused else None), _C.ptr(diff if fused else None), C, _C.ptr(dbeta if fused else None), _C.ptr(coef), _C.ptr(dnt),
+            _C.ptr(part), _C.ptr(dh), _C.ptr(dwt if fused else None), C)
+
+
+res["bwd_det_ms"] = timed(lambda: bwd(False))
+res["bwd_det_fused_ms"] = timed(lambda: bwd(True))
+b_bwd = nsel * (3 * 4 * C + 16) + 5 * N * 4 * C
+res["bwd_det_frac_hbm"] = b_bwd / res["bwd_det_ms"] / 1e6 / hbm
+dval, dnrm = torch.zeros_like(h), torch.zeros_like(h)
+
+
+def bwd_scatter():
     dval.zero_(); dnrm.zero_()
-    _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(gg), N, N, 0, C, C, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss), _C.ptr(sw),
-                                       _C.ptr(sc), _C.ptr(g.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()), "bwd")
-ms_b = timed(bwd)
-Ep, nsel = g.num_edges, int(sc.sum())
-bf = Ep * (4 * C + 4) + N * (8 * C + 8) + 8 * N * k
-bb = nsel * (12 * C + 16) + 5 * N * 4 * C
-print(json.dumps(dict(C=C, k=k, fwd_ms=round(ms_f, 3), fwd_gbs=round(bf / ms_f / 1e6), bwd_ms=round(ms_b, 3), bwd_gbs=round(bb / ms_b / 1e6), nsel=nsel,
-                      checksum=float(out.double().abs().sum()), selsum=int(ss.clamp(min=0).long().sum()))))
+    _C.call("sng_edge_agg_bwd", h, _C.ptr(h), _C.ptr(inv), _C.ptr(gg), N, N, 0, C, C, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), k, _C.ptr(ss),
+            _C.ptr(sw), _C.ptr(sc), _C.ptr(g.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh))
+
+
+res["bwd_scatter_ms"] = timed(bwd_scatter)
+res["spmm_ms"] = timed(lambda: SF.spmm(gg, g.rowptr_in, g.col_in_shift, N))
+print(json.dumps(res))

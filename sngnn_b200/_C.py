@@ -18,17 +18,20 @@ SIGNATURES = {
     "sng_last_error": (ctypes.c_char_p, []),
     "sng_device_info": (_I32, [_P, _P, _P]),
     "sng_rownorm_f32": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P]),
-    "sng_edge_topk_agg_fwd": (_I32, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _F32, _P, _I64, _P, _P, _P, _P, _P]),
+    "sng_edge_fwd": (_I32, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _I64, _I32, _F32, _P, _I64,
+                            _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "sng_edge_bwd": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P,
+                            _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "sng_edge_agg_bwd": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sng_list_agg_fwd": (_I32, [_P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "sng_spmm_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "sng_pp_fuse_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "sng_pp_beta_grad": (_I32, [_P, _P, _P, _I64, _P, _P]),
+    "sng_pp_beta_grad": (_I32, [_P, _P, _P, _I64, _P, _P, _P]),
     "sng_sddmm_dot": (_I32, [_P, _I64, _I64, _I64, _P, _P, _I64, _P, _P]),
     "sng_allpairs_dense_f32": (_I32, [_P, _I64, _I64, _I64, _P, _P]),
     "sng_class_sums_f64": (_I32, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P]),
     "sng_graph_prepare_workspace_bytes": (_SZ, [_I64, _I64]),
-    "sng_graph_prepare": (_I32, [_P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "sng_graph_prepare": (_I32, [_P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sng_simknn_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I32]),
     "sng_simknn_build": (_I32, [_P, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, _I32, _F32, _I32,
                                 _P, _P, _P, _P, _P, _P, _SZ, _P]),
@@ -73,11 +76,31 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+PARTIALS = 4096          # SNG_PARTIALS of include/sng.h
+
+
+def stream(t=None):
+    """Current CUDA stream handle of the device that owns `t` (default: the current device)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(None if t is None else t.device).cuda_stream)
+
+
+def call(name, anchor, *args):
+    """Run the asynchronous entry point `name` on the device that owns the tensor `anchor`, on that device's current
+    stream (the stream is always the last C argument), and raise on a non-zero return code.  The library launches on the
+    CURRENT device, so the guard matters whenever the tensors do not live on it (model.to('cuda:1') without set_device)."""
+    with torch.cuda.device(anchor.device):
+        rc = getattr(lib(), name)(*args, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    check(rc, name)
 
 
 def require_cuda(*tensors):
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("sngnn_b200 runs on CUDA tensors only (there is no CPU path); got a tensor on " + str(t.device))
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"sngnn_b200: tensors on different devices ({dev} and {t.device})")

@@ -43,37 +43,6 @@ __global__ void __launch_bounds__(kThreads) rownorm_kernel(const float* __restri
     }
 }
 
-// ------------------------------------------------------------------------------------------ K2 forward
-// Sorted (score desc, arrival order on ties) candidate list of one warp, in shared memory.
-struct TopList {
-    float* s;
-    int* j;
-    int cnt;
-    float kth;   // score of the last entry once the list is full, else -inf
-    __device__ __forceinline__ void insert(float sc, int src, int top_k, int lane) {
-        // number of entries that stay in front: those with score >= sc (earlier position wins ties)
-        int pos = 0;
-        for (int t0 = 0; t0 < cnt; t0 += 32) {
-            const int t = t0 + lane;
-            pos += __popc(__ballot_sync(0xffffffffu, t < cnt && s[t] >= sc));
-        }
-        const int ncnt = min(cnt + 1, top_k);
-        // shift [pos, ncnt-1) one slot down; top_k <= 64 => two slots per lane
-        float a0 = 0.f, a1 = 0.f; int b0 = 0, b1 = 0;
-        const int t0 = lane, t1 = lane + 32;
-        const bool m0 = t0 > pos && t0 < ncnt, m1 = t1 > pos && t1 < ncnt;
-        if (m0) { a0 = s[t0 - 1]; b0 = j[t0 - 1]; }
-        if (m1) { a1 = s[t1 - 1]; b1 = j[t1 - 1]; }
-        __syncwarp();
-        if (m0) { s[t0] = a0; j[t0] = b0; }
-        if (m1) { s[t1] = a1; j[t1] = b1; }
-        if (lane == 0) { s[pos] = sc; j[pos] = src; }
-        __syncwarp();
-        cnt = ncnt;
-        kth = (cnt == top_k) ? s[top_k - 1] : -CUDART_INF_F;
-    }
-};
-
 // inv_r[i] = 1 / max(||h_i||, 1e-12): one warp per row.  The edge kernels gather this scalar per edge (the array is
 // L2 resident) instead of recomputing every source row's norm from its gathered features.
 __global__ void __launch_bounds__(kThreads) row_inv_norm_kernel(const float* __restrict__ h, int64_t n, int c, int64_t ld, float* __restrict__ inv) {
@@ -86,260 +55,407 @@ __global__ void __launch_bounds__(kThreads) row_inv_norm_kernel(const float* __r
     }
 }
 
-// K2 forward.  One warp per target row; lane e of the warp owns in-edge e of the current 32-edge chunk (source id,
-// source 1/norm, score); a group of G lanes fetches one source row per step with one 128-bit load per lane.
-// Loads are never predicated: missing edges are redirected to the target row itself and masked afterwards.
-template <int G, bool SELECT_ALL>
-__global__ void __launch_bounds__(kThreads) edge_topk_agg_fwd_kernel(
-    const float* __restrict__ h, const float* __restrict__ inv_r, int n, int row_offset, int c, int ldh, const int* __restrict__ rowptr,
-    const int* __restrict__ col, int top_k, float thr, float* __restrict__ out, int ldo,
-    int* __restrict__ sel_src, float* __restrict__ sel_w, int* __restrict__ sel_cnt) {
+// ------------------------------------------------------------------------------------------ K2 forward (+ fused K4 epilogue)
+// One launch family computes, for every target row i with in-edge list P_i (CSR by target, position order):
+//   s_e = <n_i, n_j>, S_i = first min(top_k, |P_i|) edges under (s desc, position asc) with s >= thr,
+//   out_1[i] = sum_{e in S_i} s_e h_j / max(|P_i|, 1)                                  (R: models/models.py:139-158, 244-263, 331-334)
+// and, when `wt` is given (SNGNN++ on a graph whose in-lists equal its out-lists), in the SAME pass over the edges
+//   out_0[i] = sum_{e in P_i} Wt[j] + b_w,  out[i] = beta out_0 + (1 - beta) out_1 (+ bias)   (R: models/models.py:124-136)
+// Rows are dispatched by in-degree (lists built once by sng_graph_prepare):
+//   deg <= 32          edge_fwd_short_kernel: warp per row, the whole in-list lives in registers, one pass, no re-gather
+//   32 < deg <= 1024   edge_fwd_long_kernel : warp per row, 32-edge chunks, running top-k in shared memory
+//   deg > 1024         edge_fwd_hub_kernel  : block per row, 8 warps scan interleaved chunks, lists merged in shared memory
+struct EdgeFwdArgs {
+    const float* h; const float* inv_r;
+    int n, row_offset, c, ldh;
+    const int* rowptr; const int* col; const int* tpos;
+    const int* rows; int n_rows;             // long / hub kernels: explicit list of (local) row ids, or nullptr = all n rows
+    int skip_deg;                            // long kernel over all rows: rows with more in-edges are left to the hub kernel (0 = none)
+    int top_k; float thr;
+    float* out; int ldo;
+    int* sel_src; float* sel_w; int* sel_q; int* sel_cnt;      // saved for backward; all nullptr in inference
+    const float* wt; int ldw; const float* b_w; const float* beta; const float* bias; float* diff;   // fused SNGNN++ epilogue
+};
+
+constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+// order-preserving integer image of a float; 0 is reserved for "not a candidate"
+__device__ __forceinline__ unsigned okey(float s) { const unsigned ub = __float_as_uint(s); return (ub & 0x80000000u) ? ~ub : (ub | 0x80000000u); }
+__device__ __forceinline__ bool better_sp(float sa, int pa, float sb, int pb) { return sa > sb || (sa == sb && pa < pb); }
+
+template <int G>
+__device__ __forceinline__ void cross_group_sum4(float4& a) {
+    a.x = cross_group_sum<G>(a.x); a.y = cross_group_sum<G>(a.y); a.z = cross_group_sum<G>(a.z); a.w = cross_group_sum<G>(a.w);
+}
+
+template <bool FUSE>
+__device__ __forceinline__ void write_row(const EdgeFwdArgs& a, int row, int c4, const float4& acc, const float4& a0, int deg, float beta,
+                                          const float4& bw, const float4& bb) {
+    const float invd = 1.0f / (float)max(deg, 1);                    // PyG aggr='mean': the full in-degree, selected or not
+    const float4 o1 = scale4(acc, invd);
+    const int64_t o = (int64_t)row * a.ldo + c4;
+    if (FUSE) {
+        const float4 o0 = make_float4(a0.x + bw.x, a0.y + bw.y, a0.z + bw.z, a0.w + bw.w);
+        float4 r;
+        r.x = beta * o0.x + (1.f - beta) * o1.x + bb.x; r.y = beta * o0.y + (1.f - beta) * o1.y + bb.y;
+        r.z = beta * o0.z + (1.f - beta) * o1.z + bb.z; r.w = beta * o0.w + (1.f - beta) * o1.w + bb.w;
+        *reinterpret_cast<float4*>(a.out + o) = r;
+        if (a.diff) *reinterpret_cast<float4*>(a.diff + o) = make_float4(o0.x - o1.x, o0.y - o1.y, o0.z - o1.z, o0.w - o1.w);   // d out / d beta
+    } else {
+        *reinterpret_cast<float4*>(a.out + o) = o1;
+    }
+}
+
+// Short rows (deg <= 32).  A group of G = C/4 lanes fetches one source row per step with one 128-bit load per lane; the G
+// partial dot products a lane then holds are reduced ACROSS its group with a transposing butterfly (G-1 shuffles), which
+// leaves lane (q, grp) with the finished score of edge q * EPW + grp -- the edge whose source id and 1/norm it loaded in
+// the first place.  The <= 32 gathered rows stay in registers: selection is top_k rounds of a one-instruction warp max in
+// which the WINNING lane records its own rank, and the weighted sum re-uses the registers (weights are shuffled back to
+// the groups), so every source row is read exactly once.  The Wt rows of the fused epilogue ride on the same indices.
+template <int G, bool FUSE, bool SELECT_ALL>
+__global__ void __launch_bounds__(kThreads, G == 8 ? 2 : 4) edge_fwd_short_kernel(const EdgeFwdArgs a) {
     constexpr int EPW = 32 / G;                 // edges per warp step
-    constexpr int U = UnrollFwd<G>::value;      // steps whose loads are issued together
-    extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = lane % G, grp = lane / G;
-    const bool ch_ok = q * 4 < c;
-    const int c4 = ch_ok ? q * 4 : 0;           // lanes beyond the channel count read channel 0 and contribute with weight 0
-    const float* hb = h + c4;
-    TopList L;
-    L.s = smem + (size_t)warp * 2 * max(top_k, 1);
-    L.j = reinterpret_cast<int*>(L.s + max(top_k, 1));
+    const int my_e = q * EPW + grp;             // the edge of the row this lane owns: fetched at step q by group grp
+    const bool ch_ok = q * 4 < a.c;
+    const int c4 = ch_ok ? q * 4 : 0;           // lanes beyond the channel count read channel 0 and contribute zeros
+    const float* hb = a.h + c4;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < n; row += gridDim.x * kWarpsPerBlock) {
-        const int grow = row_offset + row;
-        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-        float4 ni = scale4(ldg4(hb + (int64_t)grow * ldh), __ldg(inv_r + grow));     // target row, normalised
+    float beta = 0.f;
+    float4 bw = z4, bb = z4;
+    const float* wb = nullptr;
+    if (FUSE) {
+        beta = __ldg(a.beta);
+        wb = a.wt + c4;
+        if (ch_ok) { bw = ldg4(a.b_w + c4); if (a.bias) bb = ldg4(a.bias + c4); }
+    }
+    const bool train = !SELECT_ALL && a.sel_cnt != nullptr;
+    const int stride = gridDim.x * kWarpsPerBlock;
+    int row = blockIdx.x * kWarpsPerBlock + warp;
+    int beg = 0, end = 0, jl = 0;
+    if (row < a.n) {
+        beg = __ldg(a.rowptr + row); end = __ldg(a.rowptr + row + 1);
+        jl = (my_e < end - beg && end - beg <= 32) ? __ldg(a.col + beg + my_e) : a.row_offset + row;   // missing edges read the target row
+    }
+    for (; row < a.n; row += stride) {
+        const int grow = a.row_offset + row;
+        const int cbeg = beg, deg = end - beg, cjl = jl;
+        const int nrow = row + stride;          // the next row's metadata is requested before this row's work
+        if (nrow < a.n) {
+            beg = __ldg(a.rowptr + nrow); end = __ldg(a.rowptr + nrow + 1);
+            jl = (my_e < end - beg && end - beg <= 32) ? __ldg(a.col + beg + my_e) : a.row_offset + nrow;
+        }
+        if (deg > 32) continue;                 // long rows run on their own kernels
+        const bool has = my_e < deg;
+        const float irl = __ldg(a.inv_r + cjl);
+        int tq = 0;
+        if (train && has && a.tpos) tq = __ldg(a.tpos + cbeg + my_e);
+        float4 ni = scale4(ldg4(hb + (int64_t)grow * a.ldh), __ldg(a.inv_r + grow));     // target row, normalised
         if (!ch_ok) ni = z4;
+        float4 v[G];
+        float4 a0 = z4;
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+            const int j = __shfl_sync(kFull, cjl, grp * G + u);                         // owner of edge u * EPW + grp
+            v[u] = z4;
+            if (u * EPW < deg) {                                                         // warp-uniform
+                v[u] = ldg4(hb + (int64_t)j * a.ldh);
+                if (FUSE && u * EPW + grp < deg) add4(a0, ldg4(wb + (int64_t)j * a.ldw));
+            }
+        }
+        float d[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) d[u] = dot4(ni, v[u]);
+        // transposing reduction over the group: lane q ends up with the group's sum of d[q]
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) {
+            const bool up = (q & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+                const float send = up ? d[i] : d[i + o];
+                const float keep = up ? d[i + o] : d[i];
+                d[i] = keep + __shfl_xor_sync(kFull, send, o);
+            }
+        }
+        const float my_s = d[0] * irl + 0.0f;                                            // + 0: -0 becomes +0, equal scores get equal keys
+        float wsel;
+        int cnt = 0, myrank = -1;
+        if (SELECT_ALL) {
+            wsel = has ? my_s : 0.f;
+        } else {
+            unsigned key = (has && my_s >= a.thr) ? okey(my_s) : 0u;
+            const int rounds = min(a.top_k, deg);
+            for (; cnt < rounds; ++cnt) {
+                const unsigned mx = __reduce_max_sync(kFull, key);
+                if (mx == 0u) break;
+                const bool is = key == mx;
+                const unsigned m = __ballot_sync(kFull, is);
+                bool win = is;
+                if (m & (m - 1)) {                                                       // exact tie: the lowest edge position wins
+                    const unsigned emin = __reduce_min_sync(kFull, is ? (unsigned)my_e : 64u);
+                    win = is && (unsigned)my_e == emin;
+                }
+                if (win) { key = 0u; myrank = cnt; }
+            }
+            wsel = myrank >= 0 ? my_s : 0.f;
+        }
         float4 acc = z4;
-        L.cnt = 0; L.kth = -CUDART_INF_F;
-
-        for (int base = beg; base < end; base += 32) {
-            const int nchunk = min(32, end - base);
-            const bool has = lane < nchunk;
-            const int jl = has ? __ldg(col + base + lane) : grow;
-            const float irl = __ldg(inv_r + jl);
-            float my_d = 0.f;                                    // <n_i, h_j> of edge base+lane
-            for (int st = 0; st < nchunk; st += EPW * U) {
-                float4 v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = __shfl_sync(0xffffffffu, jl, (st + u * EPW + grp) & 31);
-                    v[u] = ldg4(hb + (int64_t)j * ldh);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float d = group_sum<G>(dot4(ni, v[u]));
-                    if (SELECT_ALL) {
-                        // weight of this step's edge = its score, available in the owning lane only after the assembly below;
-                        // recompute it here from the edge's own 1/norm instead
-                        const int e = st + u * EPW + grp;
-                        const float w = __shfl_sync(0xffffffffu, irl, e & 31);
-                        if (e < nchunk && ch_ok) fma4(acc, d * w, v[u]);
-                    } else {
-                        const float t = __shfl_sync(0xffffffffu, d, (lane % EPW) * G);      // hand (step, group) to the edge's lane
-                        if (lane / EPW == st / EPW + u) my_d = t;
-                    }
-                }
-            }
-            if (!SELECT_ALL) {
-                const float my_s = my_d * irl + 0.0f;            // + 0: -0 becomes +0, so equal scores are equal as integers too
-                const bool valid = has && my_s >= thr;
-                if (L.cnt == 0) {
-                    // empty list (normally the row's only chunk): top_k rounds of a one-instruction warp max over an
-                    // order-preserving integer image of the score; the lowest lane among the maxima = lowest edge position
-                    const unsigned ub = __float_as_uint(my_s);
-                    unsigned key = valid ? ((ub & 0x80000000u) ? ~ub : (ub | 0x80000000u)) : 0u;     // 0 = not a candidate
-                    int t = 0;
-                    for (; t < top_k; ++t) {
-                        const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-                        if (mx == 0u) break;
-                        const int w = __ffs(__ballot_sync(0xffffffffu, key == mx)) - 1;
-                        if (lane == w) { L.s[t] = my_s; L.j[t] = jl; key = 0u; }
-                    }
-                    __syncwarp();
-                    L.cnt = t;
-                    L.kth = (t == top_k) ? L.s[top_k - 1] : -CUDART_INF_F;
-                } else {
-                    unsigned m = __ballot_sync(0xffffffffu, valid && (L.cnt < top_k || my_s > L.kth));
-                    while (m) {                                              // ascending lane == ascending edge position
-                        const int l = __ffs(m) - 1;
-                        m &= m - 1;
-                        const float sg = __shfl_sync(0xffffffffu, my_s, l);
-                        const int jg = __shfl_sync(0xffffffffu, jl, l);
-                        if (L.cnt < top_k || sg > L.kth) L.insert(sg, jg, top_k, lane);
-                    }
-                }
+        for (int u = 0; u < G; ++u) {
+            if (u * EPW < deg) {
+                const float w = __shfl_sync(kFull, wsel, grp * G + u);
+                fma4(acc, w, v[u]);
             }
         }
-        if (!SELECT_ALL) {
-            const int cnt = L.cnt;
-            for (int st = 0; st < cnt; st += EPW) {
-                const int t = min(st + grp, cnt - 1);                        // clamp: the duplicate gets weight 0
-                const float w = st + grp < cnt ? L.s[t] : 0.f;
-                fma4(acc, w, ldg4(hb + (int64_t)L.j[t] * ldh));
+        cross_group_sum4<G>(acc);
+        if (FUSE) cross_group_sum4<G>(a0);
+        if (grp == 0 && ch_ok) write_row<FUSE>(a, row, q * 4, acc, a0, deg, beta, bw, bb);
+        if (train) {
+            const int64_t lo = (int64_t)row * a.top_k;
+            if (myrank >= 0) {
+                a.sel_src[lo + myrank] = cjl; a.sel_w[lo + myrank] = my_s;
+                if (a.sel_q) a.sel_q[lo + myrank] = tq;
             }
-            if (lane < top_k) {
-                sel_src[(int64_t)row * top_k + lane] = lane < cnt ? L.j[lane] : -1;
-                sel_w[(int64_t)row * top_k + lane] = lane < cnt ? L.s[lane] : 0.f;
+            for (int t = cnt + lane; t < a.top_k; t += 32) {                             // -1 padding behind the list
+                a.sel_src[lo + t] = -1; a.sel_w[lo + t] = 0.f;
+                if (a.sel_q) a.sel_q[lo + t] = 0;
             }
-            if (lane + 32 < top_k) {
-                sel_src[(int64_t)row * top_k + lane + 32] = lane + 32 < cnt ? L.j[lane + 32] : -1;
-                sel_w[(int64_t)row * top_k + lane + 32] = lane + 32 < cnt ? L.s[lane + 32] : 0.f;
-            }
-            if (lane == 0) sel_cnt[row] = cnt;
-            __syncwarp();
-        }
-        acc.x = cross_group_sum<G>(acc.x); acc.y = cross_group_sum<G>(acc.y);
-        acc.z = cross_group_sum<G>(acc.z); acc.w = cross_group_sum<G>(acc.w);
-        if (grp == 0 && ch_ok) {
-            const float invd = 1.0f / (float)max(end - beg, 1);
-            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + q * 4) = scale4(acc, invd);
+            if (lane == 0) a.sel_cnt[row] = cnt;
         }
     }
 }
 
-// K2 forward, selection variant (top_k <= 32).  One warp per target row, 32 in-edges per chunk.  A group of G = C/4 lanes
-// fetches one source row per step with one 128-bit load per lane (32/G full rows per warp step, G steps per chunk), and
-// the G partial dot products a lane then holds are reduced ACROSS its group with a transposing butterfly (G-1 shuffles
-// instead of G log2 G), which leaves every lane with the finished score of exactly one edge -- the edge whose source id
-// and 1/norm it loaded in the first place.  The running top-k lives in registers (lane t = rank t).  The first chunk is
-// ranked by top_k rounds of a one-instruction warp max; later chunks only insert the candidates that beat the k-th score.
-// The <= top_k winners are re-gathered at the end (L1 hits), so nothing of a chunk has to stay live across chunks.
-template <int G, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) edge_topk_sel_fwd_kernel(
-    const float* __restrict__ h, const float* __restrict__ inv_r, int n, int row_offset, int c, int ldh, const int* __restrict__ rowptr,
-    const int* __restrict__ col, int top_k, float thr, float* __restrict__ out, int ldo,
-    int* __restrict__ sel_src, float* __restrict__ sel_w, int* __restrict__ sel_cnt) {
-    constexpr int EPW = 32 / G;                 // edges per warp step
-    constexpr int UB = G < 8 ? G : 8;           // steps whose loads are issued together
+// Sorted (score desc, position asc) candidate list of one warp, in shared memory.
+struct TopList {
+    float* s;
+    int* p;
+    int cnt;
+    float kth;   // score of the last entry once the list is full, else -inf
+    // a warp scans its chunks in increasing position order, so a newcomer loses every tie: entries with score >= sc stay in front
+    __device__ __forceinline__ void insert(float sc, int pos, int top_k, int lane) {
+        int at = 0;
+        for (int t0 = 0; t0 < cnt; t0 += 32) {
+            const int t = t0 + lane;
+            at += __popc(__ballot_sync(kFull, t < cnt && s[t] >= sc));
+        }
+        const int ncnt = min(cnt + 1, top_k);
+        // shift [at, ncnt-1) one slot down; top_k <= 64 => two slots per lane
+        float a0 = 0.f, a1 = 0.f; int b0 = 0, b1 = 0;
+        const int t0 = lane, t1 = lane + 32;
+        const bool m0 = t0 > at && t0 < ncnt, m1 = t1 > at && t1 < ncnt;
+        if (m0) { a0 = s[t0 - 1]; b0 = p[t0 - 1]; }
+        if (m1) { a1 = s[t1 - 1]; b1 = p[t1 - 1]; }
+        __syncwarp();
+        if (m0) { s[t0] = a0; p[t0] = b0; }
+        if (m1) { s[t1] = a1; p[t1] = b1; }
+        if (lane == 0 && at < top_k) { s[at] = sc; p[at] = pos; }
+        __syncwarp();
+        cnt = ncnt;
+        kth = (cnt == top_k) ? s[top_k - 1] : -CUDART_INF_F;
+    }
+};
+
+// One warp scans the 32-edge chunks first, first + step, ... of a row: lane e owns edge e of the chunk (source id, 1/norm,
+// score); a group of G lanes fetches one source row per step.  SELECT_ALL accumulates the weighted rows on the fly, the
+// selection variant only maintains the warp's top-k list (winners are re-gathered afterwards: they were loaded moments ago).
+template <int G, bool FUSE, bool SELECT_ALL>
+__device__ __forceinline__ void scan_row(const EdgeFwdArgs& a, const float* hb, const float* wb, int grow, int end, int first, int step,
+                                         const float4& ni, bool ch_ok, int lane, TopList& L, float4& acc, float4& a0) {
+    constexpr int EPW = 32 / G;
+    constexpr int U = (G <= 8) ? G : 8;         // steps whose loads are issued together
+    const int grp = lane / G;
+    for (int base = first; base < end; base += step) {
+        const int nchunk = min(32, end - base);
+        const bool has = lane < nchunk;
+        const int jl = has ? __ldg(a.col + base + lane) : grow;                          // missing edges read the target row itself
+        const float irl = __ldg(a.inv_r + jl);
+        float my_d = 0.f;                                                               // <n_i, h_j> of edge base + lane
+        for (int st = 0; st < nchunk; st += EPW * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = st + u * EPW + grp;
+                const int j = __shfl_sync(kFull, jl, e & 31);
+                v[u] = ldg4(hb + (int64_t)j * a.ldh);
+                if (FUSE && e < nchunk) add4(a0, ldg4(wb + (int64_t)j * a.ldw));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float d = group_sum<G>(dot4(ni, v[u]));
+                if (SELECT_ALL) {
+                    const int e = st + u * EPW + grp;
+                    const float w = __shfl_sync(kFull, irl, e & 31);
+                    if (e < nchunk && ch_ok) fma4(acc, d * w + 0.0f, v[u]);
+                } else {
+                    const float t = __shfl_sync(kFull, d, (lane % EPW) * G);             // hand (step, group) to the edge's lane
+                    if (lane / EPW == st / EPW + u) my_d = t;
+                }
+            }
+        }
+        if (!SELECT_ALL) {
+            const float my_s = my_d * irl + 0.0f;
+            const bool valid = has && my_s >= a.thr;
+            if (L.cnt == 0) {
+                // empty list: top_k rounds of a one-instruction warp max; the lowest lane among the maxima = lowest edge position
+                unsigned key = valid ? okey(my_s) : 0u;
+                int t = 0;
+                for (; t < a.top_k; ++t) {
+                    const unsigned mx = __reduce_max_sync(kFull, key);
+                    if (mx == 0u) break;
+                    const int w = __ffs(__ballot_sync(kFull, key == mx)) - 1;
+                    if (lane == w) { L.s[t] = my_s; L.p[t] = base + lane; key = 0u; }
+                }
+                __syncwarp();
+                L.cnt = t;
+                L.kth = (t == a.top_k) ? L.s[a.top_k - 1] : -CUDART_INF_F;
+            } else {
+                unsigned m = __ballot_sync(kFull, valid && (L.cnt < a.top_k || my_s > L.kth));
+                while (m) {                                                             // ascending lane == ascending edge position
+                    const int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float sg = __shfl_sync(kFull, my_s, l);
+                    if (L.cnt < a.top_k || sg > L.kth) L.insert(sg, base + l, a.top_k, lane);
+                }
+            }
+        }
+    }
+}
+
+// weighted sum of the <= top_k winners of a finished list (source ids re-read through their positions) + the saved lists
+template <int G>
+__device__ __forceinline__ void finish_list(const EdgeFwdArgs& a, const float* hb, int row, const float* ls, const int* lp, int cnt, int lane,
+                                            float4& acc) {
+    constexpr int EPW = 32 / G;
+    const int grp = lane / G;
+    for (int st = 0; st < cnt; st += EPW) {
+        const int t = min(st + grp, cnt - 1);                                            // clamp: the duplicate gets weight 0
+        const float w = st + grp < cnt ? ls[t] : 0.f;
+        fma4(acc, w, ldg4(hb + (int64_t)__ldg(a.col + lp[t]) * a.ldh));
+    }
+    if (a.sel_cnt) {
+        const int64_t lo = (int64_t)row * a.top_k;
+        for (int t = lane; t < a.top_k; t += 32) {
+            const bool ok = t < cnt;
+            const int p = ok ? lp[t] : 0;
+            a.sel_src[lo + t] = ok ? __ldg(a.col + p) : -1;
+            a.sel_w[lo + t] = ok ? ls[t] : 0.f;
+            if (a.sel_q) a.sel_q[lo + t] = (ok && a.tpos) ? __ldg(a.tpos + p) : 0;
+        }
+        if (lane == 0) a.sel_cnt[row] = cnt;
+    }
+}
+
+template <int G, bool FUSE, bool SELECT_ALL>
+__global__ void __launch_bounds__(kThreads) edge_fwd_long_kernel(const EdgeFwdArgs a) {
+    extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = lane % G, grp = lane / G;
-    const int my_e = q * EPW + grp;             // the edge of a chunk this lane owns: fetched at step q by group grp
-    const bool ch_ok = q * 4 < c;
-    const float* hb = h + (ch_ok ? q * 4 : 0);  // lanes beyond the channel count read channel 0 and contribute zeros
+    const bool ch_ok = q * 4 < a.c;
+    const int c4 = ch_ok ? q * 4 : 0;
+    const float* hb = a.h + c4;
+    const float* wb = FUSE ? a.wt + c4 : nullptr;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // The next row's metadata (rowptr pair, first chunk of source ids) is loaded at the END of a row, ahead of its use.
-    // (Fetching it a whole row ahead costs 16 registers -- one resident block per SM -- and measured no gain.)
-    const int stride = gridDim.x * kWarpsPerBlock;
-    int row = blockIdx.x * kWarpsPerBlock + warp;
-    int beg = 0, end = 0, jl0 = 0;
-    if (row < n) {
-        beg = __ldg(rowptr + row); end = __ldg(rowptr + row + 1);
-        jl0 = my_e < end - beg ? __ldg(col + beg + my_e) : row_offset + row;
-    }
-    for (; row < n; row += stride) {
-        const int grow = row_offset + row;
-        const int nrow = row + stride;
-        int nbeg = 0, nend = 0, njl = 0;
-        float4 ni = scale4(ldg4(hb + (int64_t)grow * ldh), __ldg(inv_r + grow));     // target row, normalised
+    float beta = 0.f;
+    float4 bw = z4, bb = z4;
+    if (FUSE) { beta = __ldg(a.beta); if (ch_ok) { bw = ldg4(a.b_w + c4); if (a.bias) bb = ldg4(a.bias + c4); } }
+    TopList L;
+    L.s = smem + (size_t)warp * 2 * max(a.top_k, 1);
+    L.p = reinterpret_cast<int*>(L.s + max(a.top_k, 1));
+    const int total = a.rows ? a.n_rows : a.n;
+    for (int ri = blockIdx.x * kWarpsPerBlock + warp; ri < total; ri += gridDim.x * kWarpsPerBlock) {
+        const int row = a.rows ? __ldg(a.rows + ri) : ri;
+        const int grow = a.row_offset + row;
+        const int beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
+        if (a.skip_deg && end - beg > a.skip_deg) continue;
+        float4 ni = scale4(ldg4(hb + (int64_t)grow * a.ldh), __ldg(a.inv_r + grow));
         if (!ch_ok) ni = z4;
-        float ls = 0.f; int lj = -1;            // rank `lane` of the running top-k
-        int cnt = 0; float kth = -CUDART_INF_F; // entries in the list; score of rank top_k-1 once full
+        float4 acc = z4, a0 = z4;
+        L.cnt = 0; L.kth = -CUDART_INF_F;
+        scan_row<G, FUSE, SELECT_ALL>(a, hb, wb, grow, end, beg, 32, ni, ch_ok, lane, L, acc, a0);
+        if (!SELECT_ALL) { finish_list<G>(a, hb, row, L.s, L.p, L.cnt, lane, acc); __syncwarp(); }
+        cross_group_sum4<G>(acc);
+        if (FUSE) cross_group_sum4<G>(a0);
+        if (grp == 0 && ch_ok) write_row<FUSE>(a, row, q * 4, acc, a0, end - beg, beta, bw, bb);
+    }
+}
 
-        for (int base = beg; base < end; base += 32) {
-            const int nchunk = min(32, end - base);
-            const bool has = my_e < nchunk;
-            const int jl = base == beg ? jl0 : (has ? __ldg(col + base + my_e) : grow);   // missing edges read the target row itself
-            const float irl = __ldg(inv_r + jl);
-            float d[G];
-#pragma unroll
-            for (int u0 = 0; u0 < G; u0 += UB) {
-                float4 v[UB];
-#pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int j = __shfl_sync(0xffffffffu, jl, grp * G + u0 + u);     // owner of edge (u0+u)*EPW + grp
-                    v[u] = (u0 + u) * EPW < nchunk ? ldg4(hb + (int64_t)j * ldh) : z4;
+// Hub rows (in-degree > 1024): one block per row.  Warp w scans chunks w, w + 8, ... with its own top-k list; the 8 lists
+// are merged by ranking their <= 8 top_k entries against each other (positions are unique, so (score, position) is a
+// strict order and the ranks are the final ranks); warp 0 then finishes the row exactly like the long-row kernel.
+template <int G, bool FUSE, bool SELECT_ALL>
+__global__ void __launch_bounds__(kThreads) edge_fwd_hub_kernel(const EdgeFwdArgs a) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G;
+    const bool ch_ok = q * 4 < a.c;
+    const int c4 = ch_ok ? q * 4 : 0;
+    const float* hb = a.h + c4;
+    const float* wb = FUSE ? a.wt + c4 : nullptr;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k1 = max(a.top_k, 1);
+    float beta = 0.f;
+    float4 bw = z4, bb = z4;
+    if (FUSE) { beta = __ldg(a.beta); if (ch_ok) { bw = ldg4(a.b_w + c4); if (a.bias) bb = ldg4(a.bias + c4); } }
+    // shared memory: the warps' partial sums (acc, a0: 128 channels each; first, so they stay 16-byte aligned), 8 warp lists,
+    // the final list, the list lengths
+    float* part = smem;
+    float* lists = smem + (size_t)kWarpsPerBlock * 2 * 128;
+    float* fin_s = lists + (size_t)kWarpsPerBlock * 2 * k1;
+    int* fin_p = reinterpret_cast<int*>(fin_s + k1);
+    int* wcnt = fin_p + k1;
+    TopList L;
+    L.s = lists + (size_t)warp * 2 * k1;
+    L.p = reinterpret_cast<int*>(L.s + k1);
+    for (int ri = blockIdx.x; ri < a.n_rows; ri += gridDim.x) {
+        const int row = __ldg(a.rows + ri);
+        const int grow = a.row_offset + row;
+        const int beg = __ldg(a.rowptr + row), end = __ldg(a.rowptr + row + 1);
+        float4 ni = scale4(ldg4(hb + (int64_t)grow * a.ldh), __ldg(a.inv_r + grow));
+        if (!ch_ok) ni = z4;
+        float4 acc = z4, a0 = z4;
+        L.cnt = 0; L.kth = -CUDART_INF_F;
+        scan_row<G, FUSE, SELECT_ALL>(a, hb, wb, grow, end, beg + 32 * warp, 32 * kWarpsPerBlock, ni, ch_ok, lane, L, acc, a0);
+        cross_group_sum4<G>(acc);
+        cross_group_sum4<G>(a0);
+        if (grp == 0) {
+            *reinterpret_cast<float4*>(part + (size_t)(warp * 2) * 128 + q * 4) = acc;
+            *reinterpret_cast<float4*>(part + (size_t)(warp * 2 + 1) * 128 + q * 4) = a0;
+        }
+        if (lane == 0) wcnt[warp] = L.cnt;
+        __syncthreads();
+        int cnt = 0;
+        if (!SELECT_ALL) {
+            int total = 0;
+            for (int w = 0; w < kWarpsPerBlock; ++w) total += wcnt[w];
+            cnt = min(total, a.top_k);
+            for (int m = threadIdx.x; m < kWarpsPerBlock * k1; m += kThreads) {
+                const int w = m / k1, i = m - w * k1;
+                if (i >= wcnt[w]) continue;
+                const float s = lists[(size_t)w * 2 * k1 + i];
+                const int p = reinterpret_cast<int*>(lists + (size_t)w * 2 * k1 + k1)[i];
+                int rank = 0;
+                for (int w2 = 0; w2 < kWarpsPerBlock; ++w2) {
+                    const float* s2 = lists + (size_t)w2 * 2 * k1;
+                    const int* p2 = reinterpret_cast<const int*>(s2 + k1);
+                    for (int i2 = 0; i2 < wcnt[w2]; ++i2) rank += better_sp(s2[i2], p2[i2], s, p) ? 1 : 0;
                 }
-#pragma unroll
-                for (int u = 0; u < UB; ++u) d[u0 + u] = dot4(ni, v[u]);
+                if (rank < a.top_k) { fin_s[rank] = s; fin_p[rank] = p; }
             }
-            // transposing reduction over the group: lane q ends up with sum over the group of d[q]
-#pragma unroll
-            for (int o = G / 2; o >= 1; o >>= 1) {
-                const bool up = (q & o) != 0;
-#pragma unroll
-                for (int i = 0; i < o; ++i) {
-                    const float send = up ? d[i] : d[i + o];
-                    const float keep = up ? d[i + o] : d[i];
-                    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            __syncthreads();
+        }
+        if (warp == 0) {
+            float4 sacc = z4, sa0 = z4;
+            if (grp == 0) {
+                for (int w = 0; w < kWarpsPerBlock; ++w) {
+                    if (SELECT_ALL) add4(sacc, *reinterpret_cast<const float4*>(part + (size_t)(w * 2) * 128 + q * 4));
+                    if (FUSE) add4(sa0, *reinterpret_cast<const float4*>(part + (size_t)(w * 2 + 1) * 128 + q * 4));
                 }
             }
-            const float my_s = d[0] * irl + 0.0f;                                    // + 0: -0 becomes +0, equal scores get equal keys
-            const bool cand = has && my_s >= thr && (cnt < top_k || my_s > kth);
-            const unsigned ub = __float_as_uint(my_s);
-            unsigned key = cand ? ((ub & 0x80000000u) ? ~ub : (ub | 0x80000000u)) : 0u;   // order-preserving image; 0 = not a candidate
-            if (cnt == 0) {
-                // empty list (the row's first, usually only, chunk): candidates come out in rank order, so rank t goes to lane t
-                int t = 0;
-                for (; t < top_k; ++t) {
-                    const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-                    if (mx == 0u) break;
-                    const unsigned m = __ballot_sync(0xffffffffu, key == mx);
-                    int w = __ffs(m) - 1;
-                    if (m & (m - 1)) {                                               // exact tie: the lowest edge position wins
-                        const unsigned emin = __reduce_min_sync(0xffffffffu, key == mx ? (unsigned)my_e : 64u);
-                        w = __ffs(__ballot_sync(0xffffffffu, key == mx && (unsigned)my_e == emin)) - 1;
-                    }
-                    const float sw = __shfl_sync(0xffffffffu, my_s, w);
-                    const int jw = __shfl_sync(0xffffffffu, jl, w);
-                    if (lane == w) key = 0u;
-                    if (lane == t) { ls = sw; lj = jw; }
-                }
-                cnt = t;
-                if (cnt == top_k) kth = __shfl_sync(0xffffffffu, ls, top_k - 1);
-                continue;
-            }
-            while (true) {
-                const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-                if (mx == 0u) break;
-                unsigned m = __ballot_sync(0xffffffffu, key == mx);
-                int w = __ffs(m) - 1;
-                if (m & (m - 1)) {                                                   // exact tie: the lowest edge position wins
-                    const unsigned emin = __reduce_min_sync(0xffffffffu, key == mx ? (unsigned)my_e : 64u);
-                    w = __ffs(__ballot_sync(0xffffffffu, key == mx && (unsigned)my_e == emin)) - 1;
-                }
-                const float sw = __shfl_sync(0xffffffffu, my_s, w);
-                const int jw = __shfl_sync(0xffffffffu, jl, w);
-                if (lane == w) key = 0u;
-                // rank of the newcomer: list entries with score >= sw stay in front (earlier positions win ties)
-                const int pos = __popc(__ballot_sync(0xffffffffu, lane < cnt && ls >= sw));
-                if (pos >= top_k) break;                                            // nothing that remains can enter either
-                const float us = __shfl_up_sync(0xffffffffu, ls, 1);
-                const int uj = __shfl_up_sync(0xffffffffu, lj, 1);
-                if (lane > pos) { ls = us; lj = uj; }
-                if (lane == pos) { ls = sw; lj = jw; }
-                cnt = min(cnt + 1, top_k);
-                if (cnt == top_k) kth = __shfl_sync(0xffffffffu, ls, top_k - 1);
-                if (cnt == top_k) key = (my_s > kth) ? key : 0u;                     // candidates the new k-th score rules out
-            }
+            if (!SELECT_ALL) { finish_list<G>(a, hb, row, fin_s, fin_p, cnt, lane, sacc); cross_group_sum4<G>(sacc); }
+            if (grp == 0 && ch_ok) write_row<FUSE>(a, row, q * 4, sacc, sa0, end - beg, beta, bw, bb);
         }
-        // weighted sum of the winners' rows (re-gathered: they were loaded moments ago)
-        float4 acc = z4;
-        for (int st = 0; st < cnt; st += EPW) {
-            const int t = min(st + grp, cnt - 1);                                    // clamp: the duplicate gets weight 0
-            const float w = __shfl_sync(0xffffffffu, ls, t);
-            const int j = __shfl_sync(0xffffffffu, lj, t);
-            fma4(acc, st + grp < cnt ? w : 0.f, ldg4(hb + (int64_t)j * ldh));
-        }
-        if (lane < top_k) {
-            sel_src[(int64_t)row * top_k + lane] = lane < cnt ? lj : -1;
-            sel_w[(int64_t)row * top_k + lane] = lane < cnt ? ls : 0.f;
-        }
-        if (lane == 0) sel_cnt[row] = cnt;
-        acc.x = cross_group_sum<G>(acc.x); acc.y = cross_group_sum<G>(acc.y);
-        acc.z = cross_group_sum<G>(acc.z); acc.w = cross_group_sum<G>(acc.w);
-        if (grp == 0 && ch_ok) {
-            const float invd = 1.0f / (float)max(end - beg, 1);
-            *reinterpret_cast<float4*>(out + (int64_t)row * ldo + q * 4) = scale4(acc, invd);
-        }
-        if (nrow < n) {
-            nbeg = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1);
-            njl = my_e < nend - nbeg ? __ldg(col + nbeg + my_e) : row_offset + nrow;
-        }
-        beg = nbeg; end = nend; jl0 = njl;
+        __syncthreads();
     }
 }
 
@@ -459,6 +575,164 @@ __global__ void __launch_bounds__(kThreads) norm_bwd_finish_kernel(const float* 
     }
 }
 
+// ------------------------------------------------------------------------------------------ K2b backward, deterministic (two gather passes)
+// Closed form of SURVEY.md §3.4 without float atomics.  For a selected edge e = (j -> i), g1 = gscale * g (gscale = 1 - beta
+// under the fused SNGNN++ epilogue, else 1), deg_i = max(|P_i|, 1):
+//   dval_j += (s_e / deg_i) g1_i          ds_e = (h_j . g1_i) / deg_i          dn_i += ds_e n_j          dn_j += ds_e n_i
+//   dh = dval + (dn - n (n . dn)) / r
+// Pass T (by target, over the saved selection lists or the whole CSR): ds_e, the target side dn_i -> dnT, and the two
+//   per-edge coefficients A_e = s_e gscale / deg_i, B_e = ds_e / r_i written at the edge's position in the BY-SOURCE
+//   arrays (tpos, built once by sng_graph_prepare).
+// Pass S (by source, over the out-edges): dval_j = sum A_e g_i, dn_j = dnT_j + sum B_e h_i, then the normalisation
+//   backward, all in registers; under the fused epilogue the same walk also sums beta g_i over ALL out-edges = dL/dWt_j.
+// Every sum runs in a fixed order: the result is bit-reproducible.
+struct EdgeBwdArgs {
+    const float* h; const float* inv_r; const float* g;
+    int n_total, n, row_offset, c, ld, ldg;
+    const int* rowptr; const int* col; const int* tpos;
+    int top_k; const int* sel_src; const float* sel_w; const int* sel_q; const int* sel_cnt;
+    const float* beta; const float* diff; int lddiff; float* dbeta_part;
+    float2* coef; float* dnT;
+    const int* rowptr_out; const int* col_out; int shift;
+    float* dh; float* dwt; int lddw;
+};
+
+template <int G, bool SELECT_ALL>
+__global__ void __launch_bounds__(kThreads) edge_bwd_target_kernel(const EdgeBwdArgs a) {
+    constexpr int EPW = 32 / G;
+    constexpr int U = Unroll<G>::value;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G, c4 = q * 4;
+    const bool ch_ok = c4 < a.c;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float gscale = a.beta ? 1.0f - __ldg(a.beta) : 1.0f;
+    float bpart = 0.f;
+    for (int row = blockIdx.x * kWarpsPerBlock + warp; row < a.n; row += gridDim.x * kWarpsPerBlock) {
+        const int grow = a.row_offset + row;
+        const int beg = __ldg(a.rowptr + row), deg = __ldg(a.rowptr + row + 1) - beg;
+        const int cnt = SELECT_ALL ? deg : __ldg(a.sel_cnt + row);
+        const float invd = 1.0f / (float)max(deg, 1);
+        const float iri = __ldg(a.inv_r + grow);
+        const float4 graw = ch_ok ? ldg4(a.g + (int64_t)row * a.ldg + c4) : z4;
+        const float4 gs = scale4(graw, invd * gscale);                     // g1_i / deg_i
+        const float4 ni = ch_ok ? scale4(ldg4(a.h + (int64_t)grow * a.ld + c4), iri) : z4;
+        if (a.diff && grp == 0 && ch_ok) bpart += dot4(ldg4(a.diff + (int64_t)row * a.lddiff + c4), graw);   // dL/dbeta
+        float4 dni = z4;
+        for (int st = 0; st < cnt; st += EPW * U) {
+            float4 v[U]; int j[U], qp[U]; float w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = st + u * EPW + grp;
+                j[u] = -1; w[u] = 0.f; qp[u] = 0;
+                if (t < cnt) {
+                    if (SELECT_ALL) { j[u] = __ldg(a.col + beg + t); qp[u] = __ldg(a.tpos + beg + t); }
+                    else {
+                        const int64_t o = (int64_t)row * a.top_k + t;
+                        j[u] = __ldg(a.sel_src + o); w[u] = __ldg(a.sel_w + o); qp[u] = __ldg(a.sel_q + o);
+                    }
+                }
+                v[u] = (j[u] >= 0 && ch_ok) ? ldg4(a.h + (int64_t)j[u] * a.ld + c4) : z4;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (st + u * EPW >= cnt) break;                              // warp-uniform
+                const float irj = j[u] >= 0 ? __ldg(a.inv_r + j[u]) : 0.f;
+                const float ds = group_sum<G>(dot4(v[u], gs));               // dL/ds_e
+                const float s = SELECT_ALL ? group_sum<G>(dot4(ni, v[u])) * irj + 0.0f : w[u];
+                if (j[u] >= 0) {
+                    fma4(dni, ds * irj, v[u]);                               // ds_e n_j
+                    if (q == 0) a.coef[qp[u]] = make_float2(s * invd * gscale, ds * iri);
+                }
+            }
+        }
+        cross_group_sum4<G>(dni);
+        if (grp == 0 && ch_ok) *reinterpret_cast<float4*>(a.dnT + (int64_t)grow * a.ld + c4) = dni;
+    }
+    if (a.dbeta_part) {                                                      // fixed-order block sum -> one partial per block
+        bpart = group_sum<32>(bpart);
+        __shared__ float red[kWarpsPerBlock];
+        if (lane == 0) red[warp] = bpart;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < kWarpsPerBlock; ++w) t += red[w];
+            a.dbeta_part[blockIdx.x] = t;
+        }
+    }
+}
+
+template <int G, bool FUSE>
+__global__ void __launch_bounds__(kThreads) edge_bwd_source_kernel(const EdgeBwdArgs a) {
+    constexpr int EPW = 32 / G;
+    constexpr int U = Unroll<G>::value;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = lane % G, grp = lane / G, c4 = q * 4;
+    const bool ch_ok = c4 < a.c;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float beta = FUSE ? __ldg(a.beta) : 0.f;
+    for (int j = blockIdx.x * kWarpsPerBlock + warp; j < a.n_total; j += gridDim.x * kWarpsPerBlock) {
+        const int jr = j - a.shift;                                          // rows of the by-source CSR are shifted source ids
+        int beg = 0, end = 0;
+        if (jr >= 0) { beg = __ldg(a.rowptr_out + jr); end = __ldg(a.rowptr_out + jr + 1); }
+        float4 dval = z4, dnj = z4, dw = z4;
+        for (int base = beg; base < end; base += 32) {
+            const int nchunk = min(32, end - base);
+            const int il = lane < nchunk ? __ldg(a.col_out + base + lane) : 0;
+            const float2 cf = lane < nchunk ? __ldg(a.coef + base + lane) : make_float2(0.f, 0.f);
+            for (int st = 0; st < nchunk; st += EPW * U) {
+                float4 gv[U], hv[U]; float ca[U], cb[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = st + u * EPW + grp;
+                    const int i = __shfl_sync(kFull, il, e & 31);
+                    ca[u] = __shfl_sync(kFull, cf.x, e & 31);
+                    cb[u] = __shfl_sync(kFull, cf.y, e & 31);
+                    const bool on = e < nchunk && ch_ok;
+                    const bool sel = on && (ca[u] != 0.f || cb[u] != 0.f);   // an unselected edge has both coefficients 0
+                    if (!on) { ca[u] = 0.f; cb[u] = 0.f; }
+                    gv[u] = (FUSE ? on : sel) ? ldg4(a.g + (int64_t)i * a.ldg + c4) : z4;
+                    hv[u] = sel ? ldg4(a.h + (int64_t)i * a.ld + c4) : z4;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    fma4(dval, ca[u], gv[u]);
+                    fma4(dnj, cb[u], hv[u]);
+                    if (FUSE) add4(dw, gv[u]);
+                }
+            }
+        }
+        cross_group_sum4<G>(dval);
+        cross_group_sum4<G>(dnj);
+        if (FUSE) cross_group_sum4<G>(dw);
+        const float irj = __ldg(a.inv_r + j);
+        const float4 nj = ch_ok ? scale4(ldg4(a.h + (int64_t)j * a.ld + c4), irj) : z4;
+        float4 dn = ch_ok ? ldg4(a.dnT + (int64_t)j * a.ld + c4) : z4;
+        add4(dn, dnj);
+        const float proj = group_sum<G>(dot4(nj, dn));
+        if (grp == 0 && ch_ok) {
+            float4 o;
+            o.x = dval.x + (dn.x - nj.x * proj) * irj; o.y = dval.y + (dn.y - nj.y * proj) * irj;
+            o.z = dval.z + (dn.z - nj.z * proj) * irj; o.w = dval.w + (dn.w - nj.w * proj) * irj;
+            *reinterpret_cast<float4*>(a.dh + (int64_t)j * a.ld + c4) = o;
+            if (FUSE) *reinterpret_cast<float4*>(a.dwt + (int64_t)j * a.lddw + c4) = scale4(dw, beta);
+        }
+    }
+}
+
+// fixed-order sum of per-block partials (deterministic replacement of a float atomicAdd)
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+    __shared__ float red[256];
+    float t = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) t += part[i];
+    red[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
 // ------------------------------------------------------------------------------------------ K3 / K4
 template <int G>
 __device__ __forceinline__ float4 gather_sum(const float* __restrict__ x, int64_t ldx, const int* __restrict__ col,
@@ -538,7 +812,7 @@ __global__ void __launch_bounds__(kThreads) pp_fuse_fwd_kernel(const float* __re
 }
 
 __global__ void __launch_bounds__(256) pp_beta_grad_kernel(const float* __restrict__ out0, const float* __restrict__ out1,
-                                                          const float* __restrict__ g, int64_t numel, float* __restrict__ dbeta) {
+                                                          const float* __restrict__ g, int64_t numel, float* __restrict__ part) {
     float acc = 0.f;
     const int64_t n4 = numel / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -546,13 +820,13 @@ __global__ void __launch_bounds__(256) pp_beta_grad_kernel(const float* __restri
         acc = fmaf(a.x - b.x, gg.x, fmaf(a.y - b.y, gg.y, fmaf(a.z - b.z, gg.z, fmaf(a.w - b.w, gg.w, acc))));
     }
     acc = group_sum<32>(acc);
-    __shared__ float part[8];
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
-        v = group_sum<32>(v);
-        if (threadIdx.x == 0) atomicAdd(dbeta, v);
+    if (threadIdx.x == 0) {                                  // fixed order: one partial per block, summed by sum_partials_kernel
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        part[blockIdx.x] = t;
     }
 }
 
@@ -626,29 +900,114 @@ extern "C" int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx
     return check_launch("sng_rownorm_f32");
 }
 
-extern "C" int sng_edge_topk_agg_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
-                                     const int32_t* rowptr, const int32_t* col, int top_k, float thr, float* out, int64_t ldo,
-                                     int32_t* sel_src, float* sel_w, int32_t* sel_cnt, float* inv_norm, void* stream) {
-    if (int rc = check_rows("sng_edge_topk_agg_fwd", n, c, ldh)) return rc;
-    SNG_REQUIRE(h && rowptr && col && out && ldo % 4 == 0 && ldo >= c, "sng_edge_topk_agg_fwd: null pointer or bad ldo");
+namespace sng {
+// dynamic shared memory of the long-row / hub kernels (see their carve-up)
+static size_t long_smem(int top_k) { return (size_t)kWarpsPerBlock * 2 * (top_k > 0 ? top_k : 1) * sizeof(float); }
+static size_t hub_smem(int top_k) {
+    const size_t k1 = top_k > 0 ? top_k : 1;
+    return ((size_t)kWarpsPerBlock * 2 * k1 + 2 * k1 + kWarpsPerBlock + (size_t)kWarpsPerBlock * 2 * 128) * sizeof(float);
+}
+
+template <int G, bool FUSE, bool SELECT_ALL>
+static void launch_edge_fwd(EdgeFwdArgs a, const int32_t* rows_long, int64_t n_long, const int32_t* rows_hub, int64_t n_hub, cudaStream_t st) {
+    const size_t ls = long_smem(a.top_k), hs = hub_smem(a.top_k);
+    if constexpr (G <= 8) {
+        if (n_long >= 0) {                                   // degree lists known: short rows on the register kernel
+            a.rows = nullptr; a.n_rows = 0;
+            edge_fwd_short_kernel<G, FUSE, SELECT_ALL><<<grid_resident(edge_fwd_short_kernel<G, FUSE, SELECT_ALL>, a.n, kWarpsPerBlock), kThreads, 0, st>>>(a);
+            if (n_long > 0) {
+                a.rows = rows_long; a.n_rows = (int)n_long;
+                edge_fwd_long_kernel<G, FUSE, SELECT_ALL><<<grid_resident(edge_fwd_long_kernel<G, FUSE, SELECT_ALL>, n_long, kWarpsPerBlock, ls), kThreads, ls, st>>>(a);
+            }
+            if (n_hub > 0) {
+                a.rows = rows_hub; a.n_rows = (int)n_hub;
+                const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 4;
+                edge_fwd_hub_kernel<G, FUSE, SELECT_ALL><<<(unsigned)(n_hub < cap ? n_hub : cap), kThreads, hs, st>>>(a);
+            }
+            return;
+        }
+    }
+    // wide rows (C > 32) or no degree lists: the chunked kernel runs every row; listed hubs still get their block kernel
+    a.rows = nullptr; a.n_rows = 0;
+    a.skip_deg = (n_long >= 0 && n_hub > 0) ? 1024 : 0;
+    edge_fwd_long_kernel<G, FUSE, SELECT_ALL><<<grid_resident(edge_fwd_long_kernel<G, FUSE, SELECT_ALL>, a.n, kWarpsPerBlock, ls), kThreads, ls, st>>>(a);
+    if (a.skip_deg) {
+        a.rows = rows_hub; a.n_rows = (int)n_hub; a.skip_deg = 0;
+        const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 4;
+        edge_fwd_hub_kernel<G, FUSE, SELECT_ALL><<<(unsigned)(n_hub < cap ? n_hub : cap), kThreads, hs, st>>>(a);
+    }
+}
+}  // namespace sng
+
+extern "C" int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
+                            const int32_t* rowptr, const int32_t* col, const int32_t* tpos,
+                            const int32_t* rows_long, int64_t n_long, const int32_t* rows_hub, int64_t n_hub,
+                            int top_k, float thr, float* out, int64_t ldo,
+                            int32_t* sel_src, float* sel_w, int32_t* sel_q, int32_t* sel_cnt, float* inv_norm,
+                            const float* wt, int64_t ldw, const float* b_w, const float* beta, const float* bias, float* diff,
+                            void* stream) {
+    if (int rc = check_rows("sng_edge_fwd", n, c, ldh)) return rc;
+    SNG_REQUIRE(h && rowptr && col && out && ldo % 4 == 0 && ldo >= c, "sng_edge_fwd: null pointer or bad ldo");
     SNG_REQUIRE(row_offset >= 0 && row_offset + n <= n_total && n_total < (1ll << 31) && ldh < (1ll << 31) && ldo < (1ll << 31),
-                "sng_edge_topk_agg_fwd: bad row_offset / n_total");
-    SNG_REQUIRE(inv_norm, "sng_edge_topk_agg_fwd: inv_norm [n_total] is required");
-    SNG_REQUIRE(top_k <= SNG_MAX_TOPK, "sng_edge_topk_agg_fwd: top_k=%d > %d", top_k, SNG_MAX_TOPK);
-    SNG_REQUIRE(top_k <= 0 || (sel_src && sel_w && sel_cnt), "sng_edge_topk_agg_fwd: selection outputs required when top_k>0");
-    SNG_REQUIRE(top_k <= 0 || thr > -1.1f, "sng_edge_topk_agg_fwd: thr must be > -1.1 (knock-out sentinel of R models.py:153)");
+                "sng_edge_fwd: bad row_offset / n_total");
+    SNG_REQUIRE(inv_norm, "sng_edge_fwd: inv_norm [n_total] is required");
+    SNG_REQUIRE(top_k <= SNG_MAX_TOPK, "sng_edge_fwd: top_k=%d > %d", top_k, SNG_MAX_TOPK);
+    SNG_REQUIRE(top_k <= 0 || thr > -1.1f, "sng_edge_fwd: thr must be > -1.1 (knock-out sentinel of R models.py:153)");
+    SNG_REQUIRE(!sel_cnt || (top_k > 0 && sel_src && sel_w), "sng_edge_fwd: sel_src / sel_w / sel_cnt go together and need top_k > 0");
+    SNG_REQUIRE(!sel_q || (sel_cnt && tpos), "sng_edge_fwd: sel_q needs sel_cnt and tpos");
+    SNG_REQUIRE(n_long < 0 || ((n_long == 0 || rows_long) && (n_hub == 0 || rows_hub) && n_hub >= 0), "sng_edge_fwd: degree lists missing");
+    SNG_REQUIRE(!wt || (b_w && beta && ldw % 4 == 0 && ldw >= c && ldw < (1ll << 31)), "sng_edge_fwd: fused epilogue needs b_w, beta and a 16-byte aligned wt");
+    SNG_REQUIRE(wt || !diff, "sng_edge_fwd: diff is an output of the fused epilogue");
     if (n == 0) return SNG_OK;
-    const size_t smem = (size_t)kWarpsPerBlock * 2 * (top_k > 0 ? top_k : 1) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     row_inv_norm_kernel<<<grid_resident(row_inv_norm_kernel, n_total, kWarpsPerBlock), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm);
+    EdgeFwdArgs a;
+    a.h = h; a.inv_r = inv_norm; a.n = (int)n; a.row_offset = (int)row_offset; a.c = (int)c; a.ldh = (int)ldh;
+    a.rowptr = rowptr; a.col = col; a.tpos = tpos; a.rows = nullptr; a.n_rows = 0; a.skip_deg = 0;
+    a.top_k = top_k > 0 ? top_k : 0; a.thr = thr; a.out = out; a.ldo = (int)ldo;
+    a.sel_src = sel_src; a.sel_w = sel_w; a.sel_q = sel_q; a.sel_cnt = sel_cnt;
+    a.wt = wt; a.ldw = (int)ldw; a.b_w = b_w; a.beta = beta; a.bias = bias; a.diff = diff;
     SNG_DISPATCH_G(c,
-        if (top_k > 0 && top_k <= 32 && !getenv("SNG_K2_OLD")) {
-            constexpr int MB = G >= 16 ? 2 : (G == 8 ? 4 : 6);
-            edge_topk_sel_fwd_kernel<G, MB><<<grid_resident(edge_topk_sel_fwd_kernel<G, MB>, n, kWarpsPerBlock), kThreads, 0, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
-        }
-        else if (top_k > 0) edge_topk_agg_fwd_kernel<G, false><<<grid_resident(edge_topk_agg_fwd_kernel<G, false>, n, kWarpsPerBlock, smem), kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, top_k, thr, out, (int)ldo, sel_src, sel_w, sel_cnt);
-        else edge_topk_agg_fwd_kernel<G, true><<<grid_resident(edge_topk_agg_fwd_kernel<G, true>, n, kWarpsPerBlock, smem), kThreads, smem, st>>>(h, inv_norm, (int)n, (int)row_offset, (int)c, (int)ldh, rowptr, col, 0, thr, out, (int)ldo, nullptr, nullptr, nullptr));
-    return check_launch("sng_edge_topk_agg_fwd");
+        if (wt) { if (top_k > 0) launch_edge_fwd<G, true, false>(a, rows_long, n_long, rows_hub, n_hub, st);
+                  else launch_edge_fwd<G, true, true>(a, rows_long, n_long, rows_hub, n_hub, st); }
+        else { if (top_k > 0) launch_edge_fwd<G, false, false>(a, rows_long, n_long, rows_hub, n_hub, st);
+               else launch_edge_fwd<G, false, true>(a, rows_long, n_long, rows_hub, n_hub, st); });
+    return check_launch("sng_edge_fwd");
+}
+
+extern "C" int sng_edge_bwd(const float* h, const float* inv_norm, const float* g, int64_t n, int64_t c, int64_t ld, int64_t ldg,
+                            const int32_t* rowptr, const int32_t* col, const int32_t* tpos,
+                            const int32_t* rowptr_out, const int32_t* col_out, int64_t src_shift, int64_t num_edges,
+                            int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_q, const int32_t* sel_cnt,
+                            const float* beta, const float* diff, int64_t lddiff, float* dbeta,
+                            float* coef, float* dn_target, float* partials, float* dh, float* dwt, int64_t lddw, void* stream) {
+    if (int rc = check_rows("sng_edge_bwd", n, c, ld)) return rc;
+    SNG_REQUIRE(h && inv_norm && g && rowptr && rowptr_out && col_out && coef && dn_target && dh && ldg % 4 == 0 && ldg >= c,
+                "sng_edge_bwd: null pointer or bad ldg");
+    SNG_REQUIRE(top_k > 0 ? (sel_src && sel_w && sel_q && sel_cnt) : (col && tpos), "sng_edge_bwd: missing selection lists / CSR + tpos");
+    SNG_REQUIRE(!dwt || (beta && lddw % 4 == 0 && lddw >= c), "sng_edge_bwd: dwt needs beta and a 16-byte aligned leading dimension");
+    SNG_REQUIRE(!dbeta || (beta && diff && partials && lddiff % 4 == 0 && lddiff >= c), "sng_edge_bwd: dbeta needs beta, diff and the partials workspace");
+    SNG_REQUIRE(src_shift >= 0 && num_edges >= 0, "sng_edge_bwd: bad src_shift / num_edges");
+    if (n == 0) return SNG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (top_k > 0 && num_edges > 0 &&
+        cudaMemsetAsync(coef, 0, (size_t)num_edges * sizeof(float2), st) != cudaSuccess) return check_launch("sng_edge_bwd memset");
+    EdgeBwdArgs a;
+    a.h = h; a.inv_r = inv_norm; a.g = g; a.n_total = (int)n; a.n = (int)n; a.row_offset = 0; a.c = (int)c; a.ld = (int)ld; a.ldg = (int)ldg;
+    a.rowptr = rowptr; a.col = col; a.tpos = tpos; a.top_k = top_k > 0 ? top_k : 0;
+    a.sel_src = sel_src; a.sel_w = sel_w; a.sel_q = sel_q; a.sel_cnt = sel_cnt;
+    a.beta = beta; a.diff = dbeta ? diff : nullptr; a.lddiff = (int)lddiff; a.dbeta_part = dbeta ? partials : nullptr;
+    a.coef = reinterpret_cast<float2*>(coef); a.dnT = dn_target;
+    a.rowptr_out = rowptr_out; a.col_out = col_out; a.shift = (int)src_shift;
+    a.dh = dh; a.dwt = dwt; a.lddw = (int)lddw;
+    int grid_t = 1;
+    SNG_DISPATCH_G(c,
+        if (top_k > 0) { grid_t = grid_resident(edge_bwd_target_kernel<G, false>, n, kWarpsPerBlock); edge_bwd_target_kernel<G, false><<<grid_t, kThreads, 0, st>>>(a); }
+        else { grid_t = grid_resident(edge_bwd_target_kernel<G, true>, n, kWarpsPerBlock); edge_bwd_target_kernel<G, true><<<grid_t, kThreads, 0, st>>>(a); }
+        if (dwt) edge_bwd_source_kernel<G, true><<<grid_resident(edge_bwd_source_kernel<G, true>, n, kWarpsPerBlock), kThreads, 0, st>>>(a);
+        else edge_bwd_source_kernel<G, false><<<grid_resident(edge_bwd_source_kernel<G, false>, n, kWarpsPerBlock), kThreads, 0, st>>>(a));
+    if (dbeta) sum_partials_kernel<<<1, 256, 0, st>>>(partials, grid_t, dbeta);
+    return check_launch("sng_edge_bwd");
 }
 
 extern "C" int sng_list_agg_fwd(const float* h, int64_t n_rows, int64_t c, int64_t ldh, int list_k, const int32_t* sel_src,
@@ -696,11 +1055,14 @@ extern "C" int sng_pp_fuse_fwd(const float* wt, int64_t n, int64_t c, int64_t ld
     return check_launch("sng_pp_fuse_fwd");
 }
 
-extern "C" int sng_pp_beta_grad(const float* out0, const float* out1, const float* g, int64_t numel, float* dbeta, void* stream) {
-    SNG_REQUIRE(out0 && out1 && g && dbeta && numel >= 0 && numel % 4 == 0, "sng_pp_beta_grad: bad arguments (numel must be a multiple of 4)");
-    if (numel == 0) return SNG_OK;
-    const int grid = grid_for_rows(numel / 4, 256);
-    pp_beta_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out0, out1, g, numel, dbeta);
+extern "C" int sng_pp_beta_grad(const float* out0, const float* out1, const float* g, int64_t numel, float* dbeta, float* partials,
+                                void* stream) {
+    SNG_REQUIRE(out0 && out1 && g && dbeta && partials && numel >= 0 && numel % 4 == 0, "sng_pp_beta_grad: bad arguments (numel must be a multiple of 4)");
+    int grid = grid_for_rows(numel / 4, 256);
+    if (grid > SNG_PARTIALS) grid = SNG_PARTIALS;
+    if (numel == 0) { return cudaMemsetAsync(dbeta, 0, sizeof(float), (cudaStream_t)stream) == cudaSuccess ? SNG_OK : check_launch("sng_pp_beta_grad"); }
+    pp_beta_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out0, out1, g, numel, partials);
+    sum_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, dbeta);
     return check_launch("sng_pp_beta_grad");
 }
 

@@ -144,7 +144,16 @@ def pp_fuse_sharded(out1_local, w_weight, w_bias, beta, bias, shard, n, lo, fuse
     return _ShardedPPFuse.apply(out1_local, w_weight, w_bias, beta, bias, shard, n, lo)
 
 
+def _gather_row_blocks(local, n):
+    """[n, ld] from every rank's [hi - lo, ld] block (no autograd)."""
+    return all_gather_rows(local.contiguous(), n)
+
+
 class _ShardedPPFuse(torch.autograd.Function):
+    """Unfused SNGNN++ epilogue on a row shard (graphs whose in-lists differ from their out-lists): sng_pp_fuse_fwd over the
+    shard's by-source CSR.  dL/dW^T rows [lo, hi) need g0 of ALL rows (all-gather of g0); the row blocks of the gradient
+    are then all-gathered, so every rank ends up with the COMPLETE dL/dw.weight (no all-reduce of a zero-padded matrix)."""
+
     @staticmethod
     def forward(ctx, out1, w_weight, w_bias, beta, bias, shard, n, lo):
         import torch.nn.functional as F
@@ -152,13 +161,13 @@ class _ShardedPPFuse(torch.autograd.Function):
         out1 = SF._check_h(out1)
         nl, cp = out1.shape
         c = w_weight.size(0)
-        wt = SF._transposed_padded(w_weight, cp)                                  # [n, Cp], replicated
+        wt = SF._padded_wt(w_weight, cp)                                          # [n, Cp], replicated
         bw = F.pad(w_bias.detach(), (0, cp - c)).contiguous()
         bb = None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous()
         out0, out = torch.empty_like(out1), torch.empty_like(out1)
         if nl:
-            _C.check(_C.lib().sng_pp_fuse_fwd(_C.ptr(wt), nl, cp, cp, _C.ptr(shard.rowptr_out), _C.ptr(shard.col_out), _C.ptr(bw),
-                                              _C.ptr(beta), _C.ptr(out1), _C.ptr(bb), _C.ptr(out0), _C.ptr(out), _C.stream()), "sng_pp_fuse_fwd")
+            _C.call("sng_pp_fuse_fwd", out1, _C.ptr(wt), nl, cp, cp, _C.ptr(shard.rowptr_out), _C.ptr(shard.col_out), _C.ptr(bw),
+                    _C.ptr(beta), _C.ptr(out1), _C.ptr(bb), _C.ptr(out0), _C.ptr(out))
         ctx.shard, ctx.c, ctx.n, ctx.lo, ctx.has_bias = shard, c, n, lo, bias is not None
         ctx.save_for_backward(out0, out1, beta)
         return out
@@ -167,30 +176,81 @@ class _ShardedPPFuse(torch.autograd.Function):
     def backward(ctx, g):
         from . import _C, functional as SF
         out0, out1, beta = ctx.saved_tensors
-        shard, c, n, lo = ctx.shard, ctx.c, ctx.n, ctx.lo
+        shard, c, n = ctx.shard, ctx.c, ctx.n
         nl, cp = out1.shape
         g = g.contiguous()
         dbeta = torch.zeros(1, dtype=torch.float32, device=g.device)
         if nl:
-            _C.check(_C.lib().sng_pp_beta_grad(_C.ptr(out0), _C.ptr(out1), _C.ptr(g), g.numel(), _C.ptr(dbeta), _C.stream()), "sng_pp_beta_grad")
+            part = torch.empty(_C.PARTIALS, dtype=torch.float32, device=g.device)
+            _C.call("sng_pp_beta_grad", g, _C.ptr(out0), _C.ptr(out1), _C.ptr(g), g.numel(), _C.ptr(dbeta), _C.ptr(part))
         g0 = g * beta
-        # dL/dW^T rows [lo, hi): row t gathers g0 over the (shifted) sources of t's in-edges -- any row of g0
-        g0_all = all_gather_rows(g0.contiguous(), n)
-        dwt = g.new_zeros(n, cp)
-        if nl:
-            dwt[lo:lo + nl] = SF.spmm(g0_all.contiguous(), shard.rowptr_in, shard.col_in_shift, nl)
+        dw = _complete_dw(g0, shard, n, nl, c, cp)
         dbias = g.sum(0)[:c] if ctx.has_bias else None
-        return g - g0, dwt[:, :c].t(), g0.sum(0)[:c], dbeta, dbias, None, None, None
+        return g - g0, dw, g0.sum(0)[:c], dbeta, dbias, None, None, None
+
+
+def _complete_dw(g0, shard, n, nl, c, cp):
+    """dL/dw.weight [C, N] (complete, identical on every rank) from this shard's g0 = beta * dL/dout rows: row t of dL/dW^T
+    gathers g0 over the (shifted) sources of t's in-edges -- any row of g0, hence the all-gather."""
+    from . import functional as SF
+    g0_all = _gather_row_blocks(g0, n)
+    if nl:
+        dwt_local = SF.spmm(g0_all.contiguous(), shard.rowptr_in, shard.col_in_shift, nl)
+    else:
+        dwt_local = g0.new_zeros(0, cp)
+    dwt = _gather_row_blocks(dwt_local, n)                                        # [n, Cp]
+    return (dwt if cp == c else dwt[:, :c]).t()
+
+
+class _ShardedFusedAgg(torch.autograd.Function):
+    """SNGNN++ layer on a row shard of a SYMMETRIC graph: aggregation, structural term and beta blend in ONE pass over the
+    shard's in-edges (sng_edge_fwd with the fused epilogue; R: models/models.py:124-136).  Backward: scatter form of the
+    aggregation backward (contribution to dL/dh of every node, reduce-scattered by AllGatherRows), dL/dW^T as above."""
+
+    @staticmethod
+    def forward(ctx, h_all, w_weight, w_bias, beta, bias, shard, n, lo, top_k, thr):
+        import torch.nn.functional as F
+        from . import functional as SF
+        h_all = SF._check_h(h_all)
+        cp = h_all.size(1)
+        c = w_weight.size(0)
+        fuse = (SF._padded_wt(w_weight, cp), F.pad(w_bias.detach(), (0, cp - c)).contiguous(), beta.detach().contiguous(),
+                None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous())
+        train = any(ctx.needs_input_grad)
+        out, sel_src, sel_w, _, sel_cnt, inv_norm, diff = SF._edge_fwd(h_all, shard, lo, int(top_k), thr, train, fuse)
+        ctx.shard, ctx.c, ctx.n, ctx.lo, ctx.k, ctx.has_bias = shard, c, n, lo, int(top_k), bias is not None
+        ctx.save_for_backward(h_all, sel_src, sel_w, sel_cnt, inv_norm, diff, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _C
+        h_all, sel_src, sel_w, sel_cnt, inv_norm, diff, beta = ctx.saved_tensors
+        shard, c, n, k = ctx.shard, ctx.c, ctx.n, ctx.k
+        n_total, cp = h_all.shape
+        nl = shard.n
+        g = g.contiguous()
+        g0 = g * beta
+        g1 = (g - g0).contiguous()
+        dval, dnrm, dh = torch.zeros_like(h_all), torch.zeros_like(h_all), torch.empty_like(h_all)
+        _C.call("sng_edge_agg_bwd", h_all, _C.ptr(h_all), _C.ptr(inv_norm), _C.ptr(g1), n_total, nl, ctx.lo, cp, cp,
+                _C.ptr(shard.rowptr_in), _C.ptr(shard.col_in), k, _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt),
+                _C.ptr(shard.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh))
+        dbeta = (diff * g).sum().reshape(1)
+        dw = _complete_dw(g0, shard, n, nl, c, cp)
+        dbias = g.sum(0)[:c] if ctx.has_bias else None
+        return dh, dw, g0.sum(0)[:c], dbeta, dbias, None, None, None, None, None
 
 
 def allreduce_grads(params):
     """Sum the (partial, per-shard) parameter gradients over ranks: every parameter is replicated, every rank holds the
-    gradient contribution of its own rows."""
+    gradient contribution of its own rows.  Structural weights whose gradient the sharded backward already assembled on
+    every rank (row blocks all-gathered, see _complete_dw) are skipped."""
     ws, _ = world()
     if ws == 1:
         return
     for p in params:
-        if p.grad is not None:
+        if p.grad is not None and not getattr(p, "_sng_grad_complete", False):
             dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
 
 
@@ -198,7 +258,8 @@ def sharded_forward(model, x_local, edge_index, n, agg=None, fuse=None):
     """Row-sharded forward of an SNGNN / SNGNN_Plus / SNGNN_Plus_Plus model (replicated parameters): this rank holds the
     feature rows [lo, hi) and returns the log-probabilities of those rows.  Mirrors _SNStack.forward / the conv forwards of
     models.py (R: models/models.py:76-86,116-137,233-242,322-329) with the aggregation and the ++ fusion replaced by their
-    sharded forms.  BatchNorm needs statistics over all nodes and is not supported here (the reference default is bn=False)."""
+    sharded forms.  BatchNorm needs statistics over all nodes and is not supported here (the reference default is bn=False);
+    neither are the non-reference options candidates='all_pairs' / denominator='selected'."""
     import torch.nn.functional as F
     from . import graph as G, models as M
     if getattr(model, "bn", False):
@@ -210,16 +271,29 @@ def sharded_forward(model, x_local, edge_index, n, agg=None, fuse=None):
     for i, conv in enumerate(convs):
         base = type(conv) is M.SNConv
         plus_plus = isinstance(conv, M.SNConv_plus_plus)
+        if not base and (conv.candidates != "edges" or conv.denominator != "candidates"):
+            raise NotImplementedError("sharded_forward supports candidates='edges', denominator='candidates' only")
+        if not base and conv.top_k <= 0:
+            raise NotImplementedError("sharded_forward: top_k <= 0")
         g = G.prepare(edge_index, n, remove_self_loops=False if base else bool(conv.is_remove_self_loops), structural=plus_plus)
         h = conv._hidden(x)
-        out, shard = edge_agg_sharded(h, g, None if base else conv.top_k, None if base else conv.thr, agg=agg)
+        injected = agg is not None or fuse is not None
         if plus_plus:
-            out = pp_fuse_sharded(out, conv.w.weight, conv.w.bias, conv.beta, conv.bias, shard, n, lo, fuse=fuse)
+            conv.w.weight._sng_grad_complete = not injected      # the CUDA backward assembles the complete gradient itself
+        if plus_plus and not injected and g.symmetric:
+            h_all = AllGatherRows.apply(h, n)
+            out = _ShardedFusedAgg.apply(h_all, conv.w.weight, conv.w.bias, conv.beta, conv.bias, g.row_slice(lo, hi), n, lo,
+                                         conv.top_k, conv.thr)
             out = out[:, :conv.lin.out_features]
         else:
-            out = out[:, :conv.lin.out_features]
-            if conv.bias is not None:
-                out = out + conv.bias
+            out, shard = edge_agg_sharded(h, g, None if base else conv.top_k, None if base else conv.thr, agg=agg)
+            if plus_plus:
+                out = pp_fuse_sharded(out, conv.w.weight, conv.w.bias, conv.beta, conv.bias, shard, n, lo, fuse=fuse)
+                out = out[:, :conv.lin.out_features]
+            else:
+                out = out[:, :conv.lin.out_features]
+                if conv.bias is not None:
+                    out = out + conv.bias
         if i < len(convs) - 1:
             out = model.dropout(F.relu(out))
         x = out

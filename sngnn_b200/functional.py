@@ -4,8 +4,6 @@ dense `lin` GEMM only; every sparse / selection / aggregation step is a libsng.s
 Channel padding: the edge kernels want 16-byte feature rows, so the layer output width C is padded to
 Cp = 4*ceil(C/4) by zero-padding the `lin` weights (zero columns change neither norms nor dot products).
 """
-import weakref
-
 import torch
 import torch.nn.functional as F
 
@@ -32,69 +30,125 @@ def _check_h(h):
     return h.contiguous()
 
 
-class EdgeTopkAgg(torch.autograd.Function):
-    """out_1 of R: models/models.py:132 / :239 / :326 -- K2 forward, K2b backward."""
+def _edge_fwd(h_all, graph, row_offset, k, thr, train, fuse=None, want_q=False):
+    """sng_edge_fwd on the target rows of `graph` (a PreparedGraph or a row shard of one).  fuse = (wt [N, Cp], b_w [Cp],
+    beta [1], bias [Cp] | None) gathers the structural term and blends in the same pass (symmetric graphs only)."""
+    c = h_all.size(1)
+    n = graph.n
+    dev = h_all.device
+    out = torch.empty(n, c, dtype=torch.float32, device=dev)
+    sel_src = sel_w = sel_cnt = sel_q = diff = None
+    if train and k > 0:
+        sel_src = torch.empty(n, k, dtype=torch.int32, device=dev)
+        sel_w = torch.empty(n, k, dtype=torch.float32, device=dev)
+        sel_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        if want_q:
+            sel_q = torch.empty(n, k, dtype=torch.int32, device=dev)
+    inv_norm = torch.empty(h_all.size(0), dtype=torch.float32, device=dev)
+    wt = bw = beta = bias = None
+    if fuse is not None:
+        wt, bw, beta, bias = fuse
+        if train:
+            diff = torch.empty_like(out)
+    rows_long, n_long, rows_hub, n_hub = graph.degree_lists()
+    _C.call("sng_edge_fwd", h_all, _C.ptr(h_all), h_all.size(0), n, row_offset, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in),
+            _C.ptr(graph.tpos if want_q else None), _C.ptr(rows_long), n_long, _C.ptr(rows_hub), n_hub, k,
+            float(thr if thr is not None else 0.0), _C.ptr(out), c, _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_q), _C.ptr(sel_cnt),
+            _C.ptr(inv_norm), _C.ptr(wt), c, _C.ptr(bw), _C.ptr(beta), _C.ptr(bias), _C.ptr(diff))
+    return out, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff
+
+
+def _padded_wt(w_weight, cp):
+    """W^T [N, Cp] of the structural weight [C, N].  The modules keep that parameter in transposed storage
+    (models.SNConv_plus_plus), so this is a view of the parameter itself when C is a multiple of 4, and a small padded copy
+    otherwise; a parameter in plain [C, N] storage costs a transpose copy per call.  Nothing is cached."""
+    c = w_weight.size(0)
+    wt = w_weight.detach().t()
+    if cp != c:
+        wt = F.pad(wt, (0, cp - c))
+    return wt.contiguous()
+
+
+class EdgeAgg(torch.autograd.Function):
+    """The similarity-navigated aggregation of one layer: out_1 of R: models/models.py:132 / :239 / :326 and -- when the
+    structural parameters are given and the graph's in-lists equal its out-lists -- the whole of
+    R: models/models.py:124-136 (out = beta (A W^T + b_w) + (1 - beta) out_1 + bias) in the same pass over the edges.
+    Forward sng_edge_fwd, backward sng_edge_bwd (two gather passes, no float atomics, bit-reproducible)."""
 
     @staticmethod
-    def forward(ctx, h, graph, top_k, thr):
+    def forward(ctx, h, graph, top_k, thr, w_weight, w_bias, beta, bias):
         h = _check_h(h)
-        n, c = h.shape
+        n, cp = h.shape
         if n != graph.n:
             raise RuntimeError(f"h has {n} rows but the graph has {graph.n} nodes")
-        out = torch.empty_like(h)
         k = int(top_k) if top_k is not None else 0
-        if k > 0:
-            sel_src = torch.empty(n, k, dtype=torch.int32, device=h.device)
-            sel_w = torch.empty(n, k, dtype=torch.float32, device=h.device)
-            sel_cnt = torch.empty(n, dtype=torch.int32, device=h.device)
-        else:
-            sel_src = sel_w = sel_cnt = None
-        inv_norm = torch.empty(n, dtype=torch.float32, device=h.device)
-        _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h), n, n, 0, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
-                                                float(thr if thr is not None else 0.0), _C.ptr(out), c,
-                                                _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(inv_norm), _C.stream()),
-                 "sng_edge_topk_agg_fwd")
-        ctx.graph, ctx.k = graph, k
-        ctx.save_for_backward(h, sel_src, sel_w, sel_cnt, inv_norm)
-        ctx.mark_non_differentiable(*[t for t in (sel_src, sel_w, sel_cnt) if t is not None])
-        if k > 0:
-            return out, sel_src, sel_w, sel_cnt
-        return out, None, None, None
+        fused = w_weight is not None
+        train = any(ctx.needs_input_grad)
+        fuse = None
+        if fused:
+            _C.require_cuda(h, w_weight, w_bias, beta, bias)
+            c = w_weight.size(0)
+            if w_weight.size(1) != n:
+                raise RuntimeError(f"w.weight is [{c},{w_weight.size(1)}] but the graph has {n} nodes "
+                                   "(R builds w = Linear(num_nodes, out_channels), models.py:95)")
+            if not graph.symmetric:
+                raise RuntimeError("the fused SNGNN++ pass needs a graph whose in-lists equal its out-lists")
+            fuse = (_padded_wt(w_weight, cp), F.pad(w_bias.detach(), (0, cp - c)).contiguous(), beta.detach().contiguous(),
+                    None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous())
+            ctx.c = c
+        out, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff = _edge_fwd(h, graph, 0, k, thr, train, fuse, want_q=True)
+        ctx.graph, ctx.k, ctx.fused, ctx.has_bias = graph, k, fused, bias is not None
+        ctx.save_for_backward(h, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff, beta if fused else None)
+        if sel_cnt is not None:
+            ctx.mark_non_differentiable(sel_src, sel_w, sel_cnt)
+        return out, sel_src, sel_w, sel_cnt
 
     @staticmethod
     def backward(ctx, g, *_):
-        h, sel_src, sel_w, sel_cnt, inv_norm = ctx.saved_tensors
-        graph, k = ctx.graph, ctx.k
-        n, c = h.shape
+        h, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff, beta = ctx.saved_tensors
+        graph, k, fused = ctx.graph, ctx.k, ctx.fused
+        n, cp = h.shape
+        dev = h.device
         g = g.contiguous()
-        dval = torch.zeros_like(h)
-        dnrm = torch.zeros_like(h)
+        coef = torch.empty(max(graph.num_edges, 1) * 2, dtype=torch.float32, device=dev)
+        dnt = torch.empty_like(h)
         dh = torch.empty_like(h)
-        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, n, 0, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in), k,
-                                           _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(graph.inv_deg),
-                                           _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
-                 "sng_edge_agg_bwd")
-        return dh, None, None, None
+        dbeta = dwt = part = None
+        if fused:
+            dbeta = torch.empty(1, dtype=torch.float32, device=dev)
+            part = torch.empty(_C.PARTIALS, dtype=torch.float32, device=dev)
+            dwt = torch.empty(n, cp, dtype=torch.float32, device=dev)
+        _C.call("sng_edge_bwd", h, _C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, cp, cp, cp, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in),
+                _C.ptr(graph.tpos), _C.ptr(graph.rowptr_out), _C.ptr(graph.col_out), graph.src_shift, graph.num_edges, k,
+                _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_q), _C.ptr(sel_cnt), _C.ptr(beta if fused else None),
+                _C.ptr(diff), cp, _C.ptr(dbeta), _C.ptr(coef), _C.ptr(dnt), _C.ptr(part), _C.ptr(dh), _C.ptr(dwt), cp)
+        if not fused:
+            return dh, None, None, None, None, None, None, None
+        c = ctx.c
+        gsum = g.sum(0)[:c]
+        dw = (dwt if cp == c else dwt[:, :c]).t()           # [C, N] in the parameter's own (transposed) layout
+        return dh, None, None, None, dw, gsum * beta, dbeta, (gsum if ctx.has_bias else None)
 
 
 def edge_topk_agg_rows(h_all, shard, row_offset, top_k=None, thr=None):
     """Forward-only K2 on a row shard: targets [row_offset, row_offset + shard.n) of `h_all` (all nodes, e.g. after an
     all-gather), `shard` = PreparedGraph.row_slice(lo, hi).  Returns (out [shard.n, C], sel_src, sel_w, sel_cnt)."""
     h_all = _check_h(h_all)
-    out, sel_src, sel_w, sel_cnt, _ = _edge_fwd_rows(h_all, shard, int(row_offset), int(top_k) if top_k is not None else 0, thr)
+    out, sel_src, sel_w, _, sel_cnt, _, _ = _edge_fwd(h_all, shard, int(row_offset), int(top_k) if top_k is not None else 0, thr, True)
     return out, sel_src, sel_w, sel_cnt
 
 
 class ShardedEdgeTopkAgg(torch.autograd.Function):
     """K2 / K2b on a ROW SHARD: forward computes out_1 for target rows [row_offset, row_offset + shard.n) from `h_all` (all
     nodes); backward returns this shard's contribution to dL/dh_all [N, C] -- contributions of different shards add
-    (the caller reduce-scatters them, see dist.AllGatherRows)."""
+    (the caller reduce-scatters them, see dist.AllGatherRows).  A shard has no transpose index, so its
+    backward is the scatter form (sng_edge_agg_bwd)."""
 
     @staticmethod
     def forward(ctx, h_all, shard, row_offset, top_k, thr):
         h_all = _check_h(h_all)
         k = int(top_k) if top_k is not None else 0
-        out, sel_src, sel_w, sel_cnt, inv_norm = _edge_fwd_rows(h_all, shard, int(row_offset), k, thr)
+        out, sel_src, sel_w, _, sel_cnt, inv_norm, _ = _edge_fwd(h_all, shard, int(row_offset), k, thr, ctx.needs_input_grad[0])
         ctx.shard, ctx.k, ctx.row_offset = shard, k, int(row_offset)
         ctx.save_for_backward(h_all, sel_src, sel_w, sel_cnt, inv_norm)
         return out
@@ -106,30 +160,16 @@ class ShardedEdgeTopkAgg(torch.autograd.Function):
         n_total, c = h_all.shape
         g = g.contiguous()
         dval, dnrm, dh = torch.zeros_like(h_all), torch.zeros_like(h_all), torch.empty_like(h_all)
-        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h_all), _C.ptr(inv_norm), _C.ptr(g), n_total, shard.n, ctx.row_offset, c, c,
-                                           _C.ptr(shard.rowptr_in), _C.ptr(shard.col_in), k, _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt),
-                                           _C.ptr(shard.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()), "sng_edge_agg_bwd")
+        _C.call("sng_edge_agg_bwd", h_all, _C.ptr(h_all), _C.ptr(inv_norm), _C.ptr(g), n_total, shard.n, ctx.row_offset, c, c,
+                _C.ptr(shard.rowptr_in), _C.ptr(shard.col_in), k, _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt),
+                _C.ptr(shard.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh))
         return dh, None, None, None, None
 
 
-def _edge_fwd_rows(h_all, shard, row_offset, k, thr):
-    c = h_all.size(1)
-    n = shard.n
-    dev = h_all.device
-    out = torch.empty(n, c, dtype=h_all.dtype, device=dev)
-    sel_src = torch.empty(n, max(k, 1), dtype=torch.int32, device=dev) if k > 0 else None
-    sel_w = torch.empty(n, max(k, 1), dtype=torch.float32, device=dev) if k > 0 else None
-    sel_cnt = torch.empty(n, dtype=torch.int32, device=dev) if k > 0 else None
-    inv_norm = torch.empty(h_all.size(0), dtype=torch.float32, device=dev)
-    _C.check(_C.lib().sng_edge_topk_agg_fwd(_C.ptr(h_all), h_all.size(0), n, row_offset, c, c, _C.ptr(shard.rowptr_in),
-                                            _C.ptr(shard.col_in), k, float(thr if thr is not None else 0.0), _C.ptr(out), c,
-                                            _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt), _C.ptr(inv_norm), _C.stream()),
-             "sng_edge_topk_agg_fwd")
-    return out, sel_src, sel_w, sel_cnt, inv_norm
-
-
-def edge_topk_agg(h, graph, top_k=None, thr=None, return_selection=False):
-    out, sel_src, sel_w, sel_cnt = EdgeTopkAgg.apply(h, graph, top_k, thr)
+def edge_topk_agg(h, graph, top_k=None, thr=None, return_selection=False, structural=None):
+    """out_1 (structural=None) or the fused SNGNN++ layer output (structural = (w.weight, w.bias, beta, bias))."""
+    w_weight, w_bias, beta, bias = structural if structural is not None else (None, None, None, None)
+    out, sel_src, sel_w, sel_cnt = EdgeAgg.apply(h, graph, top_k, thr, w_weight, w_bias, beta, bias)
     if return_selection:
         return out, (sel_src, sel_w, sel_cnt)
     return out
@@ -143,8 +183,8 @@ class ListAgg(torch.autograd.Function):
         h = _check_h(h)
         n, c = h.shape
         out = torch.empty(idx.size(0), c, dtype=h.dtype, device=h.device)
-        _C.check(_C.lib().sng_list_agg_fwd(_C.ptr(h), idx.size(0), c, c, idx.size(1), _C.ptr(idx), _C.ptr(sim), _C.ptr(cnt),
-                                           _C.ptr(inv_denom), _C.ptr(out), c, _C.stream()), "sng_list_agg_fwd")
+        _C.call("sng_list_agg_fwd", h, _C.ptr(h), idx.size(0), c, c, idx.size(1), _C.ptr(idx), _C.ptr(sim), _C.ptr(cnt),
+                _C.ptr(inv_denom), _C.ptr(out), c)
         ctx.save_for_backward(h, idx, sim, cnt, inv_denom)
         return out
 
@@ -157,9 +197,8 @@ class ListAgg(torch.autograd.Function):
         g = g.contiguous()
         dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
         _, _, inv_norm = rownorm(h, want_f32=False, want_inv=True)
-        _C.check(_C.lib().sng_edge_agg_bwd(_C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, n, 0, c, c, None, None, idx.size(1), _C.ptr(idx), _C.ptr(sim),
-                                           _C.ptr(cnt), _C.ptr(inv_denom), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh), _C.stream()),
-                 "sng_edge_agg_bwd")
+        _C.call("sng_edge_agg_bwd", h, _C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, n, 0, c, c, None, None, idx.size(1), _C.ptr(idx), _C.ptr(sim),
+                _C.ptr(cnt), _C.ptr(inv_denom), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh))
         return dh, None, None, None, None
 
 
@@ -168,28 +207,9 @@ def spmm(x, rowptr, col, n_rows, val=None, rowscale=None, bias=None):
     x = _check_h(x)
     c = x.size(1)
     out = torch.empty(n_rows, c, dtype=x.dtype, device=x.device)
-    _C.check(_C.lib().sng_spmm_fwd(_C.ptr(x), n_rows, c, c, _C.ptr(rowptr), _C.ptr(col), _C.ptr(val), _C.ptr(rowscale),
-                                   _C.ptr(bias), _C.ptr(out), c, _C.stream()), "sng_spmm_fwd")
+    _C.call("sng_spmm_fwd", x, _C.ptr(x), n_rows, c, c, _C.ptr(rowptr), _C.ptr(col), _C.ptr(val), _C.ptr(rowscale),
+            _C.ptr(bias), _C.ptr(out), c)
     return out
-
-
-_WT_CACHE = {}
-
-
-def _transposed_padded(w_weight, cp):
-    """W^T [N, Cp] (zero-padded channels) of the structural weight [C, N].  The transpose is a full copy of the parameter
-    (209 MB at pokec size), so it is kept until the parameter changes: the two evaluation forwards of an epoch reuse it."""
-    key = (id(w_weight), cp)
-    hit = _WT_CACHE.get(key)
-    # same tensor OBJECT (a freed parameter's address and version can be reused by the next model), unchanged since
-    if hit is not None and hit[0]() is w_weight and hit[1] == (w_weight._version, w_weight.data_ptr()):
-        return hit[2]
-    c = w_weight.size(0)
-    wt = F.pad(w_weight.detach(), (0, 0, 0, cp - c)).t().contiguous()
-    if len(_WT_CACHE) >= 8:
-        _WT_CACHE.pop(next(iter(_WT_CACHE)))
-    _WT_CACHE[key] = (weakref.ref(w_weight), (w_weight._version, w_weight.data_ptr()), wt)
-    return wt
 
 
 class PPFuse(torch.autograd.Function):
@@ -203,14 +223,13 @@ class PPFuse(torch.autograd.Function):
         if w_weight.size(1) != n:
             raise RuntimeError(f"w.weight is [{c},{w_weight.size(1)}] but the graph has {n} nodes "
                                "(R builds w = Linear(num_nodes, out_channels), models.py:95)")
-        wt = _transposed_padded(w_weight, cp)                                     # [N, Cp]
+        wt = _padded_wt(w_weight, cp)                                             # [N, Cp]
         bw = F.pad(w_bias.detach(), (0, cp - c)).contiguous()
         bb = None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous()
         out0 = torch.empty_like(out1)
         out = torch.empty_like(out1)
-        _C.check(_C.lib().sng_pp_fuse_fwd(_C.ptr(wt), n, cp, cp, _C.ptr(graph.rowptr_out), _C.ptr(graph.col_out), _C.ptr(bw),
-                                          _C.ptr(beta), _C.ptr(out1), _C.ptr(bb), _C.ptr(out0), _C.ptr(out), _C.stream()),
-                 "sng_pp_fuse_fwd")
+        _C.call("sng_pp_fuse_fwd", out1, _C.ptr(wt), n, cp, cp, _C.ptr(graph.rowptr_out), _C.ptr(graph.col_out), _C.ptr(bw),
+                _C.ptr(beta), _C.ptr(out1), _C.ptr(bb), _C.ptr(out0), _C.ptr(out))
         ctx.graph, ctx.c, ctx.has_bias = graph, c, bias is not None
         ctx.save_for_backward(out0, out1, beta)
         return out
@@ -221,9 +240,9 @@ class PPFuse(torch.autograd.Function):
         graph, c = ctx.graph, ctx.c
         n, cp = out1.shape
         g = g.contiguous()
-        dbeta = torch.zeros(1, dtype=torch.float32, device=g.device)
-        _C.check(_C.lib().sng_pp_beta_grad(_C.ptr(out0), _C.ptr(out1), _C.ptr(g), g.numel(), _C.ptr(dbeta), _C.stream()),
-                 "sng_pp_beta_grad")
+        dbeta = torch.empty(1, dtype=torch.float32, device=g.device)
+        part = torch.empty(_C.PARTIALS, dtype=torch.float32, device=g.device)
+        _C.call("sng_pp_beta_grad", g, _C.ptr(out0), _C.ptr(out1), _C.ptr(g), g.numel(), _C.ptr(dbeta), _C.ptr(part))
         g0 = g * beta
         dout1 = g - g0
         # dL/dW^T = A^T g0: row t gathers g0 over the (shifted) sources of t's in-edges
@@ -243,8 +262,7 @@ def rownorm(x, want_f32=True, want_f16=False, f16_ld=None, want_inv=False):
     ldh = f16_ld or (d + 15) // 16 * 16
     xh = torch.empty(n, ldh, dtype=torch.float16, device=x.device) if want_f16 else None
     inv = torch.empty(n, dtype=torch.float32, device=x.device) if want_inv else None
-    _C.check(_C.lib().sng_rownorm_f32(_C.ptr(x), n, d, d, _C.ptr(xf), d, _C.ptr(xh), ldh, _C.ptr(inv), _C.stream()),
-             "sng_rownorm_f32")
+    _C.call("sng_rownorm_f32", x, _C.ptr(x), n, d, d, _C.ptr(xf), d, _C.ptr(xh), ldh, _C.ptr(inv))
     return xf, xh, inv
 
 
@@ -255,6 +273,5 @@ def sddmm_dot(xhat, a, b):
     a = a.to(torch.int32).contiguous()
     b = b.to(torch.int32).contiguous()
     s = torch.empty(a.numel(), dtype=torch.float32, device=xhat.device)
-    _C.check(_C.lib().sng_sddmm_dot(_C.ptr(xhat), xhat.size(0), xhat.size(1), xhat.size(1), _C.ptr(a), _C.ptr(b), a.numel(),
-                                    _C.ptr(s), _C.stream()), "sng_sddmm_dot")
+    _C.call("sng_sddmm_dot", xhat, _C.ptr(xhat), xhat.size(0), xhat.size(1), xhat.size(1), _C.ptr(a), _C.ptr(b), a.numel(), _C.ptr(s))
     return s

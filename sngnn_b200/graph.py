@@ -10,6 +10,12 @@ int32 CSR arrays the kernels consume:
     the contract;  `inv_deg[i] = 1 / max(indeg(i), 1)` is the PyG aggr='mean' denominator.
   * CSR by SHIFTED SOURCE (`rowptr_out`, `col_out`): out-neighbours t of node (src - min src), for
     out_0 = A @ W^T (R: :124-130);  `col_in_shift = col_in - min(src)` serves its transpose in backward.
+  * `tpos[p]` = position of by-target edge p in the by-source arrays: the transpose index that lets the backward of the
+    aggregation run as two gather passes without float atomics (sng_edge_bwd).
+  * `rows_long` / `rows_hub`: target rows with 32 < in-degree <= 1024 / > 1024 (the forward's degree dispatch), and
+    `symmetric`: every in-list equals the out-list with min(src) == 0, which lets SNGNN++ gather W^T rows in the same pass.
+The by-source arrays are always built (the deterministic backward of every model needs them), `structural` is kept for
+API compatibility.
 
 CUDA `edge_index`: one call of `sng_graph_prepare` (stable radix sort by target / source, include/sng.h).  CPU tensors
 (the host-logic and gloo tests): the same construction in torch, with a stable argsort.
@@ -24,7 +30,13 @@ _CACHE_MAX = 8
 
 class PreparedGraph:
     __slots__ = ("n", "num_edges", "rowptr_in", "col_in", "inv_deg", "src_shift", "rowptr_out", "col_out",
-                 "col_in_shift", "dst_sorted", "_shards")
+                 "col_in_shift", "dst_sorted", "_shards", "tpos", "rows_long", "rows_hub", "symmetric", "max_deg", "is_shard")
+
+    def degree_lists(self):
+        """(rows_long, n_long, rows_hub, n_hub) for sng_edge_fwd; n_long = -1 when the lists are unknown."""
+        if self.rows_long is None:
+            return None, -1, None, 0
+        return self.rows_long, int(self.rows_long.numel()), self.rows_hub, int(self.rows_hub.numel())
 
     def row_slice(self, lo, hi):
         """Row-sharded view (targets [lo, hi)) for multi-GPU aggregation: rowptr rebased to 0.  Cached per (lo, hi)."""
@@ -42,7 +54,13 @@ class PreparedGraph:
         g.inv_deg = self.inv_deg[lo:hi].contiguous()
         g.src_shift = self.src_shift
         g.col_in_shift = None if self.col_in_shift is None else self.col_in_shift[b:e].contiguous()
-        g.rowptr_out = g.col_out = g.dst_sorted = None
+        g.rowptr_out = g.col_out = g.dst_sorted = g.tpos = None      # no transpose index for a shard: its backward scatters
+        g.symmetric, g.max_deg, g.is_shard = False, self.max_deg, True
+        g.rows_long = g.rows_hub = None
+        if self.rows_long is not None:                       # shard-local degree lists
+            for name in ("rows_long", "rows_hub"):
+                r = getattr(self, name)
+                setattr(g, name, (r[(r >= lo) & (r < hi)] - lo).contiguous())
         if self.rowptr_out is not None:                      # by-(shifted-)source CSR rows [lo, hi) for out_0 = A @ W^T
             bo, eo = int(self.rowptr_out[lo]), int(self.rowptr_out[hi])
             g.rowptr_out = (self.rowptr_out[lo:hi + 1] - bo).contiguous()
@@ -72,19 +90,21 @@ def prepare(edge_index, num_nodes, remove_self_loops, structural=False, processe
     """Build (or fetch from cache) the PreparedGraph of `edge_index` [2,E] int64.
 
     remove_self_loops: False for base SNConv (R: :323), the `is_remove_self_loops` flag otherwise.
-    structural: also build the by-source CSR needed by SNConv_plus_plus.
+    structural: ignored (the by-source CSR is always built; kept for API compatibility).
+    The cache is keyed on the tensor object, its storage address and `_version`; writes that bypass the version counter
+    (`edge_index.data[...] = ...`) are not seen -- call `clear_cache()` after such an edit.
     processed: `edge_index` already went through `process_edges` (used by tests)."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, str(edge_index.device),
            int(num_nodes), bool(remove_self_loops), bool(processed))
     hit = _CACHE.get(key)
-    if hit is not None and hit[0]() is edge_index and (not structural or hit[1].rowptr_out is not None):
+    if hit is not None and hit[0]() is edge_index:
         return hit[1]
     if edge_index.numel() and int(edge_index.max()) >= num_nodes:
         raise ValueError("edge_index refers to a node id >= num_nodes")
     if num_nodes >= 2 ** 31 or edge_index.size(1) + num_nodes >= 2 ** 31:
         raise ValueError("graph too large for int32 CSR")
     if edge_index.is_cuda and not processed:
-        g = _prepare_cuda(edge_index, int(num_nodes), bool(remove_self_loops), bool(structural))
+        g = _prepare_cuda(edge_index, int(num_nodes), bool(remove_self_loops))
         if len(_CACHE) >= _CACHE_MAX:
             _CACHE.pop(next(iter(_CACHE)))
         _CACHE[key] = (weakref.ref(edge_index), g)
@@ -94,24 +114,29 @@ def prepare(edge_index, num_nodes, remove_self_loops, structural=False, processe
     g = PreparedGraph()
     g.n = int(num_nodes)
     g.num_edges = int(src.numel())
-    g.rowptr_in, col_in, _ = _csr_from_keys(dst, src, g.n)
+    g.rowptr_in, col_in, perm_in = _csr_from_keys(dst, src, g.n)
     g.col_in = col_in.to(torch.int32).contiguous()
-    deg = (g.rowptr_in[1:] - g.rowptr_in[:-1]).to(torch.float32)
-    g.inv_deg = (1.0 / deg.clamp(min=1)).contiguous()
-    g.src_shift = 0
-    g.rowptr_out = g.col_out = g.col_in_shift = g.dst_sorted = None
-    if structural:
-        g.src_shift = int(src.min()) if src.numel() else 0            # R: models/models.py:125
-        g.rowptr_out, col_out, _ = _csr_from_keys(src - g.src_shift, dst, g.n)
-        g.col_out = col_out.to(torch.int32).contiguous()
-        g.col_in_shift = (g.col_in - g.src_shift).contiguous()
+    deg = (g.rowptr_in[1:] - g.rowptr_in[:-1])
+    g.inv_deg = (1.0 / deg.to(torch.float32).clamp(min=1)).contiguous()
+    g.dst_sorted, g.is_shard = None, False
+    g.src_shift = int(src.min()) if src.numel() else 0                # R: models/models.py:125
+    g.rowptr_out, col_out, perm_out = _csr_from_keys(src - g.src_shift, dst, g.n)
+    g.col_out = col_out.to(torch.int32).contiguous()
+    g.col_in_shift = (g.col_in - g.src_shift).contiguous()
+    inv_out = torch.empty_like(perm_out)
+    inv_out[perm_out] = torch.arange(perm_out.numel(), device=perm_out.device)
+    g.tpos = inv_out[perm_in].to(torch.int32).contiguous()
+    g.rows_long = ((deg > 32) & (deg <= 1024)).nonzero().flatten().to(torch.int32)
+    g.rows_hub = (deg > 1024).nonzero().flatten().to(torch.int32)
+    g.max_deg = int(deg.max()) if g.n else 0
+    g.symmetric = bool(g.src_shift == 0 and torch.equal(g.rowptr_in, g.rowptr_out) and torch.equal(g.col_in, g.col_out))
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = (weakref.ref(edge_index), g)
     return g
 
 
-def _prepare_cuda(edge_index, n, remove_self_loops, structural):
+def _prepare_cuda(edge_index, n, remove_self_loops):
     from . import _C
     lib = _C.lib()
     ei = edge_index.contiguous()
@@ -122,27 +147,28 @@ def _prepare_cuda(edge_index, n, remove_self_loops, structural):
     cap = e + n
     g = PreparedGraph()
     g.n = n
-    rowptr_in = torch.empty(n + 1, dtype=torch.int32, device=dev)
-    col_in = torch.empty(cap, dtype=torch.int32, device=dev)
+
+    def i32(m):
+        return torch.empty(m, dtype=torch.int32, device=dev)
+
+    rowptr_in, col_in, rowptr_out, col_out, col_in_shift, tpos, long_rows = i32(n + 1), i32(cap), i32(n + 1), i32(cap), i32(cap), i32(cap), i32(n)
     g.inv_deg = torch.empty(n, dtype=torch.float32, device=dev)
-    rowptr_out = torch.empty(n + 1, dtype=torch.int32, device=dev) if structural else None
-    col_out = torch.empty(cap, dtype=torch.int32, device=dev) if structural else None
-    col_in_shift = torch.empty(cap, dtype=torch.int32, device=dev) if structural else None
-    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    info = torch.zeros(8, dtype=torch.int32, device=dev)
     wbytes = lib.sng_graph_prepare_workspace_bytes(e, n)
     if wbytes == 0:
         raise ValueError("graph too large for int32 CSR")
     ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-    _C.check(lib.sng_graph_prepare(_C.ptr(ei), e, n, int(remove_self_loops), int(structural), _C.ptr(rowptr_in), _C.ptr(col_in),
-                                   _C.ptr(g.inv_deg), _C.ptr(rowptr_out), _C.ptr(col_out), _C.ptr(col_in_shift), _C.ptr(info),
-                                   _C.ptr(ws), wbytes, _C.stream()), "sng_graph_prepare")
-    kept, shift = (int(v) for v in info.tolist())               # one sync: the arrays are narrowed to the kept edges
+    _C.call("sng_graph_prepare", ei, _C.ptr(ei), e, n, int(remove_self_loops), 1, _C.ptr(rowptr_in), _C.ptr(col_in),
+            _C.ptr(g.inv_deg), _C.ptr(rowptr_out), _C.ptr(col_out), _C.ptr(col_in_shift), _C.ptr(tpos), _C.ptr(long_rows), _C.ptr(info),
+            _C.ptr(ws), wbytes)
+    kept, shift, sym, n_long, n_hub, max_deg = (int(v) for v in info.tolist()[:6])   # one sync: the arrays are narrowed to the kept edges
     g.num_edges = kept
     g.rowptr_in, g.col_in = rowptr_in, col_in[:kept]
-    g.src_shift = shift if structural else 0
-    g.rowptr_out = rowptr_out
-    g.col_out = col_out[:kept] if structural else None
-    g.col_in_shift = col_in_shift[:kept] if structural else None
+    g.src_shift = shift
+    g.rowptr_out, g.col_out, g.col_in_shift, g.tpos = rowptr_out, col_out[:kept], col_in_shift[:kept], tpos[:kept]
+    g.rows_long = long_rows[:n_long].clone()
+    g.rows_hub = long_rows[n - n_hub:].clone() if n_hub else long_rows[:0].clone()
+    g.symmetric, g.max_deg, g.is_shard = sym != 0, max_deg, False
     g.dst_sorted = None
     return g
 

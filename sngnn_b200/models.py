@@ -85,25 +85,33 @@ class SNConv_plus(_SNConvBase):
         self.lin.reset_parameters()
         self._zero_bias()
 
-    def _aggregate(self, h, edge_index, structural):
-        n = h.size(0)
-        g = G.prepare(edge_index, n, remove_self_loops=bool(self.is_remove_self_loops), structural=structural)
+    def _check_options(self):
+        if self.candidates not in ("edges", "all_pairs"):
+            raise ValueError(f"candidates={self.candidates!r}")
+        if self.denominator not in ("candidates", "selected"):
+            raise ValueError(f"denominator={self.denominator!r}")
+
+    def _aggregate(self, h, g):
+        """out_1 of R: models/models.py:239 / :132.  top_k <= 0: the reference runs zero scatter_max rounds, every weight
+        stays 0 and out_1 = 0 (with zero -- not missing -- gradients)."""
+        if self.top_k <= 0:
+            return h * 0.0
         if self.candidates == "edges":
-            out1, (sel_src, sel_w, sel_cnt) = SF.edge_topk_agg(h, g, self.top_k, self.thr, return_selection=True)
             if self.denominator == "selected":
+                h = h if h.requires_grad else h.detach().requires_grad_(torch.is_grad_enabled())   # the lists are only emitted in training mode
+                out1, (_, _, sel_cnt) = SF.edge_topk_agg(h, g, self.top_k, self.thr, return_selection=True)
+                if sel_cnt is None:
+                    raise RuntimeError("denominator='selected' needs grad mode (the selection lists are not emitted in inference)")
                 scale = (sel_cnt.clamp(min=1).float() * g.inv_deg).reciprocal()      # deg / max(cnt,1)
-                out1 = out1 * scale[:, None]
-        elif self.candidates == "all_pairs":
-            from . import simknn
-            out1 = simknn.allpairs_topk_agg(h, self.top_k, self.thr, bool(self.is_remove_self_loops), self.denominator)
-        else:
-            raise ValueError(self.candidates)
-        return out1, g
+                return out1 * scale[:, None]
+            return SF.edge_topk_agg(h, g, self.top_k, self.thr)
+        from . import simknn
+        return simknn.allpairs_topk_agg(h, self.top_k, self.thr, bool(self.is_remove_self_loops), self.denominator)
 
     def forward(self, x, edge_index):
-        h = self._hidden(x)
-        out, _ = self._aggregate(h, edge_index, structural=False)
-        out = out[:, :self.lin.out_features]
+        self._check_options()
+        g = G.prepare(edge_index, x.size(0), remove_self_loops=bool(self.is_remove_self_loops))
+        out = self._aggregate(self._hidden(x), g)[:, :self.lin.out_features]
         if self.bias is not None:
             out = out + self.bias
         return out
@@ -119,6 +127,10 @@ class SNConv_plus_plus(SNConv_plus):
             raise NotImplementedError("only aggr='mean'")
         self.top_k, self.thr = top_k, thr
         self.w = nn.Linear(num_nodes, out_channels)
+        # w.weight keeps the reference's name and shape [C, N] but lives in TRANSPOSED storage ([N, C] row-major): the
+        # kernels gather rows of W^T, the gradient comes out row by row, and Adam (state allocated with preserve_format)
+        # then runs on the same layout -- no transpose copy of a 209 MB parameter (pokec, C = 32) anywhere in a step.
+        self.w.weight = Parameter(torch.empty(num_nodes, out_channels).t())
         self.num_nodes = num_nodes
         self.is_remove_self_loops = is_remove_self_loops
         self.candidates, self.denominator = candidates, denominator
@@ -137,9 +149,14 @@ class SNConv_plus_plus(SNConv_plus):
     def forward(self, x, edge_index):
         if x.size(0) != self.num_nodes:
             raise RuntimeError(f"SNConv_plus_plus was built for num_nodes={self.num_nodes} but got {x.size(0)} rows")
+        self._check_options()
+        g = G.prepare(edge_index, x.size(0), remove_self_loops=bool(self.is_remove_self_loops))
         h = self._hidden(x)
-        out1, g = self._aggregate(h, edge_index, structural=True)
-        out = SF.PPFuse.apply(out1, self.w.weight, self.w.bias, self.beta, self.bias, g)
+        if self.top_k > 0 and self.candidates == "edges" and self.denominator == "candidates" and g.symmetric:
+            # in-lists == out-lists: the structural term rides on the aggregation's own pass over the edges (one kernel)
+            out = SF.edge_topk_agg(h, g, self.top_k, self.thr, structural=(self.w.weight, self.w.bias, self.beta, self.bias))
+        else:
+            out = SF.PPFuse.apply(self._aggregate(h, g), self.w.weight, self.w.bias, self.beta, self.bias, g)
         return out[:, :self.lin.out_features]
 
 

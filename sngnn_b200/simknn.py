@@ -25,7 +25,7 @@ def normalize_operands(x):
     ld32, ldh = _pad_to(d, 4), _pad_to(d, 16)
     xf = torch.empty(n, ld32, dtype=torch.float32, device=x.device)
     xh = torch.empty(n, ldh, dtype=torch.float16, device=x.device)
-    _C.check(_C.lib().sng_rownorm_f32(_C.ptr(x), n, d, d, _C.ptr(xf), ld32, _C.ptr(xh), ldh, None, _C.stream()), "sng_rownorm_f32")
+    _C.call("sng_rownorm_f32", x, _C.ptr(x), n, d, d, _C.ptr(xf), ld32, _C.ptr(xh), ldh, None)
     return xf, xh
 
 
@@ -46,10 +46,10 @@ def build_knn_normalized(xf, xh, d, top_k, thr, remove_self=True, q_lo=0, q_hi=N
     if wbytes == 0:
         raise RuntimeError(f"sng_simknn_workspace_bytes rejected nq={nq} n={n} d={d} top_k={top_k}: {_C.last_error()}")
     ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-    _C.check(_C.lib().sng_simknn_build(_C.ptr(xh[q_lo:]), _C.ptr(xh), xh.size(1), _C.ptr(xf[q_lo:]), _C.ptr(xf), xf.size(1),
-                                       nq, q_lo, n, d, int(top_k), float(thr), int(bool(remove_self)),
-                                       _C.ptr(idx), _C.ptr(sim), _C.ptr(cnt), _C.ptr(nfb), _C.ptr(nfb[1:]), _C.ptr(ws), wbytes, _C.stream()),
-             "sng_simknn_build")
+    _C.require_cuda(xf, xh)
+    _C.call("sng_simknn_build", xf, _C.ptr(xh[q_lo:]), _C.ptr(xh), xh.size(1), _C.ptr(xf[q_lo:]), _C.ptr(xf), xf.size(1),
+            nq, q_lo, n, d, int(top_k), float(thr), int(bool(remove_self)),
+            _C.ptr(idx), _C.ptr(sim), _C.ptr(cnt), _C.ptr(nfb), _C.ptr(nfb[1:]), _C.ptr(ws), wbytes)
     if return_fallback:
         return idx, sim, cnt, nfb
     return idx, sim, cnt
@@ -84,8 +84,7 @@ def seed_pass(xh_q, xh_all, d, seed_stride, force_ew=0):
     """Tensor-core seed pass only (tests / profiling): [nq, 16] group maxima over every seed_stride-th database row."""
     nq, n = xh_q.size(0), xh_all.size(0)
     seeds = torch.empty(nq, 16, dtype=torch.float32, device=xh_q.device)
-    _C.check(_C.lib().sng_simknn_seed(_C.ptr(xh_q), _C.ptr(xh_all), xh_all.size(1), nq, n, d, int(seed_stride), force_ew,
-                                      _C.ptr(seeds), _C.stream()), "sng_simknn_seed")
+    _C.call("sng_simknn_seed", xh_q, _C.ptr(xh_q), _C.ptr(xh_all), xh_all.size(1), nq, n, d, int(seed_stride), force_ew, _C.ptr(seeds))
     return seeds
 
 
@@ -102,10 +101,9 @@ def stage1_candidates(x, cand, thr_lo=-2.0, remove_self=True, force_ew=0, force_
     cm = torch.empty(n * 64, dtype=torch.float32, device=dev)
     nl = ctypes.c_int(0)
     seeds = seed_pass(xh, xh, d, seed_stride, force_ew) if seed_stride > 0 else None
-    _C.check(_C.lib().sng_simknn_stage1(_C.ptr(xh), _C.ptr(xh), xh.size(1), n, 0, n, d, cand, float(thr_lo), int(remove_self),
-                                        _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), force_ew, force_nsplit, ctypes.byref(nl),
-                                        _C.ptr(seeds), int(seed_q), int(seed_stride), None, _C.stream()),
-             "sng_simknn_stage1")
+    _C.call("sng_simknn_stage1", xh, _C.ptr(xh), _C.ptr(xh), xh.size(1), n, 0, n, d, cand, float(thr_lo), int(remove_self),
+            _C.ptr(ci), _C.ptr(cv), _C.ptr(cm), force_ew, force_nsplit, ctypes.byref(nl),
+            _C.ptr(seeds), int(seed_q), int(seed_stride), None)
     s = nl.value
     return ci[: n * s * cand].reshape(n, s, cand), cv[: n * s * cand].reshape(n, s, cand), cm[: n * s].reshape(n, s), xf, xh
 

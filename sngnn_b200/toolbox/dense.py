@@ -31,8 +31,7 @@ def _class_sums(xhat, y=None, num_classes=1):
     sums = torch.zeros(num_classes, d, dtype=torch.float64, device=xhat.device)
     cnt = torch.zeros(num_classes, dtype=torch.float64, device=xhat.device)
     yy = None if y is None else y.to(xhat.device).to(torch.int32).contiguous()
-    _C.check(_C.lib().sng_class_sums_f64(_C.ptr(xhat), _C.ptr(yy), n, d, d, num_classes, _C.ptr(sums), _C.ptr(cnt), _C.stream()),
-             "sng_class_sums_f64")
+    _C.call("sng_class_sums_f64", xhat, _C.ptr(xhat), _C.ptr(yy), n, d, d, num_classes, _C.ptr(sums), _C.ptr(cnt))
     return sums, cnt
 
 
@@ -42,7 +41,7 @@ def cosine_similarity_dense_small(x):
     xhat = _normalised(x)
     n, d = xhat.shape
     out = torch.empty(n, n, dtype=torch.float32, device=dev)
-    _C.check(_C.lib().sng_allpairs_dense_f32(_C.ptr(xhat), n, d, d, _C.ptr(out), _C.stream()), "sng_allpairs_dense_f32")
+    _C.call("sng_allpairs_dense_f32", xhat, _C.ptr(xhat), n, d, d, _C.ptr(out))
     return out.to(src)
 
 

@@ -111,29 +111,41 @@ def test_simknn_plan_is_host_logic():
         simknn.build_plan(1000, 1000, 65, 1000)                          # top_k out of range -> loud error
 
 
-def test_transposed_weight_cache_is_keyed_by_tensor_identity():
-    """The cached W^T of the ++ fusion must follow the parameter object and its version, never a recycled address:
-    a freed model's parameter memory is routinely reused by the next model (regression: golden models run back to back)."""
-    import gc
+def test_structural_weight_lives_in_transposed_storage():
+    """w.weight keeps the reference's name / shape [C, N] but is stored as W^T [N, C] row-major, so the kernels read the
+    parameter itself: no cached transpose that an in-place edit (`w.data.mul_(2)`, which bypasses the version counter)
+    could leave stale.  The layout must survive load_state_dict, deepcopy and the optimizer state."""
+    import copy
+    import sngnn_b200.models as M
     from sngnn_b200 import functional as SF
-    SF._WT_CACHE.clear()
-    w = torch.nn.Parameter(torch.arange(6.0).reshape(2, 3))
-    a = SF._transposed_padded(w, 4)
-    assert a.shape == (3, 4) and torch.equal(a[:, :2], w.detach().t()) and a[:, 2:].abs().sum() == 0
-    assert SF._transposed_padded(w, 4) is a                               # unchanged parameter: reused
-    with torch.no_grad():
-        w.add_(1.0)                                                       # optimizer step: version bump
-    b = SF._transposed_padded(w, 4)
-    assert b is not a and torch.equal(b[:, :2], w.detach().t())
-    ptr = w.data_ptr()
-    del w, a, b
-    gc.collect()
-    for _ in range(8):                                                    # a new parameter, very likely at the old address
-        w2 = torch.nn.Parameter(torch.full((2, 3), 7.0))
-        got = SF._transposed_padded(w2, 4)
-        assert torch.equal(got[:, :2], w2.detach().t())
-        if w2.data_ptr() == ptr:
-            break
+    m = M.SNGNN_Plus_Plus(8, 4, 3, 20, 2, init_beta=0.25)
+    w = m.lins[0].w.weight
+    assert w.shape == (4, 20) and w.stride() == (1, 4) and w.t().is_contiguous()
+    wt = SF._padded_wt(w, 4)
+    assert wt.data_ptr() == w.data_ptr()                                  # a view of the parameter, not a copy
+    w.data.mul_(2)                                                        # no version bump: a cached copy would now be stale
+    assert torch.equal(SF._padded_wt(w, 4), w.detach().t())
+    m.load_state_dict({k: v.clone().contiguous() for k, v in m.state_dict().items()})
+    assert m.lins[0].w.weight.stride() == (1, 4) and copy.deepcopy(m).lins[0].w.weight.stride() == (1, 4)
+    opt = torch.optim.Adam(m.parameters())
+    for p in m.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    assert opt.state[m.lins[0].w.weight]["exp_avg"].stride() == (1, 4)
+    w3 = m.lins[1].w.weight                                               # C = 3: padded copy, zero tail
+    wt3 = SF._padded_wt(w3, 4)
+    assert wt3.shape == (20, 4) and torch.equal(wt3[:, :3], w3.detach().t()) and wt3[:, 3].abs().sum() == 0
+
+
+def test_top_k_zero_follows_the_reference():
+    """R: models/models.py:250 -- `for i in range(self.top_k)` runs no round for top_k <= 0: every weight stays 0."""
+    import sngnn_b200.models as M
+    conv = M.SNConv_plus(6, 4, 10, top_k=0, thr=0.0)
+    h = torch.randn(10, 4, requires_grad=True)
+    out = conv._aggregate(h, None)
+    assert out.shape == (10, 4) and out.abs().sum() == 0
+    out.sum().backward()
+    assert h.grad is not None and h.grad.abs().sum() == 0
 
 
 def test_knn_to_csr_host_logic():

@@ -55,7 +55,7 @@ def test_models_match_reference_golden(fname):
             scale = ref.abs().max().item() + 1e-12
             err = (p.grad.detach().cpu() - ref).abs().max().item() / scale
             worst = max(worst, err)
-            assert err < 1e-4, f"{tag} grad {k}: rel-to-max err {err:.3e}"
+            assert err < 1e-5, f"{tag} grad {k}: rel-to-max err {err:.3e}"
     print(f"{fname}: worst grad error relative to max {worst:.2e}")
 
 
@@ -85,7 +85,7 @@ def test_edge_selection_and_aggregate_vs_oracle(n, e, c, k, thr, rsl):
     (out_ref * w[:, :c].cpu().double()).sum().backward()
     torch.testing.assert_close(out[:, :c].detach().cpu().double(), out_ref.detach(), rtol=1e-5, atol=1e-6)
     scale = h64.grad.abs().max()
-    assert ((hp.grad[:, :c].cpu().double() - h64.grad).abs().max() / scale) < 2e-5
+    assert ((hp.grad[:, :c].cpu().double() - h64.grad).abs().max() / scale) < 1e-5
 
     # selection lists
     n64 = F.normalize(h.double(), dim=-1, eps=1e-12)
@@ -116,7 +116,7 @@ def test_base_snconv_select_all_vs_oracle():
     ref = sn_ref.sn_aggregate(h64, sn_ref.process_edges(ei, n, False))
     (ref * w.cpu().double()).sum().backward()
     torch.testing.assert_close(out.detach().cpu().double(), ref.detach(), rtol=1e-5, atol=1e-6)
-    assert ((hp.grad.cpu().double() - h64.grad).abs().max() / h64.grad.abs().max()) < 2e-5
+    assert ((hp.grad.cpu().double() - h64.grad).abs().max() / h64.grad.abs().max()) < 1e-5
 
 
 def test_rownorm_spmm_sddmm():
@@ -132,7 +132,7 @@ def test_rownorm_spmm_sddmm():
     torch.testing.assert_close(inv, 1.0 / x.norm(dim=1).clamp(min=1e-12), rtol=1e-5, atol=0)
     n, c = 4000, 32
     ei = synth.make_graph(n, 40000, seed=3).to(DEV)
-    g = G.prepare(ei, n, True, structural=True)
+    g = G.prepare(ei, n, True)
     X = torch.randn(n, c, device=DEV)
     out = SF.spmm(X, g.rowptr_in, g.col_in, n)
     pe = G.process_edges(ei, n, True)
@@ -171,12 +171,102 @@ def test_graph_prepare_cuda_equals_torch(n, e, rsl, structural, sym):
     else:
         ei = torch.zeros(2, 0, dtype=torch.long)
     G.clear_cache()
-    ref = G.prepare(ei, n, rsl, structural=structural)
-    got = G.prepare(ei.to(DEV), n, rsl, structural=structural)
+    ref = G.prepare(ei, n, rsl)
+    got = G.prepare(ei.to(DEV), n, rsl)
     assert got.num_edges == ref.num_edges and got.n == ref.n and got.src_shift == ref.src_shift
-    for name in ("rowptr_in", "col_in", "rowptr_out", "col_out", "col_in_shift"):
+    assert got.symmetric == ref.symmetric and got.max_deg == ref.max_deg
+    assert torch.equal(got.rows_long.cpu().sort().values, ref.rows_long) and torch.equal(got.rows_hub.cpu().sort().values, ref.rows_hub)
+    for name in ("rowptr_in", "col_in", "rowptr_out", "col_out", "col_in_shift", "tpos"):
         a, b = getattr(got, name), getattr(ref, name)
         assert (a is None) == (b is None), name
         if a is not None:
             assert torch.equal(a.cpu(), b), name
     torch.testing.assert_close(got.inv_deg.cpu(), ref.inv_deg, rtol=1e-6, atol=0)
+
+
+def _hub_graph(n, e, seed, symmetric, hubs=(3, 17), hub_deg=(1500, 200)):
+    """make_graph + a few forced hub rows (in-degree > 1024 and in (32, 1024]) so every degree class of the forward runs."""
+    from sngnn_b200 import synth
+    ei = synth.make_graph(n, e, seed=seed, symmetric=symmetric, hub_offset=3.0)
+    g = torch.Generator().manual_seed(seed)
+    extra = []
+    for hnode, d in zip(hubs, hub_deg):
+        src = torch.randperm(n, generator=g)[:d]
+        src = src[src != hnode]
+        extra.append(torch.stack([src, torch.full_like(src, hnode)]))
+    ex = torch.cat(extra, 1)
+    if symmetric:
+        ex = torch.cat([ex, ex.flip(0)], 1)
+    ei = torch.cat([ei, ex], 1)
+    key = torch.unique(ei[0] * n + ei[1])                         # coalesced, sorted row-major
+    return torch.stack([key // n, key % n])
+
+
+@pytest.mark.parametrize("c,k,thr,sym", [(32, 10, 0.0, True), (32, 10, 0.0, False), (5, 3, 0.2, True), (64, 40, -0.3, True), (8, 1, 0.99, True)])
+def test_snconv_plus_plus_fused_and_unfused_vs_oracle(c, k, thr, sym):
+    """One SNConv_plus_plus layer on a graph with short, long (> 32) and hub (> 1024) rows: the fused single pass (symmetric
+    graph) and the two-kernel form (asymmetric) against the FP64 oracle -- output, every parameter gradient and dL/dx at
+    1e-5, and the backward must be bit-reproducible (no float atomics)."""
+    from oracle import sn_ref
+    import sngnn_b200.models as M
+    from sngnn_b200 import graph as G
+    n, fd = 6000, 24
+    torch.manual_seed(c * 7 + k)
+    ei = _hub_graph(n, 60000, seed=c + k, symmetric=sym)
+    x = torch.randn(n, fd)
+    x[9] = x[4]
+    conv = M.SNConv_plus_plus(fd, c, n, k, thr, 0.3, True, bias=True).to(DEV)
+    with torch.no_grad():
+        conv.bias.normal_()
+    gph = G.prepare(ei.to(DEV), n, True)
+    assert gph.symmetric == sym and gph.rows_hub.numel() >= 1 and gph.rows_long.numel() >= 1
+    xd = x.to(DEV).requires_grad_(True)
+    wgt = torch.randn(n, c, device=DEV)
+
+    def run():
+        conv.zero_grad()
+        xd.grad = None
+        out = conv(xd, ei.to(DEV))
+        (out * wgt).sum().backward()
+        return out.detach().clone(), {kk: p.grad.detach().clone() for kk, p in conv.named_parameters()}, xd.grad.detach().clone()
+
+    out, grads, dx = run()
+    out2, grads2, dx2 = run()
+    assert torch.equal(out, out2) and torch.equal(dx, dx2)
+    for kk in grads:
+        if kk not in ("lin.weight", "lin.bias"):                          # the dense lin backward is cuBLAS (split-K may differ run to run)
+            assert torch.equal(grads[kk], grads2[kk]), kk
+    p64 = {kk: p.detach().cpu().double().contiguous().requires_grad_(True) for kk, p in conv.named_parameters()}
+    x64 = x.double().requires_grad_(True)
+    ref = sn_ref.snconv_plus_plus(x64, ei, p64["lin.weight"], p64["lin.bias"], p64["w.weight"], p64["w.bias"], p64["beta"], k, thr, True,
+                                  p64["bias"])
+    (ref * wgt.cpu().double()).sum().backward()
+    torch.testing.assert_close(out.cpu().double(), ref.detach(), rtol=1e-5, atol=2e-6)
+    for kk in grads:
+        r = p64[kk].grad
+        err = (grads[kk].cpu().double() - r).abs().max() / (r.abs().max() + 1e-12)
+        assert err < 1e-5, (kk, float(err))
+    assert ((dx.cpu().double() - x64.grad).abs().max() / x64.grad.abs().max()) < 1e-5
+    # inference mode (no lists, no diff) gives the same output
+    with torch.no_grad():
+        out3 = conv(x.to(DEV), ei.to(DEV))
+    assert torch.equal(out3, out)
+
+
+def test_edge_forward_degree_classes_match_general_kernel():
+    """The degree-dispatched forward (short / long / hub kernels) against the general chunked kernel on the same rows:
+    identical selection lists, outputs equal to FP32 rounding."""
+    from sngnn_b200 import graph as G, functional as SF
+    n, c, k = 8000, 32, 10
+    ei = _hub_graph(n, 90000, seed=11, symmetric=True)
+    gph = G.prepare(ei.to(DEV), n, True)
+    h = torch.randn(n, c, device=DEV)
+    h[20] = h[21]
+    out_a, ss_a, sw_a, _, sc_a, _, _ = SF._edge_fwd(h, gph, 0, k, 0.1, True)
+    saved = gph.rows_long, gph.rows_hub
+    gph.rows_long = gph.rows_hub = None                                   # lists unknown -> general kernel on every row
+    out_b, ss_b, sw_b, _, sc_b, _, _ = SF._edge_fwd(h, gph, 0, k, 0.1, True)
+    gph.rows_long, gph.rows_hub = saved
+    assert torch.equal(sc_a, sc_b) and torch.equal(ss_a, ss_b)
+    torch.testing.assert_close(sw_a, sw_b, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(out_a, out_b, rtol=1e-5, atol=1e-6)
