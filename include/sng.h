@@ -75,15 +75,20 @@ SNG_API int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx,
  *                out-list (symmetric graph, src shift 0: info[2] of sng_graph_prepare); otherwise use sng_pp_fuse_fwd.
  * Saved for backward (all may be NULL in inference): sel_src [n,top_k] (source ids, rank order, -1 padded),
  * sel_w [n,top_k] (s_e), sel_cnt [n], sel_q [n,top_k] = tpos of the selected edges (needs tpos; input of sng_edge_bwd).
- * Degree dispatch: rows_long / rows_hub = the long_rows lists of sng_graph_prepare (rows with 32 < deg <= 1024 / deg > 1024);
- * n_long < 0 = lists unknown, one general kernel then runs every row.
+ * Degree dispatch (tables built once per graph by the caller, sngnn_b200/graph.py): rows with more than 32 in-edges are cut
+ * into chunks of <= 32 consecutive edges.  chunk_tab [n_chunks, 4] int32 = (first edge position, edges, local row id, 0);
+ * lrows [n_lrows] = those rows in ascending order, lrow_ptr [n_lrows + 1] = their chunk ranges; rows_hub [n_hub] = the rows
+ * with more than 1024 in-edges (used for c > 32 only).  workspace >= sng_edge_fwd_workspace_bytes(n_chunks, c, top_k) holds
+ * the per-chunk candidates.  n_chunks < 0 = tables unknown: one general kernel then runs every row.
  * Row sharding: the call covers target rows [row_offset, row_offset + n) of `h`, which holds ALL n_total nodes
- * (sources are arbitrary); rowptr / out / sel_* / rows_* are local to the shard, `col` holds global source ids.
+ * (sources are arbitrary); rowptr / out / sel_* / the chunk tables are local to the shard, `col` holds global source ids.
  * inv_norm [n_total] is filled with 1/max(||h_i||, 1e-12) (a pre-pass of this call) and is an input of the backward.
  */
+SNG_API size_t sng_edge_fwd_workspace_bytes(int64_t n_chunks, int64_t c, int top_k);
 SNG_API int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
                  const int32_t* rowptr, const int32_t* col, const int32_t* tpos,
-                 const int32_t* rows_long, int64_t n_long, const int32_t* rows_hub, int64_t n_hub,
+                 const int32_t* chunk_tab, int64_t n_chunks, const int32_t* lrows, const int32_t* lrow_ptr, int64_t n_lrows,
+                 const int32_t* rows_hub, int64_t n_hub, void* workspace, size_t workspace_bytes,
                  int top_k, float thr, float* out, int64_t ldo,
                  int32_t* sel_src, float* sel_w, int32_t* sel_q, int32_t* sel_cnt, float* inv_norm,
                  const float* wt, int64_t ldw, const float* b_w, const float* beta, const float* bias, float* diff,
@@ -184,7 +189,8 @@ SNG_API int sng_class_sums_f64(const float* xhat, const int32_t* y, int64_t n, i
  *   (A of R: models.py:124-127), col_in_shift [capacity] = col_in - min src (its transpose).
  *   tpos [capacity] (may be NULL; needs structural) = position of by-target edge p in the by-source arrays (the transpose
  *   index of sng_edge_bwd).  long_rows [n] (may be NULL): local ids of the rows with 32 < in-degree <= 1024 from the
- *   front, of the rows with in-degree > 1024 from the back (the degree dispatch of sng_edge_fwd).
+ *   front, of the rows with in-degree > 1024 from the back, in no particular order (the caller sorts them and derives the
+ *   chunk tables of sng_edge_fwd).
  *   info (device int32[8]) = {number of kept edges E', min src, 1 if every in-list equals the out-list and min src == 0
  *   (structural only), rows in (32, 1024], rows > 1024, max in-degree, 0, 0}.  Only the first E' entries of col_* / tpos
  *   are meaningful.  The two stable sorts are cub::DeviceRadixSort (a library sort); everything else is kernels of this library.

@@ -42,10 +42,9 @@ res["fwd_fused_train_ms"] = timed(lambda: SF._edge_fwd(h, g, 0, k, 0.0, True, fu
 res["fwd_infer_frac_hbm"] = b_plain / res["fwd_infer_ms"] / 1e6 / hbm
 res["fwd_train_frac_hbm"] = (b_plain + 8 * N * k) / res["fwd_train_ms"] / 1e6 / hbm
 res["fwd_fused_infer_frac_hbm"] = (b_plain + Ep * 4 * C) / res["fwd_fused_infer_ms"] / 1e6 / hbm
-saved = g.rows_long, g.rows_hub
-g.rows_long = g.rows_hub = None
+tab, g.chunk_tab = g.chunk_tab, None
 res["fwd_general_kernel_infer_ms"] = timed(lambda: SF._edge_fwd(h, g, 0, k, 0.0, False))
-g.rows_long, g.rows_hub = saved
+g.chunk_tab = tab
 out, ss, sw, sq, sc, inv, diff = SF._edge_fwd(h, g, 0, k, 0.0, True, fuse, want_q=True)
 nsel = int(sc.sum())
 res["selected_edges"] = nsel

@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace sng {
 
@@ -43,15 +44,28 @@ __global__ void __launch_bounds__(kThreads) rownorm_kernel(const float* __restri
     }
 }
 
-// inv_r[i] = 1 / max(||h_i||, 1e-12): one warp per row.  The edge kernels gather this scalar per edge (the array is
-// L2 resident) instead of recomputing every source row's norm from its gathered features.
+// inv_r[i] = 1 / max(||h_i||, 1e-12).  The edge kernels gather this scalar per edge (the array is L2 resident) instead of
+// recomputing every source row's norm from its gathered features.  G = C/4 lanes per row, four rows in flight per group.
+template <int G>
 __global__ void __launch_bounds__(kThreads) row_inv_norm_kernel(const float* __restrict__ h, int64_t n, int c, int64_t ld, float* __restrict__ inv) {
-    const int lane = threadIdx.x & 31;
-    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * kWarpsPerBlock) {
-        float ss = 0.f;
-        for (int k = lane * 4; k < c; k += 128) { const float4 v = ldg4(h + row * ld + k); ss += dot4(v, v); }
-        ss = group_sum<32>(ss);
-        if (lane == 0) inv[row] = inv_norm_of(ss);
+    constexpr int RPW = 32 / G;                                        // rows per warp step
+    const int lane = threadIdx.x & 31, q = lane % G, grp = lane / G;
+    const bool ch_ok = q * 4 < c;
+    const int64_t nw = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t r0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * RPW * 4; r0 < n; r0 += nw * RPW * 4) {
+        float ss[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t row = r0 + u * RPW + grp;
+            ss[u] = 0.f;
+            if (row < n && ch_ok) { const float4 v = ldg4(h + row * ld + q * 4); ss[u] = dot4(v, v); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float t = group_sum<G>(ss[u]);
+            const int64_t row = r0 + u * RPW + grp;
+            if (q == 0 && row < n) inv[row] = inv_norm_of(t);
+        }
     }
 }
 
@@ -61,15 +75,22 @@ __global__ void __launch_bounds__(kThreads) row_inv_norm_kernel(const float* __r
 //   out_1[i] = sum_{e in S_i} s_e h_j / max(|P_i|, 1)                                  (R: models/models.py:139-158, 244-263, 331-334)
 // and, when `wt` is given (SNGNN++ on a graph whose in-lists equal its out-lists), in the SAME pass over the edges
 //   out_0[i] = sum_{e in P_i} Wt[j] + b_w,  out[i] = beta out_0 + (1 - beta) out_1 (+ bias)   (R: models/models.py:124-136)
-// Rows are dispatched by in-degree (lists built once by sng_graph_prepare):
-//   deg <= 32          edge_fwd_short_kernel: warp per row, the whole in-list lives in registers, one pass, no re-gather
-//   32 < deg <= 1024   edge_fwd_long_kernel : warp per row, 32-edge chunks, running top-k in shared memory
-//   deg > 1024         edge_fwd_hub_kernel  : block per row, 8 warps scan interleaved chunks, lists merged in shared memory
+// Rows are dispatched by in-degree (tables built once per graph, sngnn_b200/graph.py):
+//   C <= 32:  deg <= 32   edge_fwd_staged_kernel<.., CHUNK = false>: warp per row, the in-list staged in shared memory, one pass
+//             deg  > 32   the row is cut into <= 32-edge chunks; edge_fwd_staged_kernel<.., CHUNK = true> scores each chunk like a
+//                         short row (so a hub is spread over many warps), edge_fwd_merge_kernel merges the chunk candidates
+//   C  > 32 or no tables: edge_fwd_long_kernel (warp per row, 32-edge chunks, running top-k in shared memory) on every row,
+//                         edge_fwd_hub_kernel (block per row) for the listed rows with deg > 1024
 struct EdgeFwdArgs {
     const float* h; const float* inv_r;
     int n, row_offset, c, ldh;
     const int* rowptr; const int* col; const int* tpos;
     const int* rows; int n_rows;             // long / hub kernels: explicit list of (local) row ids, or nullptr = all n rows
+    // rows with more than 32 in-edges, cut into <= 32-edge chunks that the staged kernel scores like short rows (CHUNK mode);
+    // edge_fwd_merge_kernel then merges the per-chunk candidates of every long row
+    const int4* chunk_tab; int n_chunks;     // (first edge position, edges, local row id, 0) per chunk
+    const int* lrows; const int* lrow_ptr; int n_lrows;      // long rows (ascending) and their chunk ranges [lrow_ptr[i], lrow_ptr[i+1])
+    float* tmp_s; int* tmp_p; int* tmp_cnt; float* tmp_acc; float* tmp_a0;   // per-chunk candidates [n_chunks, min(top_k,32)], partial sums [n_chunks, 4G]
     int skip_deg;                            // long kernel over all rows: rows with more in-edges are left to the hub kernel (0 = none)
     int top_k; float thr;
     float* out; int ldo;
@@ -106,124 +127,209 @@ __device__ __forceinline__ void write_row(const EdgeFwdArgs& a, int row, int c4,
     }
 }
 
-// Short rows (deg <= 32).  A group of G = C/4 lanes fetches one source row per step with one 128-bit load per lane; the G
-// partial dot products a lane then holds are reduced ACROSS its group with a transposing butterfly (G-1 shuffles), which
-// leaves lane (q, grp) with the finished score of edge q * EPW + grp -- the edge whose source id and 1/norm it loaded in
-// the first place.  The <= 32 gathered rows stay in registers: selection is top_k rounds of a one-instruction warp max in
-// which the WINNING lane records its own rank, and the weighted sum re-uses the registers (weights are shuffled back to
-// the groups), so every source row is read exactly once.  The Wt rows of the fused epilogue ride on the same indices.
-template <int G, bool FUSE, bool SELECT_ALL>
-__global__ void __launch_bounds__(kThreads, G == 8 ? 2 : 4) edge_fwd_short_kernel(const EdgeFwdArgs a) {
-    constexpr int EPW = 32 / G;                 // edges per warp step
+// ---- short rows (and the <= 32-edge chunks of long rows): the staged kernel ------------------------------------------------
+// Built around shared-memory row staging so that the gathers of the NEXT row are in flight while the current row is scored
+// (the floor of gathering random 128-byte rows on this part is ~10 TB/s, scripts/micro/gather_bw.cu; what a row-at-a-time
+// kernel pays is the chain rowptr -> source ids -> rows, once per row): a warp copies the <= 32 source rows of a target row (and the Wt rows of the
+// fused epilogue, and the target row itself) into its private stage with cp.async (LDGSTS, 16 bytes per lane, 32/G rows per
+// instruction, no registers held by loads in flight), two stages per warp.  Row metadata runs three rows ahead (rowptr),
+// source ids two rows ahead, gathers one row ahead, so no global load is consumed in the iteration that issued it.
+// Scoring is lane = edge: every lane reads its own staged row with 128-bit shared loads against the staged target row --
+// no shuffles, no butterfly (row slots are padded by one 16-byte chunk, which makes both this lane-per-row pattern and
+// the lane-per-channel pattern below bank-conflict free without any address swizzle).  Selection is top_k rounds of a
+// one-instruction warp max; the round's winner is known warp-wide, so the same round adds score x staged row to the
+// output (lane = channel) -- rows that are not selected are never touched again, and the output row leaves as one
+// coalesced store.  This kernel is bound by instruction issue, not by memory (ncu: profiles/): every phase is written to
+// keep the per-row instruction count down.
+constexpr int kStWarps = 4;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+// bytes of a staged row slot: the row padded by one 16-byte chunk (G > 1), so that slot strides are odd multiples of 16 B
+template <int G> constexpr int staged_row_bytes() { return G == 1 ? 16 : 16 * G + 16; }
+template <int G, bool FUSE>
+constexpr int staged_stage_bytes() { return (FUSE ? 65 : 33) * staged_row_bytes<G>(); }   // 32 source rows + the target row (+ 32 Wt rows)
+
+template <int G, bool FUSE, bool SELECT_ALL, bool CHUNK>
+__global__ void __launch_bounds__(kStWarps * 32) edge_fwd_staged_kernel(const EdgeFwdArgs a) {
+    constexpr int C = 4 * G;                    // channels of a padded row
+    constexpr int RB = staged_row_bytes<G>();
+    constexpr int EPW = 32 / G;                 // rows copied per cp.async instruction
+    constexpr int SB = staged_stage_bytes<G, FUSE>();
+    constexpr uint32_t WOFF = 33u * RB;         // Wt rows behind the target row
+    extern __shared__ __align__(128) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = lane % G, grp = lane / G;
-    const int my_e = q * EPW + grp;             // the edge of the row this lane owns: fetched at step q by group grp
-    const bool ch_ok = q * 4 < a.c;
-    const int c4 = ch_ok ? q * 4 : 0;           // lanes beyond the channel count read channel 0 and contribute zeros
-    const float* hb = a.h + c4;
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float beta = 0.f;
-    float4 bw = z4, bb = z4;
-    const float* wb = nullptr;
-    if (FUSE) {
-        beta = __ldg(a.beta);
-        wb = a.wt + c4;
-        if (ch_ok) { bw = ldg4(a.b_w + c4); if (a.bias) bb = ldg4(a.bias + c4); }
-    }
-    const bool train = !SELECT_ALL && a.sel_cnt != nullptr;
-    const int stride = gridDim.x * kWarpsPerBlock;
-    int row = blockIdx.x * kWarpsPerBlock + warp;
-    int beg = 0, end = 0, jl = 0;
-    if (row < a.n) {
-        beg = __ldg(a.rowptr + row); end = __ldg(a.rowptr + row + 1);
-        jl = (my_e < end - beg && end - beg <= 32) ? __ldg(a.col + beg + my_e) : a.row_offset + row;   // missing edges read the target row
-    }
-    for (; row < a.n; row += stride) {
-        const int grow = a.row_offset + row;
-        const int cbeg = beg, deg = end - beg, cjl = jl;
-        const int nrow = row + stride;          // the next row's metadata is requested before this row's work
-        if (nrow < a.n) {
-            beg = __ldg(a.rowptr + nrow); end = __ldg(a.rowptr + nrow + 1);
-            jl = (my_e < end - beg && end - beg <= 32) ? __ldg(a.col + beg + my_e) : a.row_offset + nrow;
+    const uint32_t sbase = smem_u32(smraw) + (uint32_t)warp * 2u * SB;
+    const int q = lane % G, grp = lane / G;     // copy role: chunk q of the row of edge st * EPW + grp
+    const bool cq_ok = q * 4 < a.c;
+    const int nch = (a.c + 3) >> 2;             // 16-byte chunks per row that hold data
+    const int ch = lane % C;                    // accumulation role: channel ch (lanes >= C duplicate lanes < C)
+    const bool ch_ok = ch < a.c;
+    const char* hq = reinterpret_cast<const char*>(a.h + q * 4);
+    const char* wq = FUSE ? reinterpret_cast<const char*>(a.wt + q * 4) : nullptr;
+    const int64_t ldhb = (int64_t)a.ldh * 4, ldwb = (int64_t)a.ldw * 4;
+    const int egrp = cq_ok ? grp : 64;                          // lanes of a chunk beyond the channel count never copy
+    const uint32_t cp_off = (uint32_t)(grp * RB + q * 16);      // this lane's copy destination inside a step's EPW slots
+    const uint32_t own_off = (uint32_t)(lane * RB);             // this lane's own row slot (lane = edge)
+    const uint32_t ch_off = (uint32_t)(ch * 4);
+    float beta = 0.f, bw = 0.f, bb = 0.f;
+    if (FUSE) { beta = __ldg(a.beta); if (ch_ok) { bw = __ldg(a.b_w + ch); if (a.bias) bb = __ldg(a.bias + ch); } }
+    const bool train = !CHUNK && !SELECT_ALL && a.sel_cnt != nullptr;
+    const bool want_q = train && a.sel_q != nullptr;
+    const int stride = gridDim.x * kStWarps;
+    const int row0 = blockIdx.x * kStWarps + warp;
+    const int n_items = CHUNK ? a.n_chunks : a.n;               // CHUNK: work item = one <= 32-edge chunk of a long row
+    const int kk = min(a.top_k, 32);
+
+    // deg < 0: no such item; rows with more than 32 in-edges are left to the chunk pass ("active" = 0 <= deg <= 32).
+    // trow = the item's target row (local id): the row itself, or the long row a chunk belongs to
+    auto load_rp = [&](int item, int& beg, int& deg, int& trow) {
+        beg = 0; deg = -1; trow = item;
+        if (item < n_items) {
+            if (CHUNK) { const int4 t = __ldg(a.chunk_tab + item); beg = t.x; deg = t.y; trow = t.z; }
+            else { beg = __ldg(a.rowptr + item); deg = __ldg(a.rowptr + item + 1) - beg; }
         }
-        if (deg > 32) continue;                 // long rows run on their own kernels
-        const bool has = my_e < deg;
-        const float irl = __ldg(a.inv_r + cjl);
-        int tq = 0;
-        if (train && has && a.tpos) tq = __ldg(a.tpos + cbeg + my_e);
-        float4 ni = scale4(ldg4(hb + (int64_t)grow * a.ldh), __ldg(a.inv_r + grow));     // target row, normalised
-        if (!ch_ok) ni = z4;
-        float4 v[G];
-        float4 a0 = z4;
+    };
+    auto load_col = [&](int beg, int deg) { return ((unsigned)deg <= 32u && lane < deg) ? __ldg(a.col + beg + lane) : 0; };
+    auto copy_steps = [&](uint32_t dst, int deg, int jl, auto lo, auto hi) {            // steps [lo, hi): per-lane predicates only, no branches
 #pragma unroll
-        for (int u = 0; u < G; ++u) {
-            const int j = __shfl_sync(kFull, cjl, grp * G + u);                         // owner of edge u * EPW + grp
-            v[u] = z4;
-            if (u * EPW < deg) {                                                         // warp-uniform
-                v[u] = ldg4(hb + (int64_t)j * a.ldh);
-                if (FUSE && u * EPW + grp < deg) add4(a0, ldg4(wb + (int64_t)j * a.ldw));
+        for (int st = decltype(lo)::value; st < decltype(hi)::value; ++st) {
+            const int j = __shfl_sync(kFull, jl, st * EPW + grp);
+            if (st * EPW + egrp < deg) {
+                cp_async16(dst + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(hq + j * ldhb));
+                if (FUSE) cp_async16(dst + WOFF + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(wq + j * ldwb));
             }
         }
-        float d[G];
-#pragma unroll
-        for (int u = 0; u < G; ++u) d[u] = dot4(ni, v[u]);
-        // transposing reduction over the group: lane q ends up with the group's sum of d[q]
-#pragma unroll
-        for (int o = G / 2; o >= 1; o >>= 1) {
-            const bool up = (q & o) != 0;
-#pragma unroll
-            for (int i = 0; i < o; ++i) {
-                const float send = up ? d[i] : d[i + o];
-                const float keep = up ? d[i + o] : d[i];
-                d[i] = keep + __shfl_xor_sync(kFull, send, o);
-            }
+    };
+    auto issue = [&](uint32_t st0, int row, int deg, int jl) {                           // gathers of one item -> one cp.async group (row = target row)
+        if ((unsigned)deg <= 32u) {
+            const uint32_t dst = st0 + cp_off;
+            constexpr int H = G > 1 ? G / 2 : 1;
+            copy_steps(dst, deg, jl, std::integral_constant<int, 0>{}, std::integral_constant<int, H>{});
+            if (G > 1 && deg > 16) copy_steps(dst, deg, jl, std::integral_constant<int, H>{}, std::integral_constant<int, G>{});
+            if (lane < nch) cp_async16(st0 + 32u * RB + (uint32_t)lane * 16u, a.h + (int64_t)(a.row_offset + row) * a.ldh + lane * 4);
         }
-        const float my_s = d[0] * irl + 0.0f;                                            // + 0: -0 becomes +0, equal scores get equal keys
-        float wsel;
-        int cnt = 0, myrank = -1;
-        if (SELECT_ALL) {
-            wsel = has ? my_s : 0.f;
-        } else {
-            unsigned key = (has && my_s >= a.thr) ? okey(my_s) : 0u;
-            const int rounds = min(a.top_k, deg);
-            for (; cnt < rounds; ++cnt) {
-                const unsigned mx = __reduce_max_sync(kFull, key);
-                if (mx == 0u) break;
-                const bool is = key == mx;
-                const unsigned m = __ballot_sync(kFull, is);
-                bool win = is;
-                if (m & (m - 1)) {                                                       // exact tie: the lowest edge position wins
-                    const unsigned emin = __reduce_min_sync(kFull, is ? (unsigned)my_e : 64u);
-                    win = is && (unsigned)my_e == emin;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // pipeline registers: item A = being computed, B = gathers in flight, C = source ids in flight, D = rowptr in flight
+    int begA, degA, trA, begB, degB, trB, begC, degC, trC, begD, degD, trD;
+    load_rp(row0, begA, degA, trA);
+    load_rp(row0 + stride, begB, degB, trB);
+    load_rp(row0 + 2 * stride, begC, degC, trC);
+    int jlA = load_col(begA, degA), jlB = load_col(begB, degB);
+    issue(sbase, trA, degA, jlA);
+    float irlA = 0.f, iriA = 0.f; int tqA = 0;
+    if ((unsigned)degA <= 32u) {
+        irlA = lane < degA ? __ldg(a.inv_r + jlA) : 0.f;
+        iriA = __ldg(a.inv_r + a.row_offset + trA);
+        if (want_q && lane < degA) tqA = __ldg(a.tpos + begA + lane);
+    }
+    uint32_t stA = sbase, stB = sbase + SB;
+    for (int row = row0; row < n_items; row += stride) {
+        // ---- look ahead: rowptr of item + 3 strides, source ids of item + 2, gathers (+ scalars) of item + 1
+        load_rp(row + 3 * stride, begD, degD, trD);
+        const int jlC = load_col(begC, degC);
+        issue(stB, trB, degB, jlB);
+        float irlB = 0.f, iriB = 0.f; int tqB = 0;
+        if ((unsigned)degB <= 32u) {
+            irlB = lane < degB ? __ldg(a.inv_r + jlB) : 0.f;
+            iriB = __ldg(a.inv_r + a.row_offset + trB);
+            if (want_q && lane < degB) tqB = __ldg(a.tpos + begB + lane);
+        }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        // ---- row A
+        if (degA <= 32) {                                                                // (degA >= 0 here)
+            const int deg = degA;
+            const bool has = lane < deg;
+            const uint32_t own = stA + own_off, tgt = stA + 32u * RB;
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                if (i < nch) {                                                           // warp-uniform
+                    const float4 o4 = lds128(own + 16u * i), t4 = lds128(tgt + 16u * i);
+                    d = fmaf(o4.x, t4.x, fmaf(o4.y, t4.y, fmaf(o4.z, t4.z, fmaf(o4.w, t4.w, d))));
                 }
-                if (win) { key = 0u; myrank = cnt; }
             }
-            wsel = myrank >= 0 ? my_s : 0.f;
+            const float my_s = (d * iriA) * irlA + 0.0f;                                 // + 0: -0 becomes +0, equal scores get equal keys
+            const uint32_t rd = stA + ch_off;                                            // lane = channel: word ch of a row slot
+            float acc = 0.f, a0 = 0.f;
+            int cnt = 0, myrank = -1;
+            if (SELECT_ALL) {
+                const float wsel = has ? my_s : 0.f;
+#pragma unroll 4
+                for (int e = 0; e < deg; ++e) acc = fmaf(__shfl_sync(kFull, wsel, e), lds32(rd + (uint32_t)(e * RB)), acc);
+            } else {
+                const bool cand = has && my_s >= a.thr;
+                unsigned key = cand ? okey(my_s) : 0u;
+                const int rounds = min(a.top_k, __popc(__ballot_sync(kFull, cand)));       // every round finds a candidate: no emptiness test inside
+#pragma unroll 2
+                for (; cnt < rounds; ++cnt) {
+                    const unsigned mx = __reduce_max_sync(kFull, key);
+                    const int w = __ffs(__ballot_sync(kFull, key == mx)) - 1;            // lowest lane = lowest edge position wins ties
+                    if (!CHUNK) acc = fmaf(__shfl_sync(kFull, my_s, w), lds32(rd + (uint32_t)(w * RB)), acc);
+                    if (lane == w) { key = 0u; myrank = cnt; }
+                }
+            }
+            if (FUSE) {
+#pragma unroll 4
+                for (int e = 0; e < deg; ++e) a0 += lds32(rd + WOFF + (uint32_t)(e * RB));
+            }
+            if (CHUNK) {
+                // a chunk only reports: its <= top_k candidates (score, edge position) in rank order and its partial sums
+                if (!SELECT_ALL) {
+                    if (myrank >= 0) { a.tmp_s[(int64_t)row * kk + myrank] = my_s; a.tmp_p[(int64_t)row * kk + myrank] = begA + lane; }
+                    if (lane == 0) a.tmp_cnt[row] = cnt;
+                }
+                if (lane < C) {
+                    if (SELECT_ALL) a.tmp_acc[(int64_t)row * C + ch] = acc;
+                    if (FUSE) a.tmp_a0[(int64_t)row * C + ch] = a0;
+                }
+            } else {
+                if (lane < C && ch_ok) {
+                    const float o1 = __fdividef(acc, (float)max(deg, 1));                // PyG aggr='mean': the full in-degree
+                    const int64_t o = (int64_t)row * a.ldo + ch;
+                    if (FUSE) {
+                        const float o0 = a0 + bw;
+                        a.out[o] = beta * o0 + (1.f - beta) * o1 + bb;
+                        if (a.diff) a.diff[o] = o0 - o1;
+                    } else {
+                        a.out[o] = o1;
+                    }
+                }
+                if (train) {
+                    const int64_t lo = (int64_t)row * a.top_k;
+                    if (myrank >= 0) {
+                        a.sel_src[lo + myrank] = jlA; a.sel_w[lo + myrank] = my_s;
+                        if (want_q) a.sel_q[lo + myrank] = tqA;
+                    }
+                    for (int t = cnt + lane; t < a.top_k; t += 32) {                     // -1 padding behind the list
+                        a.sel_src[lo + t] = -1; a.sel_w[lo + t] = 0.f;
+                        if (want_q) a.sel_q[lo + t] = 0;
+                    }
+                    if (lane == 0) a.sel_cnt[row] = cnt;
+                }
+            }
         }
-        float4 acc = z4;
-#pragma unroll
-        for (int u = 0; u < G; ++u) {
-            if (u * EPW < deg) {
-                const float w = __shfl_sync(kFull, wsel, grp * G + u);
-                fma4(acc, w, v[u]);
-            }
-        }
-        cross_group_sum4<G>(acc);
-        if (FUSE) cross_group_sum4<G>(a0);
-        if (grp == 0 && ch_ok) write_row<FUSE>(a, row, q * 4, acc, a0, deg, beta, bw, bb);
-        if (train) {
-            const int64_t lo = (int64_t)row * a.top_k;
-            if (myrank >= 0) {
-                a.sel_src[lo + myrank] = cjl; a.sel_w[lo + myrank] = my_s;
-                if (a.sel_q) a.sel_q[lo + myrank] = tq;
-            }
-            for (int t = cnt + lane; t < a.top_k; t += 32) {                             // -1 padding behind the list
-                a.sel_src[lo + t] = -1; a.sel_w[lo + t] = 0.f;
-                if (a.sel_q) a.sel_q[lo + t] = 0;
-            }
-            if (lane == 0) a.sel_cnt[row] = cnt;
-        }
+        __syncwarp();                                                                    // the stage is overwritten two iterations from now
+        begA = begB; degA = degB; trA = trB; jlA = jlB; irlA = irlB; iriA = iriB; tqA = tqB;
+        begB = begC; degB = degC; trB = trC; jlB = jlC;
+        begC = begD; degC = degD; trC = trD;
+        const uint32_t t = stA; stA = stB; stB = t;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Sorted (score desc, position asc) candidate list of one warp, in shared memory.
@@ -377,6 +483,76 @@ __global__ void __launch_bounds__(kThreads) edge_fwd_long_kernel(const EdgeFwdAr
         cross_group_sum4<G>(acc);
         if (FUSE) cross_group_sum4<G>(a0);
         if (grp == 0 && ch_ok) write_row<FUSE>(a, row, q * 4, acc, a0, end - beg, beta, bw, bb);
+    }
+}
+
+// Long rows under the staged kernel (C <= 32): warp per long row.  Merges the per-chunk candidate lists (each in rank order,
+// chunks in position order, so a newcomer loses every tie) into the row's top-k, sums the per-chunk partial sums, gathers
+// the winners' rows (lane = channel) and writes the row exactly like the staged kernel does for a short row.
+template <int G, bool FUSE, bool SELECT_ALL>
+__global__ void __launch_bounds__(kThreads) edge_fwd_merge_kernel(const EdgeFwdArgs a) {
+    constexpr int C = 4 * G;
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = lane % C;
+    const bool ch_ok = ch < a.c;
+    const int k1 = max(a.top_k, 1), kk = min(a.top_k, 32);
+    float beta = 0.f, bw = 0.f, bb = 0.f;
+    if (FUSE) { beta = __ldg(a.beta); if (ch_ok) { bw = __ldg(a.b_w + ch); if (a.bias) bb = __ldg(a.bias + ch); } }
+    TopList L;
+    L.s = smem + (size_t)warp * 2 * k1;
+    L.p = reinterpret_cast<int*>(L.s + k1);
+    for (int li = blockIdx.x * kWarpsPerBlock + warp; li < a.n_lrows; li += gridDim.x * kWarpsPerBlock) {
+        const int row = __ldg(a.lrows + li);
+        const int c0 = __ldg(a.lrow_ptr + li), c1 = __ldg(a.lrow_ptr + li + 1);
+        const int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
+        float acc = 0.f, a0 = 0.f;
+        L.cnt = 0; L.kth = -CUDART_INF_F;
+        for (int ci = c0; ci < c1; ++ci) {
+            if (!SELECT_ALL) {
+                const int n_c = __ldg(a.tmp_cnt + ci);
+                const float s = lane < n_c ? __ldg(a.tmp_s + (int64_t)ci * kk + lane) : 0.f;
+                const int p = lane < n_c ? __ldg(a.tmp_p + (int64_t)ci * kk + lane) : 0;
+                for (int t = 0; t < n_c; ++t) {                              // descending scores: the first one that cannot enter ends the chunk
+                    const float sg = __shfl_sync(kFull, s, t);
+                    if (!(L.cnt < a.top_k || sg > L.kth)) break;
+                    L.insert(sg, __shfl_sync(kFull, p, t), a.top_k, lane);
+                }
+            } else {
+                acc += __ldg(a.tmp_acc + (int64_t)ci * C + ch);
+            }
+            if (FUSE) a0 += __ldg(a.tmp_a0 + (int64_t)ci * C + ch);
+        }
+        if (!SELECT_ALL) {
+            const int cnt = L.cnt;
+            for (int t = 0; t < cnt; ++t) {
+                const int j = __ldg(a.col + L.p[t]);
+                if (ch_ok) acc = fmaf(L.s[t], __ldg(a.h + (int64_t)j * a.ldh + ch), acc);
+            }
+            if (a.sel_cnt) {
+                const int64_t lo = (int64_t)row * a.top_k;
+                for (int t = lane; t < a.top_k; t += 32) {
+                    const bool ok = t < cnt;
+                    const int p = ok ? L.p[t] : 0;
+                    a.sel_src[lo + t] = ok ? __ldg(a.col + p) : -1;
+                    a.sel_w[lo + t] = ok ? L.s[t] : 0.f;
+                    if (a.sel_q) a.sel_q[lo + t] = (ok && a.tpos) ? __ldg(a.tpos + p) : 0;
+                }
+                if (lane == 0) a.sel_cnt[row] = cnt;
+            }
+            __syncwarp();
+        }
+        if (lane < C && ch_ok) {
+            const float o1 = __fdividef(acc, (float)max(deg, 1));
+            const int64_t o = (int64_t)row * a.ldo + ch;
+            if (FUSE) {
+                const float o0 = a0 + bw;
+                a.out[o] = beta * o0 + (1.f - beta) * o1 + bb;
+                if (a.diff) a.diff[o] = o0 - o1;
+            } else {
+                a.out[o] = o1;
+            }
+        }
     }
 }
 
@@ -909,27 +1085,26 @@ static size_t hub_smem(int top_k) {
 }
 
 template <int G, bool FUSE, bool SELECT_ALL>
-static void launch_edge_fwd(EdgeFwdArgs a, const int32_t* rows_long, int64_t n_long, const int32_t* rows_hub, int64_t n_hub, cudaStream_t st) {
+static void launch_edge_fwd(EdgeFwdArgs a, const int32_t* rows_hub, int64_t n_hub, cudaStream_t st) {
     const size_t ls = long_smem(a.top_k), hs = hub_smem(a.top_k);
     if constexpr (G <= 8) {
-        if (n_long >= 0) {                                   // degree lists known: short rows on the register kernel
-            a.rows = nullptr; a.n_rows = 0;
-            edge_fwd_short_kernel<G, FUSE, SELECT_ALL><<<grid_resident(edge_fwd_short_kernel<G, FUSE, SELECT_ALL>, a.n, kWarpsPerBlock), kThreads, 0, st>>>(a);
-            if (n_long > 0) {
-                a.rows = rows_long; a.n_rows = (int)n_long;
-                edge_fwd_long_kernel<G, FUSE, SELECT_ALL><<<grid_resident(edge_fwd_long_kernel<G, FUSE, SELECT_ALL>, n_long, kWarpsPerBlock, ls), kThreads, ls, st>>>(a);
-            }
-            if (n_hub > 0) {
-                a.rows = rows_hub; a.n_rows = (int)n_hub;
-                const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 4;
-                edge_fwd_hub_kernel<G, FUSE, SELECT_ALL><<<(unsigned)(n_hub < cap ? n_hub : cap), kThreads, hs, st>>>(a);
+        if (a.n_chunks >= 0) {
+            // degree lists known, rows of <= 128 bytes: staged kernel over the short rows, then over the <= 32-edge chunks of the
+            // long rows, then the per-row merge of the chunk candidates
+            const size_t ss = (size_t)kStWarps * 2 * staged_stage_bytes<G, FUSE>();
+            cudaFuncSetAttribute(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
+            edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false><<<grid_resident(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false>, a.n, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
+            if (a.n_chunks > 0) {
+                cudaFuncSetAttribute(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
+                edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, true><<<grid_resident(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, true>, a.n_chunks, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
+                edge_fwd_merge_kernel<G, FUSE, SELECT_ALL><<<grid_resident(edge_fwd_merge_kernel<G, FUSE, SELECT_ALL>, a.n_lrows, kWarpsPerBlock, ls), kThreads, ls, st>>>(a);
             }
             return;
         }
     }
     // wide rows (C > 32) or no degree lists: the chunked kernel runs every row; listed hubs still get their block kernel
     a.rows = nullptr; a.n_rows = 0;
-    a.skip_deg = (n_long >= 0 && n_hub > 0) ? 1024 : 0;
+    a.skip_deg = n_hub > 0 ? 1024 : 0;
     edge_fwd_long_kernel<G, FUSE, SELECT_ALL><<<grid_resident(edge_fwd_long_kernel<G, FUSE, SELECT_ALL>, a.n, kWarpsPerBlock, ls), kThreads, ls, st>>>(a);
     if (a.skip_deg) {
         a.rows = rows_hub; a.n_rows = (int)n_hub; a.skip_deg = 0;
@@ -939,9 +1114,16 @@ static void launch_edge_fwd(EdgeFwdArgs a, const int32_t* rows_long, int64_t n_l
 }
 }  // namespace sng
 
+extern "C" size_t sng_edge_fwd_workspace_bytes(int64_t n_chunks, int64_t c, int top_k) {
+    if (n_chunks <= 0 || c <= 0 || c > 32) return 0;
+    const int64_t kk = top_k > 0 ? (top_k < 32 ? top_k : 32) : 0, cg = 4 * group_lanes(c);
+    return (size_t)n_chunks * (size_t)(2 * kk + 1 + 2 * cg) * 4 + 1024;
+}
+
 extern "C" int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
                             const int32_t* rowptr, const int32_t* col, const int32_t* tpos,
-                            const int32_t* rows_long, int64_t n_long, const int32_t* rows_hub, int64_t n_hub,
+                            const int32_t* chunk_tab, int64_t n_chunks, const int32_t* lrows, const int32_t* lrow_ptr, int64_t n_lrows,
+                            const int32_t* rows_hub, int64_t n_hub, void* workspace, size_t workspace_bytes,
                             int top_k, float thr, float* out, int64_t ldo,
                             int32_t* sel_src, float* sel_w, int32_t* sel_q, int32_t* sel_cnt, float* inv_norm,
                             const float* wt, int64_t ldw, const float* b_w, const float* beta, const float* bias, float* diff,
@@ -955,23 +1137,40 @@ extern "C" int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t 
     SNG_REQUIRE(top_k <= 0 || thr > -1.1f, "sng_edge_fwd: thr must be > -1.1 (knock-out sentinel of R models.py:153)");
     SNG_REQUIRE(!sel_cnt || (top_k > 0 && sel_src && sel_w), "sng_edge_fwd: sel_src / sel_w / sel_cnt go together and need top_k > 0");
     SNG_REQUIRE(!sel_q || (sel_cnt && tpos), "sng_edge_fwd: sel_q needs sel_cnt and tpos");
-    SNG_REQUIRE(n_long < 0 || ((n_long == 0 || rows_long) && (n_hub == 0 || rows_hub) && n_hub >= 0), "sng_edge_fwd: degree lists missing");
+    SNG_REQUIRE(n_chunks <= 0 || (chunk_tab && lrows && lrow_ptr && n_lrows > 0 && n_chunks < (1ll << 31)), "sng_edge_fwd: chunk tables missing");
+    SNG_REQUIRE(n_hub >= 0 && (n_hub == 0 || rows_hub), "sng_edge_fwd: hub list missing");
     SNG_REQUIRE(!wt || (b_w && beta && ldw % 4 == 0 && ldw >= c && ldw < (1ll << 31)), "sng_edge_fwd: fused epilogue needs b_w, beta and a 16-byte aligned wt");
     SNG_REQUIRE(wt || !diff, "sng_edge_fwd: diff is an output of the fused epilogue");
     if (n == 0) return SNG_OK;
+    const bool staged = c <= 32 && n_chunks >= 0;
+    if (staged && n_chunks > 0) {
+        if (!workspace || workspace_bytes < sng_edge_fwd_workspace_bytes(n_chunks, c, top_k)) { set_error("sng_edge_fwd: workspace too small"); return SNG_ERR_WORKSPACE; }
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    row_inv_norm_kernel<<<grid_resident(row_inv_norm_kernel, n_total, kWarpsPerBlock), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm);
+    SNG_DISPATCH_G(c, row_inv_norm_kernel<G><<<grid_resident(row_inv_norm_kernel<G>, n_total, kWarpsPerBlock * (32 / G) * 4), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm));
     EdgeFwdArgs a;
     a.h = h; a.inv_r = inv_norm; a.n = (int)n; a.row_offset = (int)row_offset; a.c = (int)c; a.ldh = (int)ldh;
     a.rowptr = rowptr; a.col = col; a.tpos = tpos; a.rows = nullptr; a.n_rows = 0; a.skip_deg = 0;
     a.top_k = top_k > 0 ? top_k : 0; a.thr = thr; a.out = out; a.ldo = (int)ldo;
     a.sel_src = sel_src; a.sel_w = sel_w; a.sel_q = sel_q; a.sel_cnt = sel_cnt;
     a.wt = wt; a.ldw = (int)ldw; a.b_w = b_w; a.beta = beta; a.bias = bias; a.diff = diff;
+    a.chunk_tab = reinterpret_cast<const int4*>(chunk_tab); a.n_chunks = staged ? (int)n_chunks : -1;
+    a.lrows = lrows; a.lrow_ptr = lrow_ptr; a.n_lrows = (int)n_lrows;
+    a.tmp_s = nullptr; a.tmp_p = nullptr; a.tmp_cnt = nullptr; a.tmp_acc = nullptr; a.tmp_a0 = nullptr;
+    if (staged && n_chunks > 0) {
+        const int64_t kk = a.top_k < 32 ? a.top_k : 32, cg = 4 * group_lanes(c);
+        float* w = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        a.tmp_s = w; w += n_chunks * kk;
+        a.tmp_p = reinterpret_cast<int*>(w); w += n_chunks * kk;
+        a.tmp_cnt = reinterpret_cast<int*>(w); w += n_chunks;
+        a.tmp_acc = w; w += n_chunks * cg;
+        a.tmp_a0 = w;
+    }
     SNG_DISPATCH_G(c,
-        if (wt) { if (top_k > 0) launch_edge_fwd<G, true, false>(a, rows_long, n_long, rows_hub, n_hub, st);
-                  else launch_edge_fwd<G, true, true>(a, rows_long, n_long, rows_hub, n_hub, st); }
-        else { if (top_k > 0) launch_edge_fwd<G, false, false>(a, rows_long, n_long, rows_hub, n_hub, st);
-               else launch_edge_fwd<G, false, true>(a, rows_long, n_long, rows_hub, n_hub, st); });
+        if (wt) { if (top_k > 0) launch_edge_fwd<G, true, false>(a, rows_hub, n_hub, st);
+                  else launch_edge_fwd<G, true, true>(a, rows_hub, n_hub, st); }
+        else { if (top_k > 0) launch_edge_fwd<G, false, false>(a, rows_hub, n_hub, st);
+               else launch_edge_fwd<G, false, true>(a, rows_hub, n_hub, st); });
     return check_launch("sng_edge_fwd");
 }
 

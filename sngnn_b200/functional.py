@@ -50,9 +50,16 @@ def _edge_fwd(h_all, graph, row_offset, k, thr, train, fuse=None, want_q=False):
         wt, bw, beta, bias = fuse
         if train:
             diff = torch.empty_like(out)
-    rows_long, n_long, rows_hub, n_hub = graph.degree_lists()
+    tab, ws, wbytes = graph.chunk_tab, None, 0
+    n_chunks = -1 if tab is None else int(tab.size(0))
+    if n_chunks > 0 and c <= 32:
+        wbytes = _C.lib().sng_edge_fwd_workspace_bytes(n_chunks, c, k)
+        ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    n_lrows = 0 if tab is None else int(graph.lrows.numel())
+    n_hub = 0 if graph.rows_hub is None else int(graph.rows_hub.numel())
     _C.call("sng_edge_fwd", h_all, _C.ptr(h_all), h_all.size(0), n, row_offset, c, c, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in),
-            _C.ptr(graph.tpos if want_q else None), _C.ptr(rows_long), n_long, _C.ptr(rows_hub), n_hub, k,
+            _C.ptr(graph.tpos if want_q else None), _C.ptr(tab), n_chunks, _C.ptr(graph.lrows), _C.ptr(graph.lrow_ptr), n_lrows,
+            _C.ptr(graph.rows_hub), n_hub, _C.ptr(ws), wbytes, k,
             float(thr if thr is not None else 0.0), _C.ptr(out), c, _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_q), _C.ptr(sel_cnt),
             _C.ptr(inv_norm), _C.ptr(wt), c, _C.ptr(bw), _C.ptr(beta), _C.ptr(bias), _C.ptr(diff))
     return out, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff

@@ -30,13 +30,28 @@ _CACHE_MAX = 8
 
 class PreparedGraph:
     __slots__ = ("n", "num_edges", "rowptr_in", "col_in", "inv_deg", "src_shift", "rowptr_out", "col_out",
-                 "col_in_shift", "dst_sorted", "_shards", "tpos", "rows_long", "rows_hub", "symmetric", "max_deg", "is_shard")
+                 "col_in_shift", "dst_sorted", "_shards", "tpos", "rows_long", "rows_hub", "symmetric", "max_deg", "is_shard",
+                 "chunk_tab", "lrows", "lrow_ptr")
 
-    def degree_lists(self):
-        """(rows_long, n_long, rows_hub, n_hub) for sng_edge_fwd; n_long = -1 when the lists are unknown."""
+    def build_chunks(self):
+        """Degree dispatch tables of sng_edge_fwd: every row with more than 32 in-edges is cut into chunks of <= 32 consecutive
+        edges (chunk_tab [n_chunks, 4] = first edge position, edges, row, 0), so a hub is scored by many warps.  Built once."""
         if self.rows_long is None:
-            return None, -1, None, 0
-        return self.rows_long, int(self.rows_long.numel()), self.rows_hub, int(self.rows_hub.numel())
+            self.chunk_tab = self.lrows = self.lrow_ptr = None
+            return
+        dev = self.rowptr_in.device
+        lrows = torch.cat([self.rows_long, self.rows_hub]).long().sort().values
+        rp = self.rowptr_in.long()
+        beg, deg = rp[lrows], rp[lrows + 1] - rp[lrows]
+        nch = (deg + 31) // 32
+        ptr = torch.zeros(lrows.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(nch, 0, out=ptr[1:])
+        owner = torch.repeat_interleave(torch.arange(lrows.numel(), device=dev), nch)      # chunk -> index of its long row
+        within = torch.arange(owner.numel(), device=dev) - ptr[owner]
+        cbeg = beg[owner] + 32 * within
+        clen = torch.minimum(deg[owner] - 32 * within, torch.full_like(within, 32))
+        self.chunk_tab = torch.stack([cbeg, clen, lrows[owner], torch.zeros_like(cbeg)], 1).to(torch.int32).contiguous()
+        self.lrows, self.lrow_ptr = lrows.to(torch.int32).contiguous(), ptr.to(torch.int32).contiguous()
 
     def row_slice(self, lo, hi):
         """Row-sharded view (targets [lo, hi)) for multi-GPU aggregation: rowptr rebased to 0.  Cached per (lo, hi)."""
@@ -61,6 +76,7 @@ class PreparedGraph:
             for name in ("rows_long", "rows_hub"):
                 r = getattr(self, name)
                 setattr(g, name, (r[(r >= lo) & (r < hi)] - lo).contiguous())
+        g.build_chunks()
         if self.rowptr_out is not None:                      # by-(shifted-)source CSR rows [lo, hi) for out_0 = A @ W^T
             bo, eo = int(self.rowptr_out[lo]), int(self.rowptr_out[hi])
             g.rowptr_out = (self.rowptr_out[lo:hi + 1] - bo).contiguous()
@@ -130,6 +146,7 @@ def prepare(edge_index, num_nodes, remove_self_loops, structural=False, processe
     g.rows_hub = (deg > 1024).nonzero().flatten().to(torch.int32)
     g.max_deg = int(deg.max()) if g.n else 0
     g.symmetric = bool(g.src_shift == 0 and torch.equal(g.rowptr_in, g.rowptr_out) and torch.equal(g.col_in, g.col_out))
+    g.build_chunks()
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = (weakref.ref(edge_index), g)
@@ -170,6 +187,7 @@ def _prepare_cuda(edge_index, n, remove_self_loops):
     g.rows_hub = long_rows[n - n_hub:].clone() if n_hub else long_rows[:0].clone()
     g.symmetric, g.max_deg, g.is_shard = sym != 0, max_deg, False
     g.dst_sorted = None
+    g.build_chunks()
     return g
 
 

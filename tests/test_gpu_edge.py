@@ -246,7 +246,7 @@ def test_snconv_plus_plus_fused_and_unfused_vs_oracle(c, k, thr, sym):
         r = p64[kk].grad
         err = (grads[kk].cpu().double() - r).abs().max() / (r.abs().max() + 1e-12)
         assert err < 1e-5, (kk, float(err))
-    assert ((dx.cpu().double() - x64.grad).abs().max() / x64.grad.abs().max()) < 1e-5
+    assert ((dx.cpu().double() - x64.grad).abs().max() / (x64.grad.abs().max() + 1e-12)) < 1e-5
     # inference mode (no lists, no diff) gives the same output
     with torch.no_grad():
         out3 = conv(x.to(DEV), ei.to(DEV))
@@ -263,10 +263,9 @@ def test_edge_forward_degree_classes_match_general_kernel():
     h = torch.randn(n, c, device=DEV)
     h[20] = h[21]
     out_a, ss_a, sw_a, _, sc_a, _, _ = SF._edge_fwd(h, gph, 0, k, 0.1, True)
-    saved = gph.rows_long, gph.rows_hub
-    gph.rows_long = gph.rows_hub = None                                   # lists unknown -> general kernel on every row
+    tab, gph.chunk_tab = gph.chunk_tab, None                              # tables unknown -> general kernel on every row
     out_b, ss_b, sw_b, _, sc_b, _, _ = SF._edge_fwd(h, gph, 0, k, 0.1, True)
-    gph.rows_long, gph.rows_hub = saved
+    gph.chunk_tab = tab
     assert torch.equal(sc_a, sc_b) and torch.equal(ss_a, ss_b)
     torch.testing.assert_close(sw_a, sw_b, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(out_a, out_b, rtol=1e-5, atol=1e-6)
