@@ -487,8 +487,12 @@ __global__ void __launch_bounds__(kThreads) edge_fwd_long_kernel(const EdgeFwdAr
 }
 
 // Long rows under the staged kernel (C <= 32): warp per long row.  Merges the per-chunk candidate lists (each in rank order,
-// chunks in position order, so a newcomer loses every tie) into the row's top-k, sums the per-chunk partial sums, gathers
-// the winners' rows (lane = channel) and writes the row exactly like the staged kernel does for a short row.
+// chunks in position order) into the row's top-k, sums the per-chunk partial sums, gathers the winners' rows (lane =
+// channel) and writes the row exactly like the staged kernel does for a short row.
+// top_k <= 16: a register tournament -- lanes [0, nw) hold the winners so far in rank order, the following lanes take the
+// candidates of as many further chunks as fit, and top_k rounds of a warp max pick the new winners; lane order equals edge
+// position order, so the lowest lane among equal scores is the reference's tie-break.  Larger top_k: sorted insertion into
+// a shared-memory list (a newcomer loses every tie).
 template <int G, bool FUSE, bool SELECT_ALL>
 __global__ void __launch_bounds__(kThreads) edge_fwd_merge_kernel(const EdgeFwdArgs a) {
     constexpr int C = 4 * G;
@@ -496,7 +500,8 @@ __global__ void __launch_bounds__(kThreads) edge_fwd_merge_kernel(const EdgeFwdA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ch = lane % C;
     const bool ch_ok = ch < a.c;
-    const int k1 = max(a.top_k, 1), kk = min(a.top_k, 32);
+    const int k1 = max(a.top_k, 1), kk = max(min(a.top_k, 32), 1);
+    const bool tournament = a.top_k + kk <= 32;
     float beta = 0.f, bw = 0.f, bb = 0.f;
     if (FUSE) { beta = __ldg(a.beta); if (ch_ok) { bw = __ldg(a.b_w + ch); if (a.bias) bb = __ldg(a.bias + ch); } }
     TopList L;
@@ -507,40 +512,89 @@ __global__ void __launch_bounds__(kThreads) edge_fwd_merge_kernel(const EdgeFwdA
         const int c0 = __ldg(a.lrow_ptr + li), c1 = __ldg(a.lrow_ptr + li + 1);
         const int deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row);
         float acc = 0.f, a0 = 0.f;
-        L.cnt = 0; L.kth = -CUDART_INF_F;
-        for (int ci = c0; ci < c1; ++ci) {
-            if (!SELECT_ALL) {
-                const int n_c = __ldg(a.tmp_cnt + ci);
-                const float s = lane < n_c ? __ldg(a.tmp_s + (int64_t)ci * kk + lane) : 0.f;
-                const int p = lane < n_c ? __ldg(a.tmp_p + (int64_t)ci * kk + lane) : 0;
-                for (int t = 0; t < n_c; ++t) {                              // descending scores: the first one that cannot enter ends the chunk
-                    const float sg = __shfl_sync(kFull, s, t);
-                    if (!(L.cnt < a.top_k || sg > L.kth)) break;
-                    L.insert(sg, __shfl_sync(kFull, p, t), a.top_k, lane);
-                }
-            } else {
-                acc += __ldg(a.tmp_acc + (int64_t)ci * C + ch);
+        if (SELECT_ALL || FUSE) {
+#pragma unroll 4
+            for (int ci = c0; ci < c1; ++ci) {
+                if (SELECT_ALL) acc += __ldg(a.tmp_acc + (int64_t)ci * C + ch);
+                if (FUSE) a0 += __ldg(a.tmp_a0 + (int64_t)ci * C + ch);
             }
-            if (FUSE) a0 += __ldg(a.tmp_a0 + (int64_t)ci * C + ch);
         }
         if (!SELECT_ALL) {
-            const int cnt = L.cnt;
-            for (int t = 0; t < cnt; ++t) {
-                const int j = __ldg(a.col + L.p[t]);
-                if (ch_ok) acc = fmaf(L.s[t], __ldg(a.h + (int64_t)j * a.ldh + ch), acc);
+            float ws = 0.f; int wp = 0, nw = 0;                              // winner of rank `lane` (lane < nw): score, edge position
+            if (tournament) {
+                for (int ci = c0; ci < c1;) {
+                    const int nslots = (32 - nw) / kk;                       // chunks that fit behind the current winners
+                    const int m = (lane - nw) / kk, t = (lane - nw) - m * kk;
+                    const bool slot_ok = lane >= nw && m < nslots && ci + m < c1;
+                    const int64_t o = (int64_t)(ci + (slot_ok ? m : 0)) * kk + (slot_ok ? t : 0);
+                    const int n_c = slot_ok ? __ldg(a.tmp_cnt + ci + m) : 0;
+                    const float sc = __ldg(a.tmp_s + o);                     // unconditional: [n_chunks, kk] is always in bounds
+                    const int pc = __ldg(a.tmp_p + o);
+                    const bool cand = slot_ok && t < n_c;
+                    const bool valid = cand || lane < nw;
+                    const float s = cand ? sc : ws;
+                    const int p = cand ? pc : wp;
+                    unsigned key = valid ? okey(s) : 0u;
+                    const int rounds = min(a.top_k, __popc(__ballot_sync(kFull, valid)));
+                    float ns = 0.f; int np = 0;
+                    for (int r = 0; r < rounds; ++r) {
+                        const unsigned mx = __reduce_max_sync(kFull, key);
+                        const int w = __ffs(__ballot_sync(kFull, key == mx)) - 1;
+                        const float ts = __shfl_sync(kFull, s, w);
+                        const int tp = __shfl_sync(kFull, p, w);
+                        if (lane == r) { ns = ts; np = tp; }
+                        if (lane == w) key = 0u;
+                    }
+                    ws = ns; wp = np; nw = rounds;
+                    ci += nslots;
+                }
+            } else {
+                L.cnt = 0; L.kth = -CUDART_INF_F;
+                for (int ci = c0; ci < c1; ++ci) {
+                    const int n_c = __ldg(a.tmp_cnt + ci);
+                    const float s = lane < n_c ? __ldg(a.tmp_s + (int64_t)ci * kk + lane) : 0.f;
+                    const int p = lane < n_c ? __ldg(a.tmp_p + (int64_t)ci * kk + lane) : 0;
+                    for (int t = 0; t < n_c; ++t) {                          // descending scores: the first one that cannot enter ends the chunk
+                        const float sg = __shfl_sync(kFull, s, t);
+                        if (!(L.cnt < a.top_k || sg > L.kth)) break;
+                        L.insert(sg, __shfl_sync(kFull, p, t), a.top_k, lane);
+                    }
+                }
+                nw = L.cnt;
+            }
+            // two winners per lane when top_k > 32 (list path only): ranks lane and lane + 32
+            float ws1 = 0.f; int wp1 = 0;
+            if (!tournament) {
+                ws = lane < nw ? L.s[lane] : 0.f; wp = lane < nw ? L.p[lane] : 0;
+                ws1 = lane + 32 < nw ? L.s[lane + 32] : 0.f; wp1 = lane + 32 < nw ? L.p[lane + 32] : 0;
+                __syncwarp();
+            }
+            const int j0 = lane < nw ? __ldg(a.col + wp) : -1;
+            const int j1 = lane + 32 < nw ? __ldg(a.col + wp1) : -1;
+            for (int t0 = 0; t0 < nw; t0 += 4) {                             // the winners' rows four at a time, lane = channel
+                float v[4], w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + u;
+                    const int j = t < 32 ? __shfl_sync(kFull, j0, t & 31) : __shfl_sync(kFull, j1, t & 31);
+                    w[u] = t < 32 ? __shfl_sync(kFull, ws, t & 31) : __shfl_sync(kFull, ws1, t & 31);
+                    v[u] = (t < nw && ch_ok) ? __ldg(a.h + (int64_t)j * a.ldh + ch) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc = fmaf(t0 + u < nw ? w[u] : 0.f, v[u], acc);
             }
             if (a.sel_cnt) {
                 const int64_t lo = (int64_t)row * a.top_k;
-                for (int t = lane; t < a.top_k; t += 32) {
-                    const bool ok = t < cnt;
-                    const int p = ok ? L.p[t] : 0;
-                    a.sel_src[lo + t] = ok ? __ldg(a.col + p) : -1;
-                    a.sel_w[lo + t] = ok ? L.s[t] : 0.f;
-                    if (a.sel_q) a.sel_q[lo + t] = (ok && a.tpos) ? __ldg(a.tpos + p) : 0;
+                if (lane < a.top_k) {
+                    a.sel_src[lo + lane] = j0; a.sel_w[lo + lane] = ws;
+                    if (a.sel_q) a.sel_q[lo + lane] = (lane < nw && a.tpos) ? __ldg(a.tpos + wp) : 0;
                 }
-                if (lane == 0) a.sel_cnt[row] = cnt;
+                if (lane + 32 < a.top_k) {
+                    a.sel_src[lo + lane + 32] = j1; a.sel_w[lo + lane + 32] = ws1;
+                    if (a.sel_q) a.sel_q[lo + lane + 32] = (lane + 32 < nw && a.tpos) ? __ldg(a.tpos + wp1) : 0;
+                }
+                if (lane == 0) a.sel_cnt[row] = nw;
             }
-            __syncwarp();
         }
         if (lane < C && ch_ok) {
             const float o1 = __fdividef(acc, (float)max(deg, 1));
