@@ -53,6 +53,16 @@ constexpr bool kEvTrace = false;
 #endif
 constexpr int kQueue = 256;             // hit queue entries per CTA (power of two; the plan may shrink it); one entry = 64 bytes
 constexpr int kSeedGroups = 16;         // disjoint column groups of the seed sample: (tile parity) x (32-column chunk of the tile)
+// Candidate scores are kept in shared memory as 16-bit bins (6 bytes per slot with the 32-bit column id instead of 8): at
+// d = 512 the resident A block leaves ~60 KB for the lists, and the 25 % saved is what lets top_k = 50 keep a 22-slot margin
+// (with 8 slots almost no row of a dense cluster can be proven and everything falls to the exact scan).  A bin is 3.1e-5
+// wide; every use below takes the bin's UPPER edge (+ half a bin for float rounding), so thresholds stay valid bounds.
+constexpr float kQScale = 32512.0f, kQOff = 1.0078125f, kQBin = 1.0f / 32512.0f;
+__device__ __forceinline__ unsigned short q_of(float v) {
+    const int q = __float2int_rd((v + kQOff) * kQScale);
+    return (unsigned short)min(max(q, 0), 65535);
+}
+__device__ __forceinline__ float q_upper(unsigned q) { return ((float)q + 1.5f) * kQBin - kQOff; }
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -271,12 +281,12 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t b_off = a_off + (uint32_t)p.kblocks * kTileBytes;
     // per-ROW candidate lists (slot-major: slot s of row r at [s * BM + r]), their bookkeeping, and the hit queue
     const uint32_t list_off = b_off + (uint32_t)p.stages * kTileBytes;
-    const uint32_t thr_off = list_off + (uint32_t)p.cand * BM * 8u;
+    const uint32_t thr_off = list_off + (uint32_t)p.cand * BM * 6u;
     const uint32_t q_off = (thr_off + BM * 12u + 15u) & ~15u;         // row_thr, list_cnt, list_minpos; then the 16-byte aligned queue
     const uint32_t qcap = (uint32_t)p.qcap;
     const uint32_t bar_off = q_off + qcap * 68u + 16u;             // entries (64 B), flags (4 B) + {q_head, q_tail, done}
-    float* list_val = reinterpret_cast<float*>(smem + list_off);
-    int* list_idx = reinterpret_cast<int*>(smem + list_off + (size_t)p.cand * BM * 4);
+    int* list_idx = reinterpret_cast<int*>(smem + list_off);
+    unsigned short* list_val = reinterpret_cast<unsigned short*>(smem + list_off + (size_t)p.cand * BM * 4);     // 16-bit score bins
     volatile float* row_thr = reinterpret_cast<volatile float*>(smem + thr_off);
     int* list_cnt = reinterpret_cast<int*>(smem + thr_off + BM * 4);
     int* list_minpos = reinterpret_cast<int*>(smem + thr_off + BM * 8);
@@ -507,14 +517,15 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                                 int c = list_cnt[row], slot;
                                 if (c < L) { slot = c; list_cnt[row] = ++c; }
                                 else slot = list_minpos[row];
-                                list_val[slot * BM + row] = val;
+                                list_val[slot * BM + row] = q_of(val);
                                 list_idx[slot * BM + row] = col0 + 3 * i;
-                                if (c == L) {                                        // full: the minimum becomes the row's threshold
-                                    float mn = list_val[row]; int mp = 0;
+                                if (c == L) {                                        // full: the minimum's bin becomes the row's threshold
+                                    unsigned mn = list_val[row]; int mp = 0;
 #pragma unroll 4
-                                    for (int s2 = 1; s2 < L; ++s2) { const float y = list_val[s2 * BM + row]; if (y < mn) { mn = y; mp = s2; } }
+                                    for (int s2 = 1; s2 < L; ++s2) { const unsigned y = list_val[s2 * BM + row]; if (y < mn) { mn = y; mp = s2; } }
                                     list_minpos[row] = mp;
-                                    if (mn > thr) { thr = mn; row_thr[row] = mn; }
+                                    const float tn = q_upper(mn);                    // nothing in the minimum's bin can be told from it
+                                    if (tn > thr) { thr = tn; row_thr[row] = tn; }
                                 }
                             }
                         }
@@ -536,7 +547,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 if (grow < nq_eff) {
                     const size_t o = ((size_t)grow * lists + blockIdx.y) * L + sl;
                     const bool ok = sl < list_cnt[r];
-                    p.cand_val[o] = ok ? list_val[sl * BM + r] : -CUDART_INF_F;
+                    p.cand_val[o] = ok ? q_upper(list_val[sl * BM + r]) : -CUDART_INF_F;    // upper bound of the triple's maximum
                     p.cand_idx[o] = ok ? list_idx[sl * BM + r] : -1;
                 }
             }
@@ -750,7 +761,7 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tk = fminf(tk, __shfl_xor_sync(0xffffffffu, tk, o));
-        const float cutoff = ntrip >= top_k ? tk - 2.0f * eps : -CUDART_INF_F;
+        const float cutoff = ntrip >= top_k ? tk - 2.0f * eps - 2.0f * kQBin : -CUDART_INF_F;   // the maxima are 16-bit bin upper edges
         __syncwarp();
         int nvalid = 0;
         for (int m0 = 0; m0 < m3; m0 += 32) {
@@ -1038,7 +1049,7 @@ static int seed_quantile(int top_k, int stride, double tol) {
 
 static size_t smem_bytes(int ew, int kblocks, int stages, int cand, int qcap) {
     (void)ew;
-    return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)cand * BM * 8 + BM * 12 + 16 + (size_t)qcap * 68 + 16 +
+    return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)cand * BM * 6 + BM * 12 + 16 + (size_t)qcap * 68 + 16 +
            8 * (2 * kMaxStages + 9) + 16;
 }
 
@@ -1075,7 +1086,9 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     static const int kMargins[] = {22, 14, 8, 4};
     for (int pass = 0; pass < 2 && !pl->ew; ++pass) {
         for (int ew = force_ew ? force_ew : ew_pref; ew >= 1 && !pl->ew; ew >>= 1) {
-            for (int mi = 0; mi < (top_k > 0 ? 4 : 1) && !pl->ew; ++mi) {
+            // pass 0 wants BOTH a 3-stage ring and a margin of >= 14 slots; pass 1 gives up the third stage before the margin (a
+            // row that cannot be proven costs an exact scan, a shallower ring a few per cent of the main pass)
+            for (int mi = 0; mi < (top_k > 0 ? (pass ? 4 : 2) : 1) && !pl->ew; ++mi) {
                 const int c = top_k > 0 ? cand_for(top_k, kMargins[mi]) : cand;
                 if (c > kMaxCandTotal) continue;
                 for (int qc = kQueue; qc >= 64 && !pl->ew; qc /= 4) {

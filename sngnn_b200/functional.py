@@ -10,6 +10,11 @@ import torch.nn.functional as F
 from . import _C
 
 
+# Test / benchmark hook: set to a list and every EdgeAgg forward in training mode appends its (sel_src, sel_cnt) -- the
+# selection lists of the layers in call order (the parity gates compare them with the oracle's rule).  None = off.
+record_selection = None
+
+
 def padded_channels(c):
     return (c + 3) // 4 * 4
 
@@ -105,6 +110,8 @@ class EdgeAgg(torch.autograd.Function):
             ctx.c = c
         out, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff = _edge_fwd(h, graph, 0, k, thr, train, fuse, want_q=True)
         ctx.graph, ctx.k, ctx.fused, ctx.has_bias = graph, k, fused, bias is not None
+        if record_selection is not None and sel_cnt is not None:
+            record_selection.append((sel_src, sel_cnt))
         ctx.save_for_backward(h, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff, beta if fused else None)
         if sel_cnt is not None:
             ctx.mark_non_differentiable(sel_src, sel_w, sel_cnt)
