@@ -102,6 +102,9 @@ SNG_API int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t row
  *   beta != NULL: g is scaled by (1 - beta) for the aggregation; dbeta (may be NULL) = sum(diff * g) (needs diff, partials);
  *                 dwt (may be NULL) [n, lddw] = beta * sum over out-edges (j -> i) of g_i = dL/dwt.
  * Workspaces (caller-allocated, contents irrelevant): coef [2 * num_edges] floats, dn_target [n, ld], partials [SNG_PARTIALS].
+ * chunk_tab_out / lrows_out / lrow_ptr_out: the degree tables of sng_edge_fwd built over the BY-SOURCE CSR (rows with more
+ * than 32 out-edges cut into <= 32-edge chunks; lrows_out holds true source ids), chunk_partials [n_chunks_out, 3, 4*ceil_pow2(c/4)]
+ * floats; n_chunks_out < 0 = tables unknown (the unstaged source pass then runs every row).
  * Output dh [n, ld] = dL/dh. */
 #define SNG_PARTIALS 4096
 SNG_API int sng_edge_bwd(const float* h, const float* inv_norm, const float* g, int64_t n, int64_t c, int64_t ld, int64_t ldg,
@@ -109,7 +112,9 @@ SNG_API int sng_edge_bwd(const float* h, const float* inv_norm, const float* g, 
                  const int32_t* rowptr_out, const int32_t* col_out, int64_t src_shift, int64_t num_edges,
                  int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_q, const int32_t* sel_cnt,
                  const float* beta, const float* diff, int64_t lddiff, float* dbeta,
-                 float* coef, float* dn_target, float* partials, float* dh, float* dwt, int64_t lddw, void* stream);
+                 float* coef, float* dn_target, float* partials, float* dh, float* dwt, int64_t lddw,
+                 const int32_t* chunk_tab_out, int64_t n_chunks_out, const int32_t* lrows_out, const int32_t* lrow_ptr_out,
+                 int64_t n_lrows_out, float* chunk_partials, void* stream);
 
 /* Scatter form of the backward (float atomics; used for row shards and for explicit neighbour lists, where no
  * transpose index exists).
@@ -158,6 +163,17 @@ SNG_API int sng_pp_fuse_fwd(const float* wt, int64_t n, int64_t c, int64_t ld,
 /* dbeta = sum((out0 - out1) * g), summed in a fixed order (bit-reproducible); partials = workspace of SNG_PARTIALS floats. */
 SNG_API int sng_pp_beta_grad(const float* out0, const float* out1, const float* g, int64_t numel,
                      float* dbeta, float* partials, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Mean negative log-likelihood of the rows with a label in [0, c) (a masked row carries the label -1), forward and
+ * backward, fixed-order reductions.  replaces F.nll_loss(out[mask], y[mask]) at R: train.py:81,99,113.
+ *   fwd: loss (device float) = -(1/count) sum_i logp[i, y[i]], count (device float) = labelled rows; partials = SNG_PARTIALS floats.
+ *   bwd: dlogp [n, ld] = -gscale/count at (i, y[i]), 0 elsewhere (gscale = dL/dloss, a device scalar).
+ */
+SNG_API int sng_nll_loss_fwd(const float* logp, int64_t n, int64_t c, int64_t ld, const int64_t* y, float* loss, float* count,
+                     float* partials, void* stream);
+SNG_API int sng_nll_loss_bwd(int64_t n, int64_t c, int64_t ld, const int64_t* y, const float* gscale, const float* count, float* dlogp,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SDDMM cosine at given edges: s[e] = <xhat[a[e]], xhat[b[e]]> (xhat already normalised, FP32).

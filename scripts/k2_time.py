@@ -48,22 +48,17 @@ g.chunk_tab = tab
 out, ss, sw, sq, sc, inv, diff = SF._edge_fwd(h, g, 0, k, 0.0, True, fuse, want_q=True)
 nsel = int(sc.sum())
 res["selected_edges"] = nsel
-coef = torch.empty(2 * Ep, device=dev); dnt = torch.empty_like(h); dh = torch.empty_like(h); dwt = torch.empty_like(h)
-part = torch.empty(_C.PARTIALS, device=dev); dbeta = torch.empty(1, device=dev)
 
 
 def bwd(fused):
-    _C.call("sng_edge_bwd", h, _C.ptr(h), _C.ptr(inv), _C.ptr(gg), N, C, C, C, _C.ptr(g.rowptr_in), _C.ptr(g.col_in), _C.ptr(g.tpos),
-            _C.ptr(g.rowptr_out), _C.ptr(g.col_out), g.src_shift, Ep, k, _C.ptr(ss), _C.ptr(sw), _C.ptr(sq), _C.ptr(sc),
-            _C.ptr(beta if fused else None), _C.ptr(diff if fused else None), C, _C.ptr(dbeta if fused else None), _C.ptr(coef), _C.ptr(dnt),
-            _C.ptr(part), _C.ptr(dh), _C.ptr(dwt if fused else None), C)
+    SF.edge_bwd(h, inv, gg, g, k, ss, sw, sq, sc, beta if fused else None, diff if fused else None)
 
 
 res["bwd_det_ms"] = timed(lambda: bwd(False))
 res["bwd_det_fused_ms"] = timed(lambda: bwd(True))
 b_bwd = nsel * (3 * 4 * C + 16) + 5 * N * 4 * C
 res["bwd_det_frac_hbm"] = b_bwd / res["bwd_det_ms"] / 1e6 / hbm
-dval, dnrm = torch.zeros_like(h), torch.zeros_like(h)
+dval, dnrm, dh = torch.zeros_like(h), torch.zeros_like(h), torch.empty_like(h)
 
 
 def bwd_scatter():

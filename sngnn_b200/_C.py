@@ -22,12 +22,14 @@ SIGNATURES = {
     "sng_edge_fwd": (_I32, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _I64, _P, _SZ, _I32, _F32, _P, _I64,
                             _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "sng_edge_bwd": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P,
-                            _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
+                            _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _I64, _P, _P]),
     "sng_edge_agg_bwd": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sng_list_agg_fwd": (_I32, [_P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "sng_spmm_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "sng_pp_fuse_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sng_pp_beta_grad": (_I32, [_P, _P, _P, _I64, _P, _P, _P]),
+    "sng_nll_loss_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
+    "sng_nll_loss_bwd": (_I32, [_I64, _I64, _I64, _P, _P, _P, _P, _P]),
     "sng_sddmm_dot": (_I32, [_P, _I64, _I64, _I64, _P, _P, _I64, _P, _P]),
     "sng_allpairs_dense_f32": (_I32, [_P, _I64, _I64, _I64, _P, _P]),
     "sng_class_sums_f64": (_I32, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P]),

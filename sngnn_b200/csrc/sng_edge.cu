@@ -825,6 +825,10 @@ struct EdgeBwdArgs {
     float2* coef; float* dnT;
     const int* rowptr_out; const int* col_out; int shift;
     float* dh; float* dwt; int lddw;
+    // staged source pass: source rows with more than 32 out-edges are cut into <= 32-edge chunks (tables over the by-source
+    // CSR, built like the forward's), each chunk writes partial sums, edge_bwd_source_merge_kernel adds them and finishes
+    const int4* chunk_tab; int n_chunks; const int* lrows; const int* lrow_ptr; int n_lrows;
+    float* tmp_part;                         // [n_chunks, 3, 4G]
 };
 
 template <int G, bool SELECT_ALL>
@@ -949,6 +953,282 @@ __global__ void __launch_bounds__(kThreads) edge_bwd_source_kernel(const EdgeBwd
     }
 }
 
+// ---- staged forms of the two passes (C <= 32, top_k <= 32), same pipeline as edge_fwd_staged_kernel: the rows an item needs
+// are copied into the warp's stage with cp.async one item ahead, metadata runs two / three items ahead.
+// Pass T, item = target row: stage = its <= top_k selected source rows (lane = edge for ds_e = <h_j, g_i>, lane = channel for
+// dn_i = sum ds_e n_j), plus h_i and g_i.
+template <int G>
+__global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(const EdgeBwdArgs a) {
+    constexpr int C = 4 * G;
+    constexpr int RB = staged_row_bytes<G>();
+    constexpr int EPW = 32 / G;
+    constexpr int SB = 34 * RB;                 // 32 source rows, h_i, g_i
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sbase = smem_u32(smraw) + (uint32_t)warp * 2u * SB;
+    const int q = lane % G, grp = lane / G;
+    const bool cq_ok = q * 4 < a.c;
+    const int nch = (a.c + 3) >> 2;
+    const int ch = lane % C;
+    const bool ch_ok = ch < a.c;
+    const char* hq = reinterpret_cast<const char*>(a.h + q * 4);
+    const int64_t ldhb = (int64_t)a.ld * 4;
+    const int egrp = cq_ok ? grp : 64;
+    const uint32_t cp_off = (uint32_t)(grp * RB + q * 16), own_off = (uint32_t)(lane * RB), ch_off = (uint32_t)(ch * 4);
+    const float gscale = a.beta ? 1.0f - __ldg(a.beta) : 1.0f;
+    const int stride = gridDim.x * kStWarps;
+    const int row0 = blockIdx.x * kStWarps + warp;
+    float bpart = 0.f;
+
+    auto load_meta = [&](int row, int& cnt, int& deg) {
+        cnt = -1; deg = 1;
+        if (row < a.n) { cnt = __ldg(a.sel_cnt + row); deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row); }
+    };
+    auto load_list = [&](int row, int cnt, int& j, float& w, int& qp) {
+        j = 0; w = 0.f; qp = 0;
+        if (lane < cnt) { const int64_t o = (int64_t)row * a.top_k + lane; j = __ldg(a.sel_src + o); w = __ldg(a.sel_w + o); qp = __ldg(a.sel_q + o); }
+    };
+    auto issue = [&](uint32_t st0, int row, int cnt, int jl) {
+        if (cnt >= 0) {
+            const uint32_t dst = st0 + cp_off;
+#pragma unroll
+            for (int st = 0; st < G; ++st) {
+                if (st * EPW < cnt) {                                                    // warp-uniform
+                    const int j = __shfl_sync(kFull, jl, st * EPW + grp);
+                    if (st * EPW + egrp < cnt) cp_async16(dst + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(hq + j * ldhb));
+                }
+            }
+            if (lane < nch) {
+                cp_async16(st0 + 32u * RB + (uint32_t)lane * 16u, a.h + (int64_t)(a.row_offset + row) * a.ld + lane * 4);
+                cp_async16(st0 + 33u * RB + (uint32_t)lane * 16u, a.g + (int64_t)row * a.ldg + lane * 4);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int cntA, degA, cntB, degB, cntC, degC, cntD, degD;
+    load_meta(row0, cntA, degA);
+    load_meta(row0 + stride, cntB, degB);
+    load_meta(row0 + 2 * stride, cntC, degC);
+    int jA, qA, jB, qB; float wA, wB;
+    load_list(row0, cntA, jA, wA, qA);
+    load_list(row0 + stride, cntB, jB, wB, qB);
+    issue(sbase, row0, cntA, jA);
+    float irjA = lane < cntA ? __ldg(a.inv_r + jA) : 0.f;
+    float iriA = cntA >= 0 ? __ldg(a.inv_r + a.row_offset + row0) : 0.f;
+    float dfA = (a.diff && cntA >= 0 && ch_ok) ? __ldg(a.diff + (int64_t)row0 * a.lddiff + ch) : 0.f;
+    uint32_t stA = sbase, stB = sbase + SB;
+    for (int row = row0; row < a.n; row += stride) {
+        load_meta(row + 3 * stride, cntD, degD);
+        int jC, qC; float wC;
+        load_list(row + 2 * stride, cntC, jC, wC, qC);
+        issue(stB, row + stride, cntB, jB);
+        const float irjB = lane < cntB ? __ldg(a.inv_r + jB) : 0.f;
+        const float iriB = cntB >= 0 ? __ldg(a.inv_r + a.row_offset + row + stride) : 0.f;
+        const float dfB = (a.diff && cntB >= 0 && ch_ok) ? __ldg(a.diff + (int64_t)(row + stride) * a.lddiff + ch) : 0.f;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        {
+            const int cnt = cntA;
+            const float invd = __fdividef(1.0f, (float)max(degA, 1)) * gscale;           // g1_i / deg_i = g_i * invd
+            const uint32_t own = stA + own_off, gt = stA + 33u * RB;
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                if (i < nch) {
+                    const float4 o4 = lds128(own + 16u * i), g4 = lds128(gt + 16u * i);
+                    d = fmaf(o4.x, g4.x, fmaf(o4.y, g4.y, fmaf(o4.z, g4.z, fmaf(o4.w, g4.w, d))));
+                }
+            }
+            const float ds = d * invd;                                                   // dL/ds_e (lane = selected edge)
+            if (lane < cnt) a.coef[qA] = make_float2(wA * invd, ds * iriA);
+            const float wdn = lane < cnt ? ds * irjA : 0.f;                              // ds_e / r_j: dn_i += wdn h_j
+            const uint32_t rd = stA + ch_off;
+            float dni = 0.f;
+#pragma unroll 2
+            for (int t = 0; t < cnt; ++t) dni = fmaf(__shfl_sync(kFull, wdn, t), lds32(rd + (uint32_t)(t * RB)), dni);
+            if (lane < C && ch_ok) {
+                a.dnT[(int64_t)(a.row_offset + row) * a.ld + ch] = dni;
+                if (a.diff) bpart = fmaf(dfA, lds32(rd + 33u * RB), bpart);              // dL/dbeta: diff . g (raw g)
+            }
+        }
+        __syncwarp();
+        cntA = cntB; degA = degB; jA = jB; wA = wB; qA = qB; irjA = irjB; iriA = iriB; dfA = dfB;
+        cntB = cntC; degB = degC; jB = jC; wB = wC; qB = qC;
+        cntC = cntD; degC = degD;
+        const uint32_t t = stA; stA = stB; stB = t;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (a.dbeta_part) {                                                                  // fixed-order block sum -> one partial per block
+        bpart = group_sum<32>(bpart);
+        __shared__ float red[kStWarps];
+        if (lane == 0) red[warp] = bpart;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < kStWarps; ++w) t += red[w];
+            a.dbeta_part[blockIdx.x] = t;
+        }
+    }
+}
+
+// Pass S, item = source row (or a <= 32-edge chunk of one, CHUNK): stage = g_i of its out-edges (all of them under the fused
+// epilogue, else only the selected ones) and h_i of the selected ones, slot = edge; the sums are lane = channel.
+template <int G, bool FUSE, bool CHUNK>
+__global__ void __launch_bounds__(kStWarps * 32) edge_bwd_source_staged_kernel(const EdgeBwdArgs a) {
+    constexpr int C = 4 * G;
+    constexpr int RB = 16 * G;                  // no lane-per-row reads here: no padding needed
+    constexpr int EPW = 32 / G;
+    constexpr int SB = 64 * RB;                 // 32 g rows, 32 h rows
+    constexpr uint32_t HOFF = 32u * RB;
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t sbase = smem_u32(smraw) + (uint32_t)warp * 2u * SB;
+    const int q = lane % G, grp = lane / G;
+    const bool cq_ok = q * 4 < a.c;
+    const int ch = lane % C;
+    const bool ch_ok = ch < a.c;
+    const char* hq = reinterpret_cast<const char*>(a.h + q * 4);
+    const char* gq = reinterpret_cast<const char*>(a.g + q * 4);
+    const int64_t ldhb = (int64_t)a.ld * 4, ldgb = (int64_t)a.ldg * 4;
+    const int egrp = cq_ok ? grp : 64;
+    const uint32_t cp_off = (uint32_t)(grp * RB + q * 16), ch_off = (uint32_t)(ch * 4);
+    const float beta = FUSE ? __ldg(a.beta) : 0.f;
+    const int stride = gridDim.x * kStWarps;
+    const int row0 = blockIdx.x * kStWarps + warp;
+    const int n_items = CHUNK ? a.n_chunks : a.n_total;
+
+    auto load_rp = [&](int item, int& beg, int& deg) {
+        beg = 0; deg = -1;
+        if (item < n_items) {
+            if (CHUNK) { const int4 t = __ldg(a.chunk_tab + item); beg = t.x; deg = t.y; }
+            else {
+                const int jr = item - a.shift;                               // rows of the by-source CSR are shifted source ids
+                deg = 0;
+                if (jr >= 0) { beg = __ldg(a.rowptr_out + jr); deg = __ldg(a.rowptr_out + jr + 1) - beg; }
+            }
+        }
+    };
+    auto load_edges = [&](int beg, int deg, int& il, float2& cf) {
+        il = 0; cf = make_float2(0.f, 0.f);
+        if ((unsigned)deg <= 32u && lane < deg) { il = __ldg(a.col_out + beg + lane); cf = __ldg(a.coef + beg + lane); }
+    };
+    auto issue = [&](uint32_t st0, int deg, int il, unsigned selm) {
+        if ((unsigned)deg <= 32u) {
+            const uint32_t dst = st0 + cp_off;
+#pragma unroll
+            for (int st = 0; st < G; ++st) {
+                if (st * EPW < deg) {                                                    // warp-uniform
+                    const int i = __shfl_sync(kFull, il, st * EPW + grp);
+                    const int e = st * EPW + egrp;
+                    const bool sel = e < 32 && ((selm >> e) & 1u);
+                    if (FUSE ? e < deg : sel) cp_async16(dst + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(gq + i * ldgb));
+                    if (sel) cp_async16(dst + HOFF + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(hq + i * ldhb));
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int begA, degA, begB, degB, begC, degC, begD, degD;
+    load_rp(row0, begA, degA);
+    load_rp(row0 + stride, begB, degB);
+    load_rp(row0 + 2 * stride, begC, degC);
+    int ilA, ilB; float2 cfA, cfB;
+    load_edges(begA, degA, ilA, cfA);
+    load_edges(begB, degB, ilB, cfB);
+    unsigned smA = __ballot_sync(kFull, cfA.x != 0.f || cfA.y != 0.f);                   // an unselected edge has both coefficients 0
+    issue(sbase, degA, ilA, smA);
+    // finish operands of row A (non-chunk items): h_j, dnT_j, 1/r_j -- lane = channel, requested one item ahead like the rows
+    float hjA = 0.f, dnA = 0.f, irA = 0.f;
+    if (!CHUNK && degA >= 0 && degA <= 32) {
+        irA = __ldg(a.inv_r + row0);
+        if (ch_ok) { hjA = __ldg(a.h + (int64_t)row0 * a.ld + ch); dnA = __ldg(a.dnT + (int64_t)row0 * a.ld + ch); }
+    }
+    uint32_t stA = sbase, stB = sbase + SB;
+    for (int row = row0; row < n_items; row += stride) {
+        load_rp(row + 3 * stride, begD, degD);
+        int ilC; float2 cfC;
+        load_edges(begC, degC, ilC, cfC);
+        const unsigned smB = __ballot_sync(kFull, cfB.x != 0.f || cfB.y != 0.f);
+        issue(stB, degB, ilB, smB);
+        float hjB = 0.f, dnB = 0.f, irB = 0.f;
+        if (!CHUNK && degB >= 0 && degB <= 32) {
+            irB = __ldg(a.inv_r + row + stride);
+            if (ch_ok) { hjB = __ldg(a.h + (int64_t)(row + stride) * a.ld + ch); dnB = __ldg(a.dnT + (int64_t)(row + stride) * a.ld + ch); }
+        }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        if (degA <= 32) {                                                                // (degA >= 0 here; longer rows go through the chunk pass)
+            const uint32_t rd = stA + ch_off;
+            float dval = 0.f, dnj = 0.f, dw = 0.f;
+            for (int e = 0; e < degA; ++e) {
+                const bool sel = (smA >> e) & 1u;                                        // warp-uniform
+                if (FUSE || sel) {
+                    const float gv = lds32(rd + (uint32_t)(e * RB));
+                    if (FUSE) dw += gv;
+                    if (sel) {
+                        dval = fmaf(__shfl_sync(kFull, cfA.x, e), gv, dval);
+                        dnj = fmaf(__shfl_sync(kFull, cfA.y, e), lds32(rd + HOFF + (uint32_t)(e * RB)), dnj);
+                    }
+                }
+            }
+            if (CHUNK) {
+                if (lane < C) {
+                    float* o = a.tmp_part + (int64_t)row * 3 * C + ch;
+                    o[0] = dval; o[C] = dnj; o[2 * C] = dw;
+                }
+            } else {
+                // dh_j = dval + (dn - n_j (n_j . dn)) / r_j with dn = the target-side part (dnT) + the source-side part
+                const float nj = hjA * irA;
+                const float dn = dnA + dnj;
+                float proj = (lane < C && ch_ok) ? nj * dn : 0.f;
+                proj = group_sum<32>(proj);
+                if (lane < C && ch_ok) {
+                    a.dh[(int64_t)row * a.ld + ch] = dval + (dn - nj * proj) * irA;
+                    if (FUSE) a.dwt[(int64_t)row * a.lddw + ch] = dw * beta;
+                }
+            }
+        }
+        __syncwarp();
+        begA = begB; degA = degB; ilA = ilB; cfA = cfB; smA = smB; hjA = hjB; dnA = dnB; irA = irB;
+        begB = begC; degB = degC; ilB = ilC; cfB = cfC;
+        begC = begD; degC = degD;
+        const uint32_t t = stA; stA = stB; stB = t;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// long source rows: sum of the chunk partials + the same finish (warp per row, lane = channel)
+template <int G, bool FUSE>
+__global__ void __launch_bounds__(kThreads) edge_bwd_source_merge_kernel(const EdgeBwdArgs a) {
+    constexpr int C = 4 * G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = lane % C;
+    const bool ch_ok = ch < a.c;
+    const float beta = FUSE ? __ldg(a.beta) : 0.f;
+    for (int li = blockIdx.x * kWarpsPerBlock + warp; li < a.n_lrows; li += gridDim.x * kWarpsPerBlock) {
+        const int row = __ldg(a.lrows + li);                                 // true source id
+        const int c0 = __ldg(a.lrow_ptr + li), c1 = __ldg(a.lrow_ptr + li + 1);
+        float dval = 0.f, dnj = 0.f, dw = 0.f;
+#pragma unroll 4
+        for (int ci = c0; ci < c1; ++ci) {
+            const float* o = a.tmp_part + (int64_t)ci * 3 * C + ch;
+            dval += __ldg(o); dnj += __ldg(o + C);
+            if (FUSE) dw += __ldg(o + 2 * C);
+        }
+        const float ir = __ldg(a.inv_r + row);
+        const float nj = ch_ok ? __ldg(a.h + (int64_t)row * a.ld + ch) * ir : 0.f;
+        const float dn = (ch_ok ? __ldg(a.dnT + (int64_t)row * a.ld + ch) : 0.f) + dnj;
+        float proj = (lane < C && ch_ok) ? nj * dn : 0.f;
+        proj = group_sum<32>(proj);
+        if (lane < C && ch_ok) {
+            a.dh[(int64_t)row * a.ld + ch] = dval + (dn - nj * proj) * ir;
+            if (FUSE) a.dwt[(int64_t)row * a.lddw + ch] = dw * beta;
+        }
+    }
+}
+
 // fixed-order sum of per-block partials (deterministic replacement of a float atomicAdd)
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
     __shared__ float red[256];
@@ -1057,6 +1337,55 @@ __global__ void __launch_bounds__(256) pp_beta_grad_kernel(const float* __restri
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += red[w];
         part[blockIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ loss
+// Mean negative log-likelihood over the rows whose label is >= 0 (R: train.py:81 `F.nll_loss(out[mask], y[mask])` -- a masked
+// row is a label of -1 here), forward and backward, with fixed-order reductions.  torch's nll_loss spends 1.5 + 0.9 ms on
+// the 1.6 M rows of the pokec shape (one CTA walks them); this is one streaming pass each way.
+__global__ void __launch_bounds__(256) nll_loss_fwd_kernel(const float* __restrict__ logp, int64_t n, int c, int64_t ld, const int64_t* __restrict__ y,
+                                                          float* __restrict__ part_sum, float* __restrict__ part_cnt) {
+    float acc = 0.f, cnt = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = __ldg(y + i);
+        if (t >= 0 && t < c) { acc -= __ldg(logp + i * ld + t); cnt += 1.f; }
+    }
+    acc = group_sum<32>(acc); cnt = group_sum<32>(cnt);
+    __shared__ float ra[8], rc[8];
+    if ((threadIdx.x & 31) == 0) { ra[threadIdx.x >> 5] = acc; rc[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < 8; ++w) { a += ra[w]; b += rc[w]; }
+        part_sum[blockIdx.x] = a; part_cnt[blockIdx.x] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) nll_loss_finish_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_cnt, int n,
+                                                             float* __restrict__ loss, float* __restrict__ count) {
+    __shared__ float ra[256], rc[256];
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) { a += part_sum[i]; b += part_cnt[i]; }
+    ra[threadIdx.x] = a; rc[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { ra[threadIdx.x] += ra[threadIdx.x + o]; rc[threadIdx.x] += rc[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *count = rc[0]; *loss = rc[0] > 0.f ? ra[0] / rc[0] : 0.f; }
+}
+
+// dlogp[i, t] = -gscale / count for t = y[i], 0 elsewhere (the whole [n, c] gradient is written: no memset needed)
+__global__ void __launch_bounds__(256) nll_loss_bwd_kernel(int64_t n, int c, int64_t ld, const int64_t* __restrict__ y, const float* __restrict__ gscale,
+                                                          const float* __restrict__ count, float* __restrict__ dlogp) {
+    const float cntv = __ldg(count);
+    const float g = cntv > 0.f ? -__ldg(gscale) / cntv : 0.f;
+    const int64_t total = n * (int64_t)c;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / c;
+        const int t = (int)(e - i * c);
+        dlogp[i * ld + t] = (__ldg(y + i) == t) ? g : 0.f;
     }
 }
 
@@ -1228,12 +1557,36 @@ extern "C" int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t 
     return check_launch("sng_edge_fwd");
 }
 
+namespace sng {
+template <int G>
+static int launch_bwd_target_staged(const EdgeBwdArgs& a, cudaStream_t st) {
+    const size_t ss = (size_t)kStWarps * 2 * 34 * staged_row_bytes<G>();
+    cudaFuncSetAttribute(edge_bwd_target_staged_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
+    const int grid = grid_resident(edge_bwd_target_staged_kernel<G>, a.n, kStWarps, ss, kStWarps * 32);
+    edge_bwd_target_staged_kernel<G><<<grid, kStWarps * 32, ss, st>>>(a);
+    return grid;
+}
+template <int G, bool FUSE>
+static void launch_bwd_source_staged(const EdgeBwdArgs& a, cudaStream_t st) {
+    const size_t ss = (size_t)kStWarps * 2 * 64 * 16 * G;
+    cudaFuncSetAttribute(edge_bwd_source_staged_kernel<G, FUSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
+    edge_bwd_source_staged_kernel<G, FUSE, false><<<grid_resident(edge_bwd_source_staged_kernel<G, FUSE, false>, a.n_total, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
+    if (a.n_chunks > 0) {
+        cudaFuncSetAttribute(edge_bwd_source_staged_kernel<G, FUSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
+        edge_bwd_source_staged_kernel<G, FUSE, true><<<grid_resident(edge_bwd_source_staged_kernel<G, FUSE, true>, a.n_chunks, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
+        edge_bwd_source_merge_kernel<G, FUSE><<<grid_resident(edge_bwd_source_merge_kernel<G, FUSE>, a.n_lrows, kWarpsPerBlock), kThreads, 0, st>>>(a);
+    }
+}
+}  // namespace sng
+
 extern "C" int sng_edge_bwd(const float* h, const float* inv_norm, const float* g, int64_t n, int64_t c, int64_t ld, int64_t ldg,
                             const int32_t* rowptr, const int32_t* col, const int32_t* tpos,
                             const int32_t* rowptr_out, const int32_t* col_out, int64_t src_shift, int64_t num_edges,
                             int top_k, const int32_t* sel_src, const float* sel_w, const int32_t* sel_q, const int32_t* sel_cnt,
                             const float* beta, const float* diff, int64_t lddiff, float* dbeta,
-                            float* coef, float* dn_target, float* partials, float* dh, float* dwt, int64_t lddw, void* stream) {
+                            float* coef, float* dn_target, float* partials, float* dh, float* dwt, int64_t lddw,
+                            const int32_t* chunk_tab_out, int64_t n_chunks_out, const int32_t* lrows_out, const int32_t* lrow_ptr_out,
+                            int64_t n_lrows_out, float* chunk_partials, void* stream) {
     if (int rc = check_rows("sng_edge_bwd", n, c, ld)) return rc;
     SNG_REQUIRE(h && inv_norm && g && rowptr && rowptr_out && col_out && coef && dn_target && dh && ldg % 4 == 0 && ldg >= c,
                 "sng_edge_bwd: null pointer or bad ldg");
@@ -1241,6 +1594,8 @@ extern "C" int sng_edge_bwd(const float* h, const float* inv_norm, const float* 
     SNG_REQUIRE(!dwt || (beta && lddw % 4 == 0 && lddw >= c), "sng_edge_bwd: dwt needs beta and a 16-byte aligned leading dimension");
     SNG_REQUIRE(!dbeta || (beta && diff && partials && lddiff % 4 == 0 && lddiff >= c), "sng_edge_bwd: dbeta needs beta, diff and the partials workspace");
     SNG_REQUIRE(src_shift >= 0 && num_edges >= 0, "sng_edge_bwd: bad src_shift / num_edges");
+    SNG_REQUIRE(n_chunks_out <= 0 || (chunk_tab_out && lrows_out && lrow_ptr_out && n_lrows_out > 0 && chunk_partials),
+                "sng_edge_bwd: by-source chunk tables / partials workspace missing");
     if (n == 0) return SNG_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (top_k > 0 && num_edges > 0 &&
@@ -1253,12 +1608,27 @@ extern "C" int sng_edge_bwd(const float* h, const float* inv_norm, const float* 
     a.coef = reinterpret_cast<float2*>(coef); a.dnT = dn_target;
     a.rowptr_out = rowptr_out; a.col_out = col_out; a.shift = (int)src_shift;
     a.dh = dh; a.dwt = dwt; a.lddw = (int)lddw;
+    a.chunk_tab = reinterpret_cast<const int4*>(chunk_tab_out); a.n_chunks = (int)n_chunks_out; a.lrows = lrows_out; a.lrow_ptr = lrow_ptr_out;
+    a.n_lrows = (int)n_lrows_out; a.tmp_part = chunk_partials;
+    const bool staged_t = c <= 32 && top_k > 0 && top_k <= 32;      // pass T from the saved lists, rows staged in shared memory
+    const bool staged_s = c <= 32 && n_chunks_out >= 0;              // pass S with the by-source chunk tables
     int grid_t = 1;
     SNG_DISPATCH_G(c,
-        if (top_k > 0) { grid_t = grid_resident(edge_bwd_target_kernel<G, false>, n, kWarpsPerBlock); edge_bwd_target_kernel<G, false><<<grid_t, kThreads, 0, st>>>(a); }
-        else { grid_t = grid_resident(edge_bwd_target_kernel<G, true>, n, kWarpsPerBlock); edge_bwd_target_kernel<G, true><<<grid_t, kThreads, 0, st>>>(a); }
-        if (dwt) edge_bwd_source_kernel<G, true><<<grid_resident(edge_bwd_source_kernel<G, true>, n, kWarpsPerBlock), kThreads, 0, st>>>(a);
-        else edge_bwd_source_kernel<G, false><<<grid_resident(edge_bwd_source_kernel<G, false>, n, kWarpsPerBlock), kThreads, 0, st>>>(a));
+        if constexpr (G <= 8) {
+            if (staged_t) grid_t = launch_bwd_target_staged<G>(a, st);
+        }
+        if (!staged_t || G > 8) {
+            if (top_k > 0) { grid_t = grid_resident(edge_bwd_target_kernel<G, false>, n, kWarpsPerBlock); edge_bwd_target_kernel<G, false><<<grid_t, kThreads, 0, st>>>(a); }
+            else { grid_t = grid_resident(edge_bwd_target_kernel<G, true>, n, kWarpsPerBlock); edge_bwd_target_kernel<G, true><<<grid_t, kThreads, 0, st>>>(a); }
+        }
+        bool done_s = false;
+        if constexpr (G <= 8) {
+            if (staged_s) { if (dwt) launch_bwd_source_staged<G, true>(a, st); else launch_bwd_source_staged<G, false>(a, st); done_s = true; }
+        }
+        if (!done_s) {
+            if (dwt) edge_bwd_source_kernel<G, true><<<grid_resident(edge_bwd_source_kernel<G, true>, n, kWarpsPerBlock), kThreads, 0, st>>>(a);
+            else edge_bwd_source_kernel<G, false><<<grid_resident(edge_bwd_source_kernel<G, false>, n, kWarpsPerBlock), kThreads, 0, st>>>(a);
+        });
     if (dbeta) sum_partials_kernel<<<1, 256, 0, st>>>(partials, grid_t, dbeta);
     return check_launch("sng_edge_bwd");
 }
@@ -1317,6 +1687,24 @@ extern "C" int sng_pp_beta_grad(const float* out0, const float* out1, const floa
     pp_beta_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out0, out1, g, numel, partials);
     sum_partials_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, grid, dbeta);
     return check_launch("sng_pp_beta_grad");
+}
+
+extern "C" int sng_nll_loss_fwd(const float* logp, int64_t n, int64_t c, int64_t ld, const int64_t* y, float* loss, float* count,
+                               float* partials, void* stream) {
+    SNG_REQUIRE(logp && y && loss && count && partials && n >= 0 && c > 0 && ld >= c && c < (1ll << 30), "sng_nll_loss_fwd: bad arguments");
+    int grid = grid_for_rows(n > 0 ? n : 1, 256);
+    if (grid > SNG_PARTIALS / 2) grid = SNG_PARTIALS / 2;
+    nll_loss_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logp, n, (int)c, ld, y, partials, partials + SNG_PARTIALS / 2);
+    nll_loss_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, partials + SNG_PARTIALS / 2, grid, loss, count);
+    return check_launch("sng_nll_loss_fwd");
+}
+
+extern "C" int sng_nll_loss_bwd(int64_t n, int64_t c, int64_t ld, const int64_t* y, const float* gscale, const float* count, float* dlogp,
+                               void* stream) {
+    SNG_REQUIRE(y && gscale && count && dlogp && n >= 0 && c > 0 && ld >= c, "sng_nll_loss_bwd: bad arguments");
+    if (n == 0) return SNG_OK;
+    nll_loss_bwd_kernel<<<grid_for_rows(n * c, 256), 256, 0, (cudaStream_t)stream>>>(n, (int)c, ld, y, gscale, count, dlogp);
+    return check_launch("sng_nll_loss_bwd");
 }
 
 extern "C" int sng_sddmm_dot(const float* xhat, int64_t n, int64_t d, int64_t ld, const int32_t* a, const int32_t* b,

@@ -121,27 +121,46 @@ class EdgeAgg(torch.autograd.Function):
     def backward(ctx, g, *_):
         h, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff, beta = ctx.saved_tensors
         graph, k, fused = ctx.graph, ctx.k, ctx.fused
-        n, cp = h.shape
-        dev = h.device
+        cp = h.size(1)
         g = g.contiguous()
-        coef = torch.empty(max(graph.num_edges, 1) * 2, dtype=torch.float32, device=dev)
-        dnt = torch.empty_like(h)
-        dh = torch.empty_like(h)
-        dbeta = dwt = part = None
-        if fused:
-            dbeta = torch.empty(1, dtype=torch.float32, device=dev)
-            part = torch.empty(_C.PARTIALS, dtype=torch.float32, device=dev)
-            dwt = torch.empty(n, cp, dtype=torch.float32, device=dev)
-        _C.call("sng_edge_bwd", h, _C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, cp, cp, cp, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in),
-                _C.ptr(graph.tpos), _C.ptr(graph.rowptr_out), _C.ptr(graph.col_out), graph.src_shift, graph.num_edges, k,
-                _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_q), _C.ptr(sel_cnt), _C.ptr(beta if fused else None),
-                _C.ptr(diff), cp, _C.ptr(dbeta), _C.ptr(coef), _C.ptr(dnt), _C.ptr(part), _C.ptr(dh), _C.ptr(dwt), cp)
+        dh, dwt, dbeta = edge_bwd(h, inv_norm, g, graph, k, sel_src, sel_w, sel_q, sel_cnt, beta if fused else None, diff)
         if not fused:
             return dh, None, None, None, None, None, None, None
         c = ctx.c
         gsum = g.sum(0)[:c]
         dw = (dwt if cp == c else dwt[:, :c]).t()           # [C, N] in the parameter's own (transposed) layout
         return dh, None, None, None, dw, gsum * beta, dbeta, (gsum if ctx.has_bias else None)
+
+
+def edge_bwd(h, inv_norm, g, graph, k, sel_src, sel_w, sel_q, sel_cnt, beta=None, diff=None):
+    """sng_edge_bwd: dL/dh [N, Cp] of the aggregation -- two gather passes, no float atomics -- and, with `beta` (the fused
+    SNGNN++ epilogue), dL/dW^T [N, Cp] and dL/dbeta.  `g` = dL/dout."""
+    n, cp = h.shape
+    dev = h.device
+    fused = beta is not None
+    coef = torch.empty(max(graph.num_edges, 1) * 2, dtype=torch.float32, device=dev)
+    dnt = torch.empty_like(h)
+    dh = torch.empty_like(h)
+    dbeta = dwt = part = None
+    if fused:
+        dbeta = torch.empty(1, dtype=torch.float32, device=dev)
+        part = torch.empty(_C.PARTIALS, dtype=torch.float32, device=dev)
+        dwt = torch.empty(n, cp, dtype=torch.float32, device=dev)
+    tab = graph.chunk_tab_out if cp <= 32 else None
+    n_chunks = -1 if tab is None else int(tab.size(0))
+    cpart = None
+    if n_chunks > 0:
+        cg = 4
+        while cg < cp:
+            cg *= 2
+        cpart = torch.empty(n_chunks * 3 * cg, dtype=torch.float32, device=dev)
+    _C.call("sng_edge_bwd", h, _C.ptr(h), _C.ptr(inv_norm), _C.ptr(g), n, cp, cp, cp, _C.ptr(graph.rowptr_in), _C.ptr(graph.col_in),
+            _C.ptr(graph.tpos), _C.ptr(graph.rowptr_out), _C.ptr(graph.col_out), graph.src_shift, graph.num_edges, k,
+            _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_q), _C.ptr(sel_cnt), _C.ptr(beta), _C.ptr(diff if fused else None), cp,
+            _C.ptr(dbeta), _C.ptr(coef), _C.ptr(dnt), _C.ptr(part), _C.ptr(dh), _C.ptr(dwt), cp,
+            _C.ptr(tab), n_chunks, _C.ptr(graph.lrows_out if tab is not None else None),
+            _C.ptr(graph.lrow_ptr_out if tab is not None else None), 0 if tab is None else int(graph.lrows_out.numel()), _C.ptr(cpart))
+    return dh, dwt, dbeta
 
 
 def edge_topk_agg_rows(h_all, shard, row_offset, top_k=None, thr=None):
@@ -289,3 +308,36 @@ def sddmm_dot(xhat, a, b):
     s = torch.empty(a.numel(), dtype=torch.float32, device=xhat.device)
     _C.call("sng_sddmm_dot", xhat, _C.ptr(xhat), xhat.size(0), xhat.size(1), xhat.size(1), _C.ptr(a), _C.ptr(b), a.numel(), _C.ptr(s))
     return s
+
+
+class _NllLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logp, y):
+        _C.require_cuda(logp, y)
+        logp = logp.contiguous()
+        y = y.contiguous().long()
+        n, c = logp.shape
+        out = torch.empty(2, dtype=torch.float32, device=logp.device)             # loss, count
+        part = torch.empty(_C.PARTIALS, dtype=torch.float32, device=logp.device)
+        _C.call("sng_nll_loss_fwd", logp, _C.ptr(logp), n, c, c, _C.ptr(y), _C.ptr(out), _C.ptr(out[1:]), _C.ptr(part))
+        ctx.save_for_backward(y, out)
+        ctx.shape = (n, c)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        y, out = ctx.saved_tensors
+        n, c = ctx.shape
+        d = torch.empty(n, c, dtype=torch.float32, device=y.device)
+        g = g.contiguous().float().reshape(1)
+        _C.call("sng_nll_loss_bwd", y, n, c, c, _C.ptr(y), _C.ptr(g), _C.ptr(out[1:]), _C.ptr(d))
+        return d, None
+
+
+def nll_loss(logp, y, mask=None):
+    """Mean negative log-likelihood of `logp` [N, C] (the models' log_softmax output) against labels `y` [N] -- what
+    R: train.py:81 computes as F.nll_loss(out[mask], y[mask]).  `mask` (bool [N]) keeps the masked form in ONE pass: masked-out
+    rows get the label -1 instead of being gathered away.  Fixed-order reductions: bit-reproducible, forward and backward."""
+    if mask is not None:
+        y = torch.where(mask, y, torch.full_like(y, -1))
+    return _NllLoss.apply(logp, y)

@@ -31,17 +31,13 @@ _CACHE_MAX = 8
 class PreparedGraph:
     __slots__ = ("n", "num_edges", "rowptr_in", "col_in", "inv_deg", "src_shift", "rowptr_out", "col_out",
                  "col_in_shift", "dst_sorted", "_shards", "tpos", "rows_long", "rows_hub", "symmetric", "max_deg", "is_shard",
-                 "chunk_tab", "lrows", "lrow_ptr")
+                 "chunk_tab", "lrows", "lrow_ptr", "chunk_tab_out", "lrows_out", "lrow_ptr_out")
 
-    def build_chunks(self):
-        """Degree dispatch tables of sng_edge_fwd: every row with more than 32 in-edges is cut into chunks of <= 32 consecutive
-        edges (chunk_tab [n_chunks, 4] = first edge position, edges, row, 0), so a hub is scored by many warps.  Built once."""
-        if self.rows_long is None:
-            self.chunk_tab = self.lrows = self.lrow_ptr = None
-            return
-        dev = self.rowptr_in.device
-        lrows = torch.cat([self.rows_long, self.rows_hub]).long().sort().values
-        rp = self.rowptr_in.long()
+    @staticmethod
+    def _chunk_tables(rowptr, lrows):
+        """(chunk_tab [n_chunks, 4] = first edge position, edges, row, 0; lrow_ptr) of the rows `lrows` (ascending) of a CSR."""
+        dev = rowptr.device
+        rp = rowptr.long()
         beg, deg = rp[lrows], rp[lrows + 1] - rp[lrows]
         nch = (deg + 31) // 32
         ptr = torch.zeros(lrows.numel() + 1, dtype=torch.int64, device=dev)
@@ -50,8 +46,24 @@ class PreparedGraph:
         within = torch.arange(owner.numel(), device=dev) - ptr[owner]
         cbeg = beg[owner] + 32 * within
         clen = torch.minimum(deg[owner] - 32 * within, torch.full_like(within, 32))
-        self.chunk_tab = torch.stack([cbeg, clen, lrows[owner], torch.zeros_like(cbeg)], 1).to(torch.int32).contiguous()
-        self.lrows, self.lrow_ptr = lrows.to(torch.int32).contiguous(), ptr.to(torch.int32).contiguous()
+        tab = torch.stack([cbeg, clen, lrows[owner], torch.zeros_like(cbeg)], 1).to(torch.int32).contiguous()
+        return tab, ptr.to(torch.int32).contiguous()
+
+    def build_chunks(self):
+        """Degree dispatch tables of sng_edge_fwd / sng_edge_bwd: every row with more than 32 in-edges (out-edges for the
+        by-source pass of the backward) is cut into chunks of <= 32 consecutive edges, so a hub is handled by many warps.
+        Built once per graph."""
+        self.chunk_tab = self.lrows = self.lrow_ptr = self.chunk_tab_out = self.lrows_out = self.lrow_ptr_out = None
+        if self.rows_long is None:
+            return
+        lrows = torch.cat([self.rows_long, self.rows_hub]).long().sort().values
+        self.chunk_tab, self.lrow_ptr = self._chunk_tables(self.rowptr_in, lrows)
+        self.lrows = lrows.to(torch.int32).contiguous()
+        if self.rowptr_out is not None and not self.is_shard:
+            rp = self.rowptr_out.long()
+            lr = ((rp[1:] - rp[:-1]) > 32).nonzero().flatten()                             # rows of the by-source CSR = source id - shift
+            self.chunk_tab_out, self.lrow_ptr_out = self._chunk_tables(self.rowptr_out, lr)
+            self.lrows_out = (lr + self.src_shift).to(torch.int32).contiguous()               # true source ids
 
     def row_slice(self, lo, hi):
         """Row-sharded view (targets [lo, hi)) for multi-GPU aggregation: rowptr rebased to 0.  Cached per (lo, hi)."""

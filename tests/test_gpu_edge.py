@@ -269,3 +269,22 @@ def test_edge_forward_degree_classes_match_general_kernel():
     assert torch.equal(sc_a, sc_b) and torch.equal(ss_a, ss_b)
     torch.testing.assert_close(sw_a, sw_b, rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(out_a, out_b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,c", [(1, 2), (5000, 5), (200003, 2)])
+def test_nll_loss_matches_torch_and_is_reproducible(n, c):
+    from sngnn_b200 import functional as SF
+    torch.manual_seed(n)
+    logits = torch.randn(n, c, device=DEV)
+    y = torch.randint(0, c, (n,), device=DEV)
+    mask = torch.rand(n, device=DEV) < 0.6
+    mask[0] = True
+    a = torch.log_softmax(logits, 1).requires_grad_(True)
+    b = a.detach().clone().requires_grad_(True)
+    la = SF.nll_loss(a, y, mask)
+    lb = F.nll_loss(b[mask], y[mask])
+    (la * 3.0).backward(); (lb * 3.0).backward()
+    torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-9)
+    assert torch.equal(SF.nll_loss(a.detach(), y, mask), la.detach())          # fixed-order reduction
+    torch.testing.assert_close(SF.nll_loss(a.detach(), y), F.nll_loss(a.detach(), y), rtol=1e-5, atol=1e-6)
