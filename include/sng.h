@@ -176,6 +176,25 @@ SNG_API int sng_nll_loss_bwd(int64_t n, int64_t c, int64_t ld, const int64_t* y,
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Data formats either side of the path.
+ * sng_knn_to_csr: fixed-width neighbour lists (idx / sim [nq, top_k], cnt [nq], the outputs of sng_simknn_build or the saved
+ *   lists of sng_edge_fwd) -> CSR: rowptr [nq+1] = exclusive scan of cnt (cub::DeviceScan), col [sum cnt] in rank order,
+ *   val (may be NULL) = the similarities.  This is "then emits CSR neighbour lists" of the all-pairs builder.
+ * sng_pp_fuse_bwd: backward of sng_pp_fuse_fwd: dbeta = sum((out0 - out1) g) (fixed order), g0 = beta g, dout1 = (1 - beta) g,
+ *   dwt [n, c] = A^T g0 (row t gathers g0 over col_in_shift of t's in-edges).  Rows contiguous (ld == c).
+ * sng_segment_mean: out[s] = mean of val[e] over seg[e] == s (0 for an empty segment), FP64 accumulation;
+ *   replaces torch_scatter.scatter_mean at R: SimGFAToolbox/dense.py:163.  workspace >= 12 * n_seg + 256 bytes.
+ */
+SNG_API size_t sng_knn_to_csr_workspace_bytes(int64_t nq);
+SNG_API int sng_knn_to_csr(const int32_t* idx, const float* sim, const int32_t* cnt, int64_t nq, int top_k, int32_t* rowptr, int32_t* col,
+                   float* val, void* workspace, size_t workspace_bytes, void* stream);
+SNG_API int sng_pp_fuse_bwd(const float* out0, const float* out1, const float* g, const float* beta, int64_t n, int64_t c, int64_t ld,
+                    const int32_t* rowptr_in, const int32_t* col_in_shift, float* dbeta, float* partials, float* g0, float* dout1,
+                    float* dwt, void* stream);
+SNG_API int sng_segment_mean(const float* val, const int32_t* seg, int64_t num, int64_t n_seg, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * SDDMM cosine at given edges: s[e] = <xhat[a[e]], xhat[b[e]]> (xhat already normalised, FP32).
  * replaces index_select x2 + mul + sum at R: SimGFAToolbox/dense.py:152-164 and the per-node mm of :53-58.
  */

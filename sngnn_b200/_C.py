@@ -30,6 +30,10 @@ SIGNATURES = {
     "sng_pp_beta_grad": (_I32, [_P, _P, _P, _I64, _P, _P, _P]),
     "sng_nll_loss_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
     "sng_nll_loss_bwd": (_I32, [_I64, _I64, _I64, _P, _P, _P, _P, _P]),
+    "sng_knn_to_csr_workspace_bytes": (_SZ, [_I64]),
+    "sng_knn_to_csr": (_I32, [_P, _P, _P, _I64, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "sng_pp_fuse_bwd": (_I32, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sng_segment_mean": (_I32, [_P, _P, _I64, _I64, _P, _P, _SZ, _P]),
     "sng_sddmm_dot": (_I32, [_P, _I64, _I64, _I64, _P, _P, _I64, _P, _P]),
     "sng_allpairs_dense_f32": (_I32, [_P, _I64, _I64, _I64, _P, _P]),
     "sng_class_sums_f64": (_I32, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P]),

@@ -1053,12 +1053,20 @@ static size_t smem_bytes(int ew, int kblocks, int stages, int cand, int qcap) {
            8 * (2 * kMaxStages + 9) + 16;
 }
 
-static int env_int(const char* name, int lo, int hi) {       // tuning overrides for experiments
+// Tuning / debugging overrides through environment variables exist only in instrumented builds (make EXTRA=-DSNG_KNN_INSTRUMENT):
+// the product library reads no environment and keeps no global state besides the cached SM count and driver entry point.
+#ifdef SNG_KNN_INSTRUMENT
+static int env_int(const char* name, int lo, int hi) {
     const char* e = getenv(name);
     if (!e) return 0;
     const int v = atoi(e);
     return (v >= lo && v <= hi) ? v : 0;
 }
+static bool env_flag(const char* name) { return getenv(name) != nullptr; }
+#else
+static int env_int(const char*, int, int) { return 0; }
+static bool env_flag(const char*) { return false; }
+#endif
 
 // Candidate slots per row list.  The list keeps the row's best `cand` FP16 scores; stage 2 proves a row only if its k-th
 // exact score clears the list's drop bound by the FP16 error, so cand - top_k is the number of near-cut columns a row may
@@ -1119,7 +1127,7 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     pl->seed_stride = pl->seed_q = 0;
     // (the seed pass is never column-split, so with many splits it would cost as much as the main pass)
     const bool forced = env_int("SNG_KNN_SEED_S", 2, 256) != 0;
-    if (top_k > 0 && (ns <= 2 || forced) && !getenv("SNG_KNN_NOSEED")) {
+    if (top_k > 0 && (ns <= 2 || forced) && !env_flag("SNG_KNN_NOSEED")) {
         if (forced) {
             const int stride = env_int("SNG_KNN_SEED_S", 2, 256);
             int q = env_int("SNG_KNN_SEED_Q", 1, kSeedGroups - 2);
@@ -1166,7 +1174,7 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
     p.seeds = seed_pass ? nullptr : seeds; p.seed_out = seed_out; p.seed_q = pl.seed_q; p.seed_stride = pl.seed_stride > 0 ? pl.seed_stride : 1;
     dim3 grid((unsigned)(2 * ((nq + 2 * BM - 1) / (2 * BM))), (unsigned)p.nsplit);        // x: CTA pairs (cluster of 2), y: column splits
     p.trace = nullptr;
-    if (getenv("SNG_KNN_TRACE") && !seed_pass) {              // debugging aid only: allocates, synchronises and prints
+    if (env_flag("SNG_KNN_TRACE") && !seed_pass) {              // debugging aid only: allocates, synchronises and prints
         cudaMalloc(&p.trace, (64 * 8 + 16) * sizeof(long long));
         cudaMemset(p.trace, 0, (64 * 8 + 16) * sizeof(long long));
     }
@@ -1306,7 +1314,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     // retry plan (decided up front: it determines where stage 2 files the rows it cannot prove): the longest list that fits
     Plan pr;
     bool retry = false;
-    if (!getenv("SNG_KNN_NORETRY")) {
+    if (!env_flag("SNG_KNN_NORETRY")) {
         const int want = top_k + 32 <= 64 ? 64 : (top_k + 32 <= 96 ? 96 : 128);
         for (int rcand = want; rcand >= top_k + 8 && !retry; rcand -= 16) {
             if (make_plan(&pr, kRetryRows, n, d, 0, rcand, pl.ew) != SNG_OK || pr.ew != pl.ew) continue;
@@ -1324,7 +1332,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     if (pl.seed_stride > 0)
         if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, nullptr, nullptr, nullptr, nullptr, seeds, nullptr, st)) return rc;
     if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min,
-                               pl.seed_stride > 0 ? seeds : nullptr, nullptr, getenv("SNG_KNN_NOPHASE") ? nullptr : phase, st)) return rc;
+                               pl.seed_stride > 0 ? seeds : nullptr, nullptr, env_flag("SNG_KNN_NOPHASE") ? nullptr : phase, st)) return rc;
     const int d4 = (int)((d + 3) / 4);
     // stage 2 flags the rows it cannot prove: into the retry list when there is a retry pass, else straight into the scan list
     int* flag_rows = retry ? fb_rows : fb2_rows;

@@ -275,12 +275,11 @@ class PPFuse(torch.autograd.Function):
         g = g.contiguous()
         dbeta = torch.empty(1, dtype=torch.float32, device=g.device)
         part = torch.empty(_C.PARTIALS, dtype=torch.float32, device=g.device)
-        _C.call("sng_pp_beta_grad", g, _C.ptr(out0), _C.ptr(out1), _C.ptr(g), g.numel(), _C.ptr(dbeta), _C.ptr(part))
-        g0 = g * beta
-        dout1 = g - g0
+        g0, dout1, dwt = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g)
         # dL/dW^T = A^T g0: row t gathers g0 over the (shifted) sources of t's in-edges
-        dwt = spmm(g0, graph.rowptr_in, graph.col_in_shift, n)
-        dw = dwt[:, :c].t()
+        _C.call("sng_pp_fuse_bwd", g, _C.ptr(out0), _C.ptr(out1), _C.ptr(g), _C.ptr(beta), n, cp, cp, _C.ptr(graph.rowptr_in),
+                _C.ptr(graph.col_in_shift), _C.ptr(dbeta), _C.ptr(part), _C.ptr(g0), _C.ptr(dout1), _C.ptr(dwt))
+        dw = (dwt if cp == c else dwt[:, :c]).t()
         db_w = g0.sum(0)[:c]
         dbias = g.sum(0)[:c] if ctx.has_bias else None
         return dout1, dw, db_w, dbeta, dbias, None

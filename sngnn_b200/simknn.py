@@ -61,14 +61,30 @@ def build_knn(x, top_k, thr=-1.0, remove_self=True, q_lo=0, q_hi=None, return_fa
     return build_knn_normalized(xf, xh, x.size(1), top_k, thr, remove_self, q_lo, q_hi, return_fallback)
 
 
-def knn_to_csr(idx, cnt):
-    """CSR neighbour lists (rowptr int32 [nq+1], col int32 [nnz]) + gather index into the flattened [nq*k] lists."""
+def knn_to_csr(idx, cnt, sim=None):
+    """CSR neighbour lists of fixed-width kNN lists (sng_knn_to_csr: exclusive scan + compaction on the device):
+    rowptr int32 [nq+1], col int32 [nnz] (rank order within a row) and, with `sim`, val float32 [nnz]."""
+    if not idx.is_cuda:                                      # host lists (tests of the host logic): same result with torch ops
+        nq, k = idx.shape
+        rowptr = torch.zeros(nq + 1, dtype=torch.int64)
+        torch.cumsum(cnt.long().clamp(0, k), 0, out=rowptr[1:])
+        keep = torch.arange(k)[None, :] < cnt[:, None]
+        flat = keep.reshape(-1).nonzero().flatten()
+        out = (rowptr.to(torch.int32), idx.reshape(-1)[flat].contiguous())
+        return out + ((sim.reshape(-1)[flat].contiguous(),) if sim is not None else ())
+    _C.require_cuda(idx, cnt, sim)
+    idx, cnt = idx.contiguous(), cnt.contiguous()
     nq, k = idx.shape
-    rowptr = torch.zeros(nq + 1, dtype=torch.int64, device=idx.device)
-    torch.cumsum(cnt.long(), 0, out=rowptr[1:])
-    keep = torch.arange(k, device=idx.device)[None, :] < cnt[:, None]
-    flat = keep.reshape(-1).nonzero().flatten()
-    return rowptr.to(torch.int32), idx.reshape(-1)[flat].contiguous(), flat
+    dev = idx.device
+    rowptr = torch.empty(nq + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(nq * k, dtype=torch.int32, device=dev)
+    val = torch.empty(nq * k, dtype=torch.float32, device=dev) if sim is not None else None
+    wbytes = _C.lib().sng_knn_to_csr_workspace_bytes(nq)
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    _C.call("sng_knn_to_csr", idx, _C.ptr(idx), _C.ptr(None if sim is None else sim.contiguous()), _C.ptr(cnt), nq, k, _C.ptr(rowptr), _C.ptr(col),
+            _C.ptr(val), _C.ptr(ws), wbytes)
+    nnz = int(rowptr[-1])
+    return (rowptr, col[:nnz]) + ((val[:nnz],) if sim is not None else ())
 
 
 def build_plan(nq, n, d, top_k):

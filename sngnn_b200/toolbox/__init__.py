@@ -7,6 +7,7 @@ from .dense import (node_similarity_dense_small, node_similarity_dense_large_par
                     class_similarity_dense_large, linked_node_similarity_dense_large, linked_node_similarity_dense_small,
                     neighborhood_similarity_dense_large, neighborhood_similarity_dense_small, cosine_similarity_dense_small,
                     cosine_similarity, edge_similarity_weight)
+from . import sharded  # noqa: F401  (row-sharded forms: one all-reduce of the class sums)
 from .sparse import (cosine_similarity_sparse, class_similarity_sparse, neighborhood_similarity_sparse, node_similarity_sparse,
                      linked_node_similarity_sparse, edge_index_to_sparse_csc_tensor)
 

@@ -82,9 +82,13 @@ def linked_node_similarity_dense_large(x, edge_index):
 
 
 def _per_source_mean(s, src_ids, length):
-    tot = torch.zeros(length, dtype=s.dtype, device=s.device).index_add_(0, src_ids, s)
-    deg = torch.zeros(length, dtype=s.dtype, device=s.device).index_add_(0, src_ids, torch.ones_like(s))
-    return tot / deg.clamp(min=1)
+    """scatter_mean of the edge scores by source id (R: SimGFAToolbox/dense.py:163, :86-97): sng_segment_mean, FP64 accumulation."""
+    seg = src_ids.to(torch.int32).contiguous()
+    out = torch.empty(length, dtype=torch.float32, device=s.device)
+    wbytes = 12 * length + 256
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=s.device)
+    _C.call("sng_segment_mean", s, _C.ptr(s.contiguous()), _C.ptr(seg), seg.numel(), length, _C.ptr(out), _C.ptr(ws), wbytes)
+    return out
 
 
 def neighborhood_similarity_dense_small(x, edge_index):

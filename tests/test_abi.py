@@ -152,5 +152,7 @@ def test_knn_to_csr_host_logic():
     from sngnn_b200 import simknn
     idx = torch.tensor([[4, 2, -1], [-1, -1, -1], [0, 1, 3]], dtype=torch.int32)
     cnt = torch.tensor([2, 0, 3], dtype=torch.int32)
-    rowptr, col, flat = simknn.knn_to_csr(idx, cnt)
-    assert rowptr.tolist() == [0, 2, 2, 5] and col.tolist() == [4, 2, 0, 1, 3] and flat.tolist() == [0, 1, 6, 7, 8]
+    sim = torch.arange(9.0).reshape(3, 3)
+    rowptr, col, val = simknn.knn_to_csr(idx, cnt, sim)
+    assert rowptr.tolist() == [0, 2, 2, 5] and col.tolist() == [4, 2, 0, 1, 3] and val.tolist() == [0.0, 1.0, 6.0, 7.0, 8.0]
+    assert len(simknn.knn_to_csr(idx, cnt)) == 2

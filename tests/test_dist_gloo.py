@@ -169,3 +169,51 @@ def test_sharded_training_step_world2_matches_unsharded_oracle():
             p.join(180)
             assert p.exitcode == 0, f"{kind}: worker exited with {p.exitcode}"
         assert dict(ret) == {0: True, 1: True}
+
+
+def _toolbox_worker(rank, ws, port, n, ret):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    import torch.nn.functional as F
+    from sngnn_b200 import dist as D, synth
+    from sngnn_b200.toolbox import sharded as TS
+    from oracle import toolbox_ref
+    d, k = 9, 4
+    x = synth.make_features(n, d, "clustered", seed=3)
+    y = synth.make_labels(n, k, seed=4)
+    ei = synth.make_graph(n, 5 * n, seed=5, hub_offset=2.0)
+    lo, hi = D.shard_bounds(n, ws, rank)
+
+    def class_sums(xl, yl, kk):                                  # CPU stand-in of K0 + sng_class_sums_f64 on the local rows
+        xh = F.normalize(xl.float(), dim=-1).double()
+        yy = torch.zeros(xl.size(0), dtype=torch.long) if yl is None else yl
+        s = torch.zeros(kk, xl.size(1), dtype=torch.float64).index_add_(0, yy, xh)
+        return s, torch.bincount(yy, minlength=kk).double()
+
+    _, m = TS.node_similarity_dense_large_parted_sharded(x[lo:hi], n, class_sums=class_sums)
+    assert torch.allclose(m, toolbox_ref.node_similarity_dense_large_parted(x)[1], rtol=1e-4)
+    cs = TS.class_similarity_dense_large_sharded(x[lo:hi], y[lo:hi], k, class_sums=class_sums)
+    assert torch.allclose(cs, toolbox_ref.class_similarity_dense_large(x, y), rtol=1e-4, atol=1e-6)
+    s, mean = TS.linked_node_similarity_dense_sharded(x[lo:hi], ei, n, edge_cos=lambda xh, a, b: (xh[a] * xh[b]).sum(-1))
+    ref_s, ref_mean = toolbox_ref.linked_node_similarity_dense_small(x, ei)
+    per = (ei.size(1) + ws - 1) // ws
+    assert torch.allclose(s, ref_s.flatten()[rank * per:(rank + 1) * per], atol=1e-6) and torch.allclose(mean, ref_mean, atol=1e-6)
+    ret[rank] = True
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_toolbox_reductions_world2_match_unsharded_oracle():
+    """Sim-GFA metrics from row shards (SURVEY.md §8(e) 'toolbox reductions'): class sums all-reduced, edge means all-reduced."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_toolbox_worker, args=(r, 2, port, 57, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0, f"worker exited with {p.exitcode}"
+    assert dict(ret) == {0: True, 1: True}

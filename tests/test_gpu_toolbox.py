@@ -69,3 +69,32 @@ def test_class_sums_large_shape():
     cnt = torch.bincount(y, minlength=k).double()
     ref = (s @ s.t()) / (cnt[:, None] * cnt[None, :])
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-9)
+
+
+def test_cosine_similarity_noeps_and_knn_to_csr_and_segment_mean():
+    """R: utils/data_transform.py:83-86 (x / ||x|| without eps: an all-zero row gives NaN rows / columns), the CSR emit of the
+    kNN lists (sng_knn_to_csr) and the scatter_mean replacement (sng_segment_mean) against torch."""
+    from oracle import toolbox_ref
+    from sngnn_b200 import simknn
+    import sngnn_b200.toolbox.dense as D
+    torch.manual_seed(1)
+    x = torch.randn(300, 17)
+    x[5] = 0
+    got = D.cosine_similarity(x)
+    ref = toolbox_ref.cosine_similarity_noeps(x)
+    assert torch.equal(torch.isnan(got), torch.isnan(ref))
+    m = ~torch.isnan(ref)
+    torch.testing.assert_close(got[m], ref[m], rtol=1e-5, atol=1e-6)
+    # kNN lists -> CSR on the device == the host construction
+    xd = torch.randn(2000, 33, device="cuda")
+    idx, sim, cnt = simknn.build_knn(xd, 7, 0.2, True)
+    rp, col, val = simknn.knn_to_csr(idx, cnt, sim)
+    rp_h, col_h, val_h = simknn.knn_to_csr(idx.cpu(), cnt.cpu(), sim.cpu())
+    assert torch.equal(rp.cpu(), rp_h) and torch.equal(col.cpu(), col_h) and torch.equal(val.cpu(), val_h)
+    # segmented mean
+    s = torch.randn(50000, device="cuda")
+    seg = torch.randint(0, 997, (50000,), device="cuda")
+    out = D._per_source_mean(s, seg, 1000)
+    tot = torch.zeros(1000, dtype=torch.float64, device="cuda").index_add_(0, seg, s.double())
+    c = torch.bincount(seg, minlength=1000).clamp(min=1)
+    torch.testing.assert_close(out.double(), tot / c, rtol=1e-6, atol=1e-7)
