@@ -46,6 +46,10 @@ SNG_API int sng_version(void);
 SNG_API const char* sng_last_error(void);
 /* SM count / compute capability of the current device; fails (SNG_ERR_CUDA) when there is no GPU. */
 SNG_API int sng_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Tests / experiments only: while enabled, the similarity-kNN planner honours its SNG_KNN_* environment overrides (seed
+ * stride / quantile, candidate slots, ring depth ...).  Off by default: the library then never reads the environment.
+ * Returns the previous setting. */
+SNG_API int sng_set_debug_env(int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * K0  row normalisation: xhat = x / max(||x||_2, 1e-12)

@@ -17,6 +17,7 @@ SIGNATURES = {
     "sng_version": (_I32, []),
     "sng_last_error": (ctypes.c_char_p, []),
     "sng_device_info": (_I32, [_P, _P, _P]),
+    "sng_set_debug_env": (_I32, [_I32]),
     "sng_rownorm_f32": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P, _P]),
     "sng_edge_fwd_workspace_bytes": (_SZ, [_I64, _I64, _I32]),
     "sng_edge_fwd": (_I32, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _I64, _P, _SZ, _I32, _F32, _P, _I64,

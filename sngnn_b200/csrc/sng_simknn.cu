@@ -1053,20 +1053,18 @@ static size_t smem_bytes(int ew, int kblocks, int stages, int cand, int qcap) {
            8 * (2 * kMaxStages + 9) + 16;
 }
 
-// Tuning / debugging overrides through environment variables exist only in instrumented builds (make EXTRA=-DSNG_KNN_INSTRUMENT):
-// the product library reads no environment and keeps no global state besides the cached SM count and driver entry point.
-#ifdef SNG_KNN_INSTRUMENT
+// Tuning / debugging overrides through environment variables are OFF unless a test or experiment switches them on with
+// sng_set_debug_env(1): the product call path reads no environment (one static flag is tested instead) and keeps no other
+// global state besides the cached SM count and driver entry point.
+static int g_debug_env = 0;
 static int env_int(const char* name, int lo, int hi) {
+    if (!g_debug_env) return 0;
     const char* e = getenv(name);
     if (!e) return 0;
     const int v = atoi(e);
     return (v >= lo && v <= hi) ? v : 0;
 }
-static bool env_flag(const char* name) { return getenv(name) != nullptr; }
-#else
-static int env_int(const char*, int, int) { return 0; }
-static bool env_flag(const char*) { return false; }
-#endif
+static bool env_flag(const char* name) { return g_debug_env && getenv(name) != nullptr; }
 
 // Candidate slots per row list.  The list keeps the row's best `cand` FP16 scores; stage 2 proves a row only if its k-th
 // exact score clears the list's drop bound by the FP16 error, so cand - top_k is the number of near-cut columns a row may
@@ -1225,6 +1223,8 @@ using namespace sng;
 using namespace sng::knn;
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" int sng_set_debug_env(int enabled) { const int was = sng::knn::g_debug_env; sng::knn::g_debug_env = enabled ? 1 : 0; return was; }
 
 extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, int top_k) {
     if (nq <= 0 || n <= 0 || d <= 0 || top_k <= 0 || top_k > SNG_KNN_MAX_TOPK) return 0;

@@ -5,6 +5,16 @@ import torch
 from parity import compare_lists, check_tie_order
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def debug_env():
+    """The planner's SNG_KNN_* overrides are read only while a test switches them on (include/sng.h: sng_set_debug_env)."""
+    from sngnn_b200 import _C
+    _C.lib().sng_set_debug_env(1)
+    yield
+    _C.lib().sng_set_debug_env(0)
+
 DEV = "cuda"
 
 
@@ -152,7 +162,7 @@ def test_seed_pass_group_maxima(n, d, stride, ew):
 @pytest.mark.parametrize("n,d,k,thr,rs,kind,stride,q", [(20000, 65, 10, -1.0, True, "normal", 2, 0), (20000, 65, 10, 0.5, True, "clustered", 2, 0),
                                                          (36000, 128, 5, -1.0, False, "clustered", 4, 0), (20000, 40, 10, -1.0, True, "normal", 2, 1),
                                                          (24000, 200, 10, 0.2, True, "clustered", 2, 0), (70000, 300, 50, -1.0, True, "clustered", 32, 0)])
-def test_seeded_build_matches_oracle(n, d, k, thr, rs, kind, stride, q, monkeypatch):
+def test_seeded_build_matches_oracle(n, d, k, thr, rs, kind, stride, q, monkeypatch, debug_env):
     """Full build with threshold seeding switched on (SNG_KNN_SEED_S shrinks the stride so it engages at test sizes;
     q = 1 makes the seeded threshold far too aggressive, so the proof must send many rows to the exact scan)."""
     from sngnn_b200 import simknn
@@ -192,7 +202,7 @@ def test_default_plan_build_matches_oracle(n, d, k):
     assert check_tie_order(idx, sim, cnt)
 
 
-def test_build_without_retry_pass_matches_oracle(monkeypatch):
+def test_build_without_retry_pass_matches_oracle(monkeypatch, debug_env):
     """SNG_KNN_NORETRY: unproven rows go straight to the exact scan (the path every row took before the retry pass existed)."""
     from sngnn_b200 import simknn
     monkeypatch.setenv("SNG_KNN_NORETRY", "1")
