@@ -2,7 +2,8 @@
 
   cosine at edges          -> K0 row-normalise + sng_sddmm_dot (never an N x N matrix; R builds one per node, dense.py:53-58)
   sums over all pairs      -> sng_class_sums_f64 closed form <S_a, S_b> (R materialises 1000-row blocks, dense.py:17-27,108-128)
-  the N x N matrix itself  -> sng_allpairs_dense_f32, only for the *_small functions that return it
+  the N x N matrix itself  -> sng_gemm_nt_f16 on the tensor cores (tcgen05 / TMEM / TMA) with the FP16 split x-hat = hi + lo
+                              ([hi|hi|lo] x [hi|lo|hi]^T = FP32 product to ~2^-22), only for the *_small functions that return it
 """
 import torch
 
@@ -35,14 +36,35 @@ def _class_sums(xhat, y=None, num_classes=1):
     return sums, cnt
 
 
+def split_f16_operands(xhat):
+    """A = [hi | hi | lo], B = [hi | lo | hi] (FP16, K' = 3 d padded to a multiple of 8) of the FP32 matrix xhat = hi + lo:
+    one FP16 contraction A B^T over K' then equals xhat xhat^T up to the dropped lo.lo term (~2^-22 for unit rows)."""
+    hi = xhat.half()
+    lo = (xhat - hi.float()).half()
+    n, d = xhat.shape
+    kp = (3 * d + 7) // 8 * 8
+    a = torch.zeros(n, kp, dtype=torch.float16, device=xhat.device)
+    b = torch.zeros(n, kp, dtype=torch.float16, device=xhat.device)
+    a[:, :d], a[:, d:2 * d], a[:, 2 * d:3 * d] = hi, hi, lo
+    b[:, :d], b[:, d:2 * d], b[:, 2 * d:3 * d] = hi, lo, hi
+    return a, b, 3 * d
+
+
+def gemm_nt(a, b, k, row_scale=None, col_scale=None):
+    """out [m, n] float32 = diag(row_scale) (a b^T) diag(col_scale) on the tensor cores (sng_gemm_nt_f16); a [m, lda], b [n, ldb] FP16."""
+    _C.require_cuda(a, b, row_scale, col_scale)
+    m, n = a.size(0), b.size(0)
+    out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    _C.call("sng_gemm_nt_f16", a, _C.ptr(a), a.size(1), _C.ptr(b), b.size(1), m, n, k, _C.ptr(row_scale), _C.ptr(col_scale), _C.ptr(out), n)
+    return out
+
+
 def cosine_similarity_dense_small(x):
     """R: dense.py:138-141 -- the full N x N cosine matrix."""
     src, dev = _dev(x)
     xhat = _normalised(x)
-    n, d = xhat.shape
-    out = torch.empty(n, n, dtype=torch.float32, device=dev)
-    _C.call("sng_allpairs_dense_f32", xhat, _C.ptr(xhat), n, d, d, _C.ptr(out))
-    return out.to(src)
+    a, b, k = split_f16_operands(xhat)
+    return gemm_nt(a, b, k).to(src)
 
 
 def node_similarity_dense_small(x):

@@ -98,3 +98,49 @@ def test_cosine_similarity_noeps_and_knn_to_csr_and_segment_mean():
     tot = torch.zeros(1000, dtype=torch.float64, device="cuda").index_add_(0, seg, s.double())
     c = torch.bincount(seg, minlength=1000).clamp(min=1)
     torch.testing.assert_close(out.double(), tot / c, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,d", [(130, 7), (1000, 65), (3001, 300), (2277, 2325)])
+def test_tensor_core_allpairs_matches_fp64(n, d):
+    """cosine_similarity_dense_small through sng_gemm_nt_f16 (tcgen05, FP16 split hi + lo) against the FP64 product: the split
+    keeps the FP32-level accuracy the goldens were generated with (ragged tile edges and K tails included)."""
+    import sngnn_b200.toolbox.dense as D
+    torch.manual_seed(n + d)
+    x = torch.randn(n, d, device="cuda") * torch.rand(n, 1, device="cuda").mul(3).exp()
+    x[3] = 0
+    got = D.cosine_similarity_dense_small(x).double()
+    xh = torch.nn.functional.normalize(x.double(), dim=-1)
+    ref = xh @ xh.t()
+    # the tensor cores accumulate K' = 3 d products per entry with truncating FP32 adds: ~2.5e-9 per product on unit rows
+    assert (got - ref).abs().max().item() < 2e-6 + 2.5e-9 * 3 * d
+    # plain exact use: small integers in FP16, FP32 accumulation, epilogue scales
+    a = torch.randint(0, 3, (n, d), device="cuda").half()
+    ap = torch.zeros(n, (d + 7) // 8 * 8, dtype=torch.float16, device="cuda")
+    ap[:, :d] = a
+    rs = torch.rand(n, device="cuda")
+    cnt = D.gemm_nt(ap, ap, d, rs, rs)
+    ref = (a.double() @ a.double().t()) * rs.double()[:, None] * rs.double()[None, :]
+    torch.testing.assert_close(cnt.double(), ref, rtol=1e-6, atol=1e-6)
+
+
+def test_sparse_metrics_mid_size_vs_oracle():
+    """Adjacency-as-features metrics at a size where parity is more than the N = 300 golden: tensor-core M^T M with exact
+    0/1 operands, merged-list edge cosines, closed-form class sums -- against the scipy oracle."""
+    import sngnn_b200.toolbox as T
+    from oracle import toolbox_ref
+    from sngnn_b200 import synth
+    n = 3000
+    ei = synth.make_graph(n, 40000, seed=9, symmetric=True, hub_offset=3.0)
+    ei = torch.cat([ei, ei[:, :300]], 1)                                  # duplicate edges: entries of M larger than 1
+    ei = ei[:, (ei[0] * n + ei[1]).argsort(stable=True)]
+    y = synth.make_labels(n, 4, seed=2)
+    xdummy = torch.zeros(n, 1)
+    adj = T.edge_index_to_sparse_csc_tensor(xdummy, ei)
+    for fn, ref_fn, args in ((T.node_similarity_sparse, toolbox_ref.node_similarity_sparse, (adj,)),
+                             (T.linked_node_similarity_sparse, toolbox_ref.linked_node_similarity_sparse, (adj, ei)),
+                             (T.neighborhood_similarity_sparse, toolbox_ref.neighborhood_similarity_sparse, (adj, ei))):
+        got, ref = fn(*args), ref_fn(*args)
+        assert got[0].shape == ref[0].shape
+        _close(got[0], ref[0], rtol=1e-5, atol=1e-6)
+        _close(got[1], ref[1], rtol=1e-5, atol=1e-7)
+    _close(T.class_similarity_sparse(adj, y), toolbox_ref.class_similarity_sparse(adj, y), rtol=1e-5, atol=1e-7)
