@@ -86,7 +86,8 @@ SNG_API int sng_rownorm_f32(const float* x, int64_t n, int64_t d, int64_t ldx,
  * the per-chunk candidates.  n_chunks < 0 = tables unknown: one general kernel then runs every row.
  * Row sharding: the call covers target rows [row_offset, row_offset + n) of `h`, which holds ALL n_total nodes
  * (sources are arbitrary); rowptr / out / sel_* / the chunk tables are local to the shard, `col` holds global source ids.
- * inv_norm [n_total] is filled with 1/max(||h_i||, 1e-12) (a pre-pass of this call) and is an input of the backward.
+ * inv_norm [n_total] is filled with 1/max(||h_i||, 1e-12) (a pre-pass of this call, skipped when inv_norm_ready != 0: the
+ * caller -- sng_lin_norm_fwd -- already produced it) and is an input of the backward.
  */
 SNG_API size_t sng_edge_fwd_workspace_bytes(int64_t n_chunks, int64_t c, int top_k);
 SNG_API int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t row_offset, int64_t c, int64_t ldh,
@@ -94,7 +95,7 @@ SNG_API int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t row
                  const int32_t* chunk_tab, int64_t n_chunks, const int32_t* lrows, const int32_t* lrow_ptr, int64_t n_lrows,
                  const int32_t* rows_hub, int64_t n_hub, void* workspace, size_t workspace_bytes,
                  int top_k, float thr, float* out, int64_t ldo,
-                 int32_t* sel_src, float* sel_w, int32_t* sel_q, int32_t* sel_cnt, float* inv_norm,
+                 int32_t* sel_src, float* sel_w, int32_t* sel_q, int32_t* sel_cnt, float* inv_norm, int inv_norm_ready,
                  const float* wt, int64_t ldw, const float* b_w, const float* beta, const float* bias, float* diff,
                  void* stream);
 
@@ -178,6 +179,16 @@ SNG_API int sng_nll_loss_fwd(const float* logp, int64_t n, int64_t c, int64_t ld
                      float* partials, void* stream);
 SNG_API int sng_nll_loss_bwd(int64_t n, int64_t c, int64_t ld, const int64_t* y, const float* gscale, const float* count, float* dlogp,
                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * lin + bias + 1/norm in one pass:  h [n, cp] = x W^T + b with cp = 4 * ceil(c / 4) zero-padded channels,
+ * inv_norm[i] = 1 / max(||h_i||, 1e-12).  replaces `x = self.lin(x); norm = F.normalize(x)` at R: models/models.py:121-122,
+ * 237-238, 324-325 (FP32 FMA; supported when cp is a power of two in [4, 128] and f * cp <= 24576 -- sng_lin_norm_supported --
+ * otherwise the caller keeps the library GEMM and lets sng_edge_fwd compute inv_norm).  x [n, ldx], w [c, ldw], bias [c] or NULL.
+ */
+SNG_API int sng_lin_norm_supported(int64_t f, int64_t c);
+SNG_API int sng_lin_norm_fwd(const float* x, int64_t n, int64_t f, int64_t ldx, const float* w, int64_t c, int64_t ldw, const float* bias,
+                     float* h, float* inv_norm, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Data formats either side of the path.

@@ -1508,7 +1508,7 @@ extern "C" int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t 
                             const int32_t* chunk_tab, int64_t n_chunks, const int32_t* lrows, const int32_t* lrow_ptr, int64_t n_lrows,
                             const int32_t* rows_hub, int64_t n_hub, void* workspace, size_t workspace_bytes,
                             int top_k, float thr, float* out, int64_t ldo,
-                            int32_t* sel_src, float* sel_w, int32_t* sel_q, int32_t* sel_cnt, float* inv_norm,
+                            int32_t* sel_src, float* sel_w, int32_t* sel_q, int32_t* sel_cnt, float* inv_norm, int inv_norm_ready,
                             const float* wt, int64_t ldw, const float* b_w, const float* beta, const float* bias, float* diff,
                             void* stream) {
     if (int rc = check_rows("sng_edge_fwd", n, c, ldh)) return rc;
@@ -1530,7 +1530,8 @@ extern "C" int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t 
         if (!workspace || workspace_bytes < sng_edge_fwd_workspace_bytes(n_chunks, c, top_k)) { set_error("sng_edge_fwd: workspace too small"); return SNG_ERR_WORKSPACE; }
     }
     cudaStream_t st = (cudaStream_t)stream;
-    SNG_DISPATCH_G(c, row_inv_norm_kernel<G><<<grid_resident(row_inv_norm_kernel<G>, n_total, kWarpsPerBlock * (32 / G) * 4), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm));
+    if (!inv_norm_ready)                                     // (sng_lin_norm_fwd already produced it with h)
+        SNG_DISPATCH_G(c, row_inv_norm_kernel<G><<<grid_resident(row_inv_norm_kernel<G>, n_total, kWarpsPerBlock * (32 / G) * 4), kThreads, 0, st>>>(h, n_total, (int)c, ldh, inv_norm));
     EdgeFwdArgs a;
     a.h = h; a.inv_r = inv_norm; a.n = (int)n; a.row_offset = (int)row_offset; a.c = (int)c; a.ldh = (int)ldh;
     a.rowptr = rowptr; a.col = col; a.tpos = tpos; a.rows = nullptr; a.n_rows = 0; a.skip_deg = 0;

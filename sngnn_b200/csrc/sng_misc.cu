@@ -106,3 +106,147 @@ extern "C" int sng_segment_mean(const float* val, const int32_t* seg, int64_t nu
     segment_finish_kernel<<<grid_1d(n_seg), 256, 0, st>>>(sums, counts, (int)n_seg, out);
     return check_launch("sng_segment_mean");
 }
+
+// ------------------------------------------------------------------------------------------ lin + bias + 1/norm
+// h = x W^T + b with the output width zero-padded to cp, and inv_norm[i] = 1 / max(||h_i||, 1e-12), in one pass over x
+// (R: models/models.py:121-122 `x = self.lin(x); norm = F.normalize(x)`; the library GEMM + separate norm pass it replaces
+// reads h twice more).  FP32 FMA on the CUDA cores: at the shapes of this path (F x C <= 24 K weights) the layer is
+// bound by reading x, not by arithmetic.  Block = 256 threads; a thread owns 4 rows x 4 channels; x is staged TRANSPOSED
+// in K chunks of 32 (one 128-bit shared load = the 4 rows of a thread), W^T chunks beside it.
+namespace sng {
+constexpr int kLinKC = 32;
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool ok) {       // 4-byte async copy; !ok writes a zero
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+
+template <int CG>                                   // CG = cp / 4 channel groups per row (power of two <= 32)
+__global__ void __launch_bounds__(256) lin_norm_kernel(const float* __restrict__ x, int64_t n, int f, int64_t ldx, const float* __restrict__ w, int c,
+                                                      int64_t ldw, const float* __restrict__ bias, float* __restrict__ h, float* __restrict__ inv) {
+    constexpr int KC = CG <= 2 ? 16 : kLinKC;       // K chunk (narrow outputs have 512 / 1024 rows per tile: a shorter chunk keeps the tile in shared memory)
+    constexpr int RG = 256 / CG;                    // row groups per block
+    constexpr int R = RG * 4;                       // rows per block tile
+    constexpr int RS = R;                           // row stride of the transposed x tile; groups of 4 rows are XOR-swizzled by kk & 7
+    constexpr int cp = CG * 4;
+    constexpr int XB = KC * RS, WB = KC * cp;
+    extern __shared__ float sm[];
+    float* xs = sm;                                 // 2 x [KC][RS]   (x chunk, transposed: 4-byte cp.async, two chunks in flight)
+    float* ws = sm + 2 * XB;                        // 2 x [KC][cp]
+    const int cg = threadIdx.x % CG, rg = threadIdx.x / CG;
+    const int nkc = (f + KC - 1) / KC;
+    const int64_t ntiles = (n + R - 1) / R;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nkc;           // flattened (row tile, K chunk) sequence of this block
+
+    auto stage = [&](int64_t it) {                  // chunk `it` -> buffer it & 1 (an empty group beyond the end keeps the counting uniform)
+        if (it < total) {
+            const int64_t r0 = (blockIdx.x + (it / nkc) * gridDim.x) * R;
+            const int k0 = (int)(it % nkc) * KC;
+            float* xb = xs + (it & 1) * XB;
+            float* wb = ws + (it & 1) * WB;
+            // a warp copies 4 rows x 8 consecutive k (32-byte segments of global memory) and stores them transposed: row group
+            // (4 rows = one 128-bit read of the compute loop) XOR (k & 7) makes the 32 stores of a warp hit 32 different banks
+#pragma unroll 4
+            for (int t = threadIdx.x; t < R * KC; t += 256) {
+                const int l = t & 31, s = t >> 5;
+                const int kk = (s % (KC / 8)) * 8 + (l & 7), rr = (s / (KC / 8)) * 4 + (l >> 3);
+                const int64_t row = r0 + rr;
+                if (k0 + kk < f)                                                  // columns beyond f are never read by the compute loop
+                    cp_async4(xb + kk * RS + ((((rr >> 2) ^ (kk & 7))) << 2) + (rr & 3), row < n ? x + row * ldx + k0 + kk : x, row < n);
+            }
+            for (int t = threadIdx.x; t < cp * KC; t += 256) {
+                const int cc = t / KC, kk = t % KC;
+                if (k0 + kk < f) cp_async4(wb + kk * cp + cc, cc < c ? w + (int64_t)cc * ldw + k0 + kk : w, cc < c);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) {
+        b4.x = cg * 4 + 0 < c ? __ldg(bias + cg * 4 + 0) : 0.f; b4.y = cg * 4 + 1 < c ? __ldg(bias + cg * 4 + 1) : 0.f;
+        b4.z = cg * 4 + 2 < c ? __ldg(bias + cg * 4 + 2) : 0.f; b4.w = cg * 4 + 3 < c ? __ldg(bias + cg * 4 + 3) : 0.f;
+    }
+    float acc[4][4];
+    stage(0);
+    for (int64_t it = 0; it < total; ++it) {
+        stage(it + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const int kc = (int)(it % nkc);
+        if (kc == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        }
+        const float* xb = xs + (it & 1) * XB;
+        const float* wb = ws + (it & 1) * WB;
+        const int kmax = min(KC, f - kc * KC);                                    // the K tail is not padded with zero work
+#pragma unroll 8
+        for (int kk = 0; kk < kmax; ++kk) {
+            const float4 xv = *reinterpret_cast<const float4*>(xb + kk * RS + ((rg ^ (kk & 7)) << 2));
+            const float4 wv = *reinterpret_cast<const float4*>(wb + kk * cp + cg * 4);
+            const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][0] = fmaf(xr[i], wv.x, acc[i][0]); acc[i][1] = fmaf(xr[i], wv.y, acc[i][1]);
+                acc[i][2] = fmaf(xr[i], wv.z, acc[i][2]); acc[i][3] = fmaf(xr[i], wv.w, acc[i][3]);
+            }
+        }
+        if (kc == nkc - 1) {
+            const int64_t r0 = (blockIdx.x + (it / nkc) * gridDim.x) * R;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t row = r0 + rg * 4 + i;
+                const float4 o = make_float4(acc[i][0] + b4.x, acc[i][1] + b4.y, acc[i][2] + b4.z, acc[i][3] + b4.w);   // padding channels stay 0
+                float ss = dot4(o, o);
+                ss = group_sum<CG>(ss);                                            // the CG threads of a row are consecutive lanes
+                if (row < n) {
+                    *reinterpret_cast<float4*>(h + row * cp + cg * 4) = o;
+                    if (inv && cg == 0) inv[row] = inv_norm_of(ss);
+                }
+            }
+        }
+        __syncthreads();                                                           // the buffer is refilled by the next stage()
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+}  // namespace sng
+
+extern "C" int sng_lin_norm_supported(int64_t f, int64_t c) {
+    if (f <= 0 || c <= 0) return 0;
+    const int64_t cp = (c + 3) / 4 * 4;
+    return (cp == 4 || cp == 8 || cp == 16 || cp == 32 || cp == 64 || cp == 128) && f * cp <= 24576 ? 1 : 0;
+}
+
+extern "C" int sng_lin_norm_fwd(const float* x, int64_t n, int64_t f, int64_t ldx, const float* w, int64_t c, int64_t ldw, const float* bias,
+                                float* h, float* inv_norm, void* stream) {
+    SNG_REQUIRE(x && w && h && n >= 0 && f > 0 && c > 0 && ldx >= f && ldw >= f, "sng_lin_norm_fwd: bad arguments");
+    SNG_REQUIRE(sng_lin_norm_supported(f, c), "sng_lin_norm_fwd: unsupported shape (f=%lld c=%lld): padded c must be a power of two in [4,128], f*c_padded <= 24576",
+                (long long)f, (long long)c);
+    if (n == 0) return SNG_OK;
+    const int cgn = (int)((c + 3) / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SNG_LIN_LAUNCH(CGV)                                                                                                      \
+    {                                                                                                                            \
+        constexpr int R = (256 / CGV) * 4;                                                                                       \
+        const size_t smem = (size_t)2 * (CGV <= 2 ? 16 : kLinKC) * (R + CGV * 4) * sizeof(float);                                                  \
+        cudaFuncSetAttribute(lin_norm_kernel<CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                      \
+        int occ = 1;                                                                                                             \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lin_norm_kernel<CGV>, 256, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; } \
+        const int64_t need = (n + R - 1) / R, cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * occ;                         \
+        lin_norm_kernel<CGV><<<(unsigned)(need < cap ? need : cap), 256, smem, st>>>(x, n, (int)f, ldx, w, (int)c, ldw, bias, h, inv_norm); \
+    }
+    switch (cgn) {
+        case 1: SNG_LIN_LAUNCH(1) break;
+        case 2: SNG_LIN_LAUNCH(2) break;
+        case 3: case 4: SNG_LIN_LAUNCH(4) break;
+        case 5: case 6: case 7: case 8: SNG_LIN_LAUNCH(8) break;
+        default:
+            if (cgn <= 16) SNG_LIN_LAUNCH(16) else SNG_LIN_LAUNCH(32)
+            break;
+    }
+#undef SNG_LIN_LAUNCH
+    return check_launch("sng_lin_norm_fwd");
+}

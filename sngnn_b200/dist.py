@@ -46,6 +46,14 @@ def all_gather_rows(local, n, out=None, pad=None):
     return out[:n]
 
 
+def half_operand(xf_all, ldh):
+    """FP16 copy [n, ldh] (zero padded) of normalised FP32 rows [n, ld32]: the K1 tensor-core operand, converted locally."""
+    xh = torch.zeros(xf_all.size(0), ldh, dtype=torch.float16, device=xf_all.device)
+    w = min(ldh, xf_all.size(1))
+    xh[:, :w] = xf_all[:, :w]
+    return xh
+
+
 def build_knn_sharded(x_local, n, top_k, thr=-1.0, remove_self=True, normalize=None, build=None):
     """Similarity-kNN of this rank's query rows against all n nodes.
 
@@ -61,8 +69,10 @@ def build_knn_sharded(x_local, n, top_k, thr=-1.0, remove_self=True, normalize=N
         build = build or simknn.build_knn_normalized
     d = x_local.size(1)
     xf, xh = normalize(x_local)                       # K0 on the local shard only
-    xf_all = all_gather_rows(xf, n)                   # FP32 x-hat for the exact rescore
-    xh_all = all_gather_rows(xh, n)                   # FP16 x-hat for the tensor cores
+    xf_all = all_gather_rows(xf, n)                   # ONE collective: FP32 x-hat (needed for the exact rescore anyway)
+    # the tensor-core operand is the FP16 rounding of the same values, so it is converted locally instead of gathered:
+    # bit-identical to what the owning rank's K0 emitted, and it saves the second all-gather (261 of 705 MB at pokec scale)
+    xh_all = half_operand(xf_all, xh.size(1))
     if hi == lo:
         return None
     return build(xf_all, xh_all, d, top_k, thr, remove_self, lo, hi)

@@ -19,6 +19,43 @@ def padded_channels(c):
     return (c + 3) // 4 * 4
 
 
+class LinNorm(torch.autograd.Function):
+    """h [N, Cp] = x W^T + b (channels zero-padded to Cp) and inv_norm = 1 / max(||h_i||, 1e-12) in ONE pass over x
+    (sng_lin_norm_fwd; R: models/models.py:121-122).  Backward is the dense layer's: three library GEMMs / reductions."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cp):
+        _C.require_cuda(x, weight, bias)
+        x = x.contiguous().float()
+        w = weight.contiguous()
+        n, f = x.shape
+        c = w.size(0)
+        h = torch.empty(n, cp, dtype=torch.float32, device=x.device)
+        inv = torch.empty(n, dtype=torch.float32, device=x.device)
+        _C.call("sng_lin_norm_fwd", x, _C.ptr(x), n, f, f, _C.ptr(w), c, f, _C.ptr(None if bias is None else bias.contiguous()), _C.ptr(h), _C.ptr(inv))
+        ctx.save_for_backward(x, w)
+        ctx.has_bias, ctx.c = bias is not None, c
+        ctx.mark_non_differentiable(inv)
+        return h, inv
+
+    @staticmethod
+    def backward(ctx, gh, _ginv):
+        x, w = ctx.saved_tensors
+        g = gh[:, :ctx.c]
+        dx = g @ w if ctx.needs_input_grad[0] else None
+        dw = g.t() @ x if ctx.needs_input_grad[1] else None
+        db = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+def lin_norm(x, weight, bias, cp):
+    """(h [N, Cp], inv_norm [N] | None): the fused kernel when the shape is supported, else library GEMM (inv_norm = None: the
+    aggregation call then computes it)."""
+    if x.is_cuda and _C.lib().sng_lin_norm_supported(x.size(1), weight.size(0)):
+        return LinNorm.apply(x, weight, bias, cp)
+    return linear_padded(x, weight, bias, cp), None
+
+
 def linear_padded(x, weight, bias, cp):
     """h = x @ W^T + b with the output width zero-padded to `cp` (R: models/models.py:121,237,324)."""
     c = weight.size(0)
@@ -35,7 +72,7 @@ def _check_h(h):
     return h.contiguous()
 
 
-def _edge_fwd(h_all, graph, row_offset, k, thr, train, fuse=None, want_q=False):
+def _edge_fwd(h_all, graph, row_offset, k, thr, train, fuse=None, want_q=False, inv_norm=None):
     """sng_edge_fwd on the target rows of `graph` (a PreparedGraph or a row shard of one).  fuse = (wt [N, Cp], b_w [Cp],
     beta [1], bias [Cp] | None) gathers the structural term and blends in the same pass (symmetric graphs only)."""
     c = h_all.size(1)
@@ -49,7 +86,9 @@ def _edge_fwd(h_all, graph, row_offset, k, thr, train, fuse=None, want_q=False):
         sel_cnt = torch.empty(n, dtype=torch.int32, device=dev)
         if want_q:
             sel_q = torch.empty(n, k, dtype=torch.int32, device=dev)
-    inv_norm = torch.empty(h_all.size(0), dtype=torch.float32, device=dev)
+    inv_ready = inv_norm is not None                      # produced with h by sng_lin_norm_fwd
+    if not inv_ready:
+        inv_norm = torch.empty(h_all.size(0), dtype=torch.float32, device=dev)
     wt = bw = beta = bias = None
     if fuse is not None:
         wt, bw, beta, bias = fuse
@@ -66,7 +105,7 @@ def _edge_fwd(h_all, graph, row_offset, k, thr, train, fuse=None, want_q=False):
             _C.ptr(graph.tpos if want_q else None), _C.ptr(tab), n_chunks, _C.ptr(graph.lrows), _C.ptr(graph.lrow_ptr), n_lrows,
             _C.ptr(graph.rows_hub), n_hub, _C.ptr(ws), wbytes, k,
             float(thr if thr is not None else 0.0), _C.ptr(out), c, _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_q), _C.ptr(sel_cnt),
-            _C.ptr(inv_norm), _C.ptr(wt), c, _C.ptr(bw), _C.ptr(beta), _C.ptr(bias), _C.ptr(diff))
+            _C.ptr(inv_norm), int(inv_ready), _C.ptr(wt), c, _C.ptr(bw), _C.ptr(beta), _C.ptr(bias), _C.ptr(diff))
     return out, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff
 
 
@@ -88,7 +127,7 @@ class EdgeAgg(torch.autograd.Function):
     Forward sng_edge_fwd, backward sng_edge_bwd (two gather passes, no float atomics, bit-reproducible)."""
 
     @staticmethod
-    def forward(ctx, h, graph, top_k, thr, w_weight, w_bias, beta, bias):
+    def forward(ctx, h, graph, top_k, thr, w_weight, w_bias, beta, bias, inv_norm=None):
         h = _check_h(h)
         n, cp = h.shape
         if n != graph.n:
@@ -108,7 +147,7 @@ class EdgeAgg(torch.autograd.Function):
             fuse = (_padded_wt(w_weight, cp), F.pad(w_bias.detach(), (0, cp - c)).contiguous(), beta.detach().contiguous(),
                     None if bias is None else F.pad(bias.detach(), (0, cp - c)).contiguous())
             ctx.c = c
-        out, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff = _edge_fwd(h, graph, 0, k, thr, train, fuse, want_q=True)
+        out, sel_src, sel_w, sel_q, sel_cnt, inv_norm, diff = _edge_fwd(h, graph, 0, k, thr, train, fuse, want_q=True, inv_norm=inv_norm)
         ctx.graph, ctx.k, ctx.fused, ctx.has_bias = graph, k, fused, bias is not None
         if record_selection is not None and sel_cnt is not None:
             record_selection.append((sel_src, sel_cnt))
@@ -125,11 +164,11 @@ class EdgeAgg(torch.autograd.Function):
         g = g.contiguous()
         dh, dwt, dbeta = edge_bwd(h, inv_norm, g, graph, k, sel_src, sel_w, sel_q, sel_cnt, beta if fused else None, diff)
         if not fused:
-            return dh, None, None, None, None, None, None, None
+            return dh, None, None, None, None, None, None, None, None
         c = ctx.c
         gsum = g.sum(0)[:c]
         dw = (dwt if cp == c else dwt[:, :c]).t()           # [C, N] in the parameter's own (transposed) layout
-        return dh, None, None, None, dw, gsum * beta, dbeta, (gsum if ctx.has_bias else None)
+        return dh, None, None, None, dw, gsum * beta, dbeta, (gsum if ctx.has_bias else None), None
 
 
 def edge_bwd(h, inv_norm, g, graph, k, sel_src, sel_w, sel_q, sel_cnt, beta=None, diff=None):
@@ -199,10 +238,11 @@ class ShardedEdgeTopkAgg(torch.autograd.Function):
         return dh, None, None, None, None
 
 
-def edge_topk_agg(h, graph, top_k=None, thr=None, return_selection=False, structural=None):
-    """out_1 (structural=None) or the fused SNGNN++ layer output (structural = (w.weight, w.bias, beta, bias))."""
+def edge_topk_agg(h, graph, top_k=None, thr=None, return_selection=False, structural=None, inv_norm=None):
+    """out_1 (structural=None) or the fused SNGNN++ layer output (structural = (w.weight, w.bias, beta, bias)).
+    inv_norm = 1 / max(||h_i||, 1e-12) when the caller already has it (lin_norm), else it is computed here."""
     w_weight, w_bias, beta, bias = structural if structural is not None else (None, None, None, None)
-    out, sel_src, sel_w, sel_cnt = EdgeAgg.apply(h, graph, top_k, thr, w_weight, w_bias, beta, bias)
+    out, sel_src, sel_w, sel_cnt = EdgeAgg.apply(h, graph, top_k, thr, w_weight, w_bias, beta, bias, inv_norm)
     if return_selection:
         return out, (sel_src, sel_w, sel_cnt)
     return out

@@ -26,6 +26,13 @@ def _as_bool(flag):
 
 
 class _SNConvBase(nn.Module):
+    @staticmethod
+    def _check_width(out_channels):
+        # the edge kernels hold a row in at most 32 lanes x 4 channels; fail at construction, not at the first forward
+        if SF.padded_channels(out_channels) > 128:
+            raise ValueError(f"out_channels={out_channels}: the B200 edge kernels support at most 128 channels per layer "
+                             "(the reference accepts any width)")
+
     def _init_bias(self, bias, out_channels):
         if bias:
             self.bias = Parameter(torch.empty(out_channels))
@@ -40,6 +47,10 @@ class _SNConvBase(nn.Module):
         cp = SF.padded_channels(self.lin.out_features)
         return SF.linear_padded(x, self.lin.weight, self.lin.bias, cp)
 
+    def _hidden_norm(self, x):
+        """(h, 1/||h||) -- R: models/models.py:121-122 -- in one pass over x when the shape allows (else inv_norm = None)."""
+        return SF.lin_norm(x, self.lin.weight, self.lin.bias, SF.padded_channels(self.lin.out_features))
+
 
 class SNConv(_SNConvBase):
     """R: models/models.py:305-334 -- cosine-weighted mean over all in-neighbours incl. a self loop."""
@@ -48,6 +59,7 @@ class SNConv(_SNConvBase):
         super().__init__()
         if aggr != "mean":
             raise NotImplementedError("only aggr='mean' (the value every reference call site uses)")
+        self._check_width(out_channels)
         self.lin = nn.Linear(in_channels, out_channels)
         self._init_bias(bias, out_channels)
         self.reset_parameters()
@@ -58,8 +70,8 @@ class SNConv(_SNConvBase):
 
     def forward(self, x, edge_index):
         g = G.prepare(edge_index, x.size(0), remove_self_loops=False)
-        h = self._hidden(x)
-        out = SF.edge_topk_agg(h, g, None, None)[:, :self.lin.out_features]
+        h, inv = self._hidden_norm(x)
+        out = SF.edge_topk_agg(h, g, None, None, inv_norm=inv)[:, :self.lin.out_features]
         if self.bias is not None:
             out = out + self.bias
         return out
@@ -77,6 +89,7 @@ class SNConv_plus(_SNConvBase):
         self.num_nodes = num_nodes
         self.is_remove_self_loops = is_remove_self_loops
         self.candidates, self.denominator = candidates, denominator
+        self._check_width(out_channels)
         self.lin = nn.Linear(in_channels, out_channels)
         self._init_bias(bias, out_channels)
         self.reset_parameters()
@@ -91,7 +104,7 @@ class SNConv_plus(_SNConvBase):
         if self.denominator not in ("candidates", "selected"):
             raise ValueError(f"denominator={self.denominator!r}")
 
-    def _aggregate(self, h, g):
+    def _aggregate(self, h, g, inv=None):
         """out_1 of R: models/models.py:239 / :132.  top_k <= 0: the reference runs zero scatter_max rounds, every weight
         stays 0 and out_1 = 0 (with zero -- not missing -- gradients)."""
         if self.top_k <= 0:
@@ -99,19 +112,20 @@ class SNConv_plus(_SNConvBase):
         if self.candidates == "edges":
             if self.denominator == "selected":
                 h = h if h.requires_grad else h.detach().requires_grad_(torch.is_grad_enabled())   # the lists are only emitted in training mode
-                out1, (_, _, sel_cnt) = SF.edge_topk_agg(h, g, self.top_k, self.thr, return_selection=True)
+                out1, (_, _, sel_cnt) = SF.edge_topk_agg(h, g, self.top_k, self.thr, return_selection=True, inv_norm=inv)
                 if sel_cnt is None:
                     raise RuntimeError("denominator='selected' needs grad mode (the selection lists are not emitted in inference)")
                 scale = (sel_cnt.clamp(min=1).float() * g.inv_deg).reciprocal()      # deg / max(cnt,1)
                 return out1 * scale[:, None]
-            return SF.edge_topk_agg(h, g, self.top_k, self.thr)
+            return SF.edge_topk_agg(h, g, self.top_k, self.thr, inv_norm=inv)
         from . import simknn
         return simknn.allpairs_topk_agg(h, self.top_k, self.thr, bool(self.is_remove_self_loops), self.denominator)
 
     def forward(self, x, edge_index):
         self._check_options()
         g = G.prepare(edge_index, x.size(0), remove_self_loops=bool(self.is_remove_self_loops))
-        out = self._aggregate(self._hidden(x), g)[:, :self.lin.out_features]
+        h, inv = self._hidden_norm(x)
+        out = self._aggregate(h, g, inv)[:, :self.lin.out_features]
         if self.bias is not None:
             out = out + self.bias
         return out
@@ -126,6 +140,7 @@ class SNConv_plus_plus(SNConv_plus):
         if aggr != "mean":
             raise NotImplementedError("only aggr='mean'")
         self.top_k, self.thr = top_k, thr
+        self._check_width(out_channels)
         self.w = nn.Linear(num_nodes, out_channels)
         # w.weight keeps the reference's name and shape [C, N] but lives in TRANSPOSED storage ([N, C] row-major): the
         # kernels gather rows of W^T, the gradient comes out row by row, and Adam (state allocated with preserve_format)
@@ -151,12 +166,12 @@ class SNConv_plus_plus(SNConv_plus):
             raise RuntimeError(f"SNConv_plus_plus was built for num_nodes={self.num_nodes} but got {x.size(0)} rows")
         self._check_options()
         g = G.prepare(edge_index, x.size(0), remove_self_loops=bool(self.is_remove_self_loops))
-        h = self._hidden(x)
+        h, inv = self._hidden_norm(x)
         if self.top_k > 0 and self.candidates == "edges" and self.denominator == "candidates" and g.symmetric:
             # in-lists == out-lists: the structural term rides on the aggregation's own pass over the edges (one kernel)
-            out = SF.edge_topk_agg(h, g, self.top_k, self.thr, structural=(self.w.weight, self.w.bias, self.beta, self.bias))
+            out = SF.edge_topk_agg(h, g, self.top_k, self.thr, structural=(self.w.weight, self.w.bias, self.beta, self.bias), inv_norm=inv)
         else:
-            out = SF.PPFuse.apply(self._aggregate(h, g), self.w.weight, self.w.bias, self.beta, self.bias, g)
+            out = SF.PPFuse.apply(self._aggregate(h, g, inv), self.w.weight, self.w.bias, self.beta, self.bias, g)
         return out[:, :self.lin.out_features]
 
 

@@ -288,3 +288,29 @@ def test_nll_loss_matches_torch_and_is_reproducible(n, c):
     torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-9)
     assert torch.equal(SF.nll_loss(a.detach(), y, mask), la.detach())          # fixed-order reduction
     torch.testing.assert_close(SF.nll_loss(a.detach(), y), F.nll_loss(a.detach(), y), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,f,c", [(1, 3, 2), (5000, 65, 32), (3001, 269, 32), (2277, 2325, 5), (4097, 128, 64), (700, 40, 16)])
+def test_lin_norm_matches_linear_and_normalize(n, f, c):
+    """sng_lin_norm_fwd (lin + bias + 1/norm in one pass, R: models/models.py:121-122) against F.linear / F.normalize, forward
+    and backward; unsupported shapes fall back to the library GEMM with inv_norm = None."""
+    from sngnn_b200 import functional as SF, _C
+    torch.manual_seed(n + f)
+    x = torch.randn(n, f, device=DEV, requires_grad=True)
+    lin = torch.nn.Linear(f, c).to(DEV)
+    cp = SF.padded_channels(c)
+    h, inv = SF.lin_norm(x, lin.weight, lin.bias, cp)
+    assert bool(_C.lib().sng_lin_norm_supported(f, c)) == (inv is not None)
+    ref = F.linear(x, lin.weight, lin.bias)
+    torch.testing.assert_close(h[:, :c], ref, rtol=2e-5, atol=2e-5)
+    assert h.shape == (n, cp) and (cp == c or h[:, c:].abs().max().item() == 0)
+    if inv is not None:
+        torch.testing.assert_close(inv, 1.0 / ref.norm(dim=1).clamp(min=1e-12), rtol=2e-5, atol=0)
+    w = torch.randn(n, cp, device=DEV)
+    (h * w).sum().backward()
+    gx, gw, gb = x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()
+    x.grad = None; lin.zero_grad()
+    (ref * w[:, :c]).sum().backward()
+    torch.testing.assert_close(gx, x.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gw, lin.weight.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(gb, lin.bias.grad, rtol=1e-4, atol=1e-3)
