@@ -11,6 +11,7 @@ namespace sng {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaPeekAtLastError -> SNG_ERR_CUDA + message
 int sm_count();                       // cached; <=0 if no device
+int debug_env_int(const char* name, int lo, int hi);   // tuning override; always 0 unless sng_set_debug_env(1) was called
 
 #define SNG_REQUIRE(cond, ...)                                  \
     do {                                                        \

@@ -829,6 +829,7 @@ struct EdgeBwdArgs {
     // CSR, built like the forward's), each chunk writes partial sums, edge_bwd_source_merge_kernel adds them and finishes
     const int4* chunk_tab; int n_chunks; const int* lrows; const int* lrow_ptr; int n_lrows;
     float* tmp_part;                         // [n_chunks, 3, 4G]
+    int slots;                               // staged source pass: row slots per warp (>= 64: any single item fits)
 };
 
 template <int G, bool SELECT_ALL>
@@ -962,7 +963,11 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(c
     constexpr int C = 4 * G;
     constexpr int RB = staged_row_bytes<G>();
     constexpr int EPW = 32 / G;
-    constexpr int SB = 34 * RB;                 // 32 source rows, h_i, g_i
+    // a stage holds only what a row can need: min(top_k, 32) selected source rows, then h_i and g_i.  (Sized for 32 rows, the
+    // stages cost 9.8 KB per warp at C = 32 and 20 warps fit an SM; at top_k = 10 they cost 3.4 KB and registers set the limit.)
+    const uint32_t KS = (uint32_t)min(a.top_k, 32);
+    const uint32_t SB = (KS + 2u) * RB;
+    const uint32_t HI = KS * RB, GI = HI + RB;  // byte offsets of h_i and g_i inside a stage
     extern __shared__ __align__(128) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t sbase = smem_u32(smraw) + (uint32_t)warp * 2u * SB;
@@ -974,7 +979,7 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(c
     const char* hq = reinterpret_cast<const char*>(a.h + q * 4);
     const int64_t ldhb = (int64_t)a.ld * 4;
     const int egrp = cq_ok ? grp : 64;
-    const uint32_t cp_off = (uint32_t)(grp * RB + q * 16), own_off = (uint32_t)(lane * RB), ch_off = (uint32_t)(ch * 4);
+    const uint32_t cp_off = (uint32_t)(grp * RB + q * 16), own_off = (uint32_t)(min(lane, (int)KS - 1) * RB), ch_off = (uint32_t)(ch * 4);
     const float gscale = a.beta ? 1.0f - __ldg(a.beta) : 1.0f;
     const int stride = gridDim.x * kStWarps;
     const int row0 = blockIdx.x * kStWarps + warp;
@@ -999,8 +1004,8 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(c
                 }
             }
             if (lane < nch) {
-                cp_async16(st0 + 32u * RB + (uint32_t)lane * 16u, a.h + (int64_t)(a.row_offset + row) * a.ld + lane * 4);
-                cp_async16(st0 + 33u * RB + (uint32_t)lane * 16u, a.g + (int64_t)row * a.ldg + lane * 4);
+                cp_async16(st0 + HI + (uint32_t)lane * 16u, a.h + (int64_t)(a.row_offset + row) * a.ld + lane * 4);
+                cp_async16(st0 + GI + (uint32_t)lane * 16u, a.g + (int64_t)row * a.ldg + lane * 4);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1031,7 +1036,7 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(c
         {
             const int cnt = cntA;
             const float invd = __fdividef(1.0f, (float)max(degA, 1)) * gscale;           // g1_i / deg_i = g_i * invd
-            const uint32_t own = stA + own_off, gt = stA + 33u * RB;
+            const uint32_t own = stA + own_off, gt = stA + GI;
             float d = 0.f;
 #pragma unroll
             for (int i = 0; i < G; ++i) {
@@ -1049,7 +1054,7 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(c
             for (int t = 0; t < cnt; ++t) dni = fmaf(__shfl_sync(kFull, wdn, t), lds32(rd + (uint32_t)(t * RB)), dni);
             if (lane < C && ch_ok) {
                 a.dnT[(int64_t)(a.row_offset + row) * a.ld + ch] = dni;
-                if (a.diff) bpart = fmaf(dfA, lds32(rd + 33u * RB), bpart);              // dL/dbeta: diff . g (raw g)
+                if (a.diff) bpart = fmaf(dfA, lds32(rd + GI), bpart);                    // dL/dbeta: diff . g (raw g)
             }
         }
         __syncwarp();
@@ -1073,17 +1078,21 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(c
 }
 
 // Pass S, item = source row (or a <= 32-edge chunk of one, CHUNK): stage = g_i of its out-edges (all of them under the fused
-// epilogue, else only the selected ones) and h_i of the selected ones, slot = edge; the sums are lane = channel.
+// epilogue, else only the selected ones) and h_i of the selected ones; the sums are lane = channel.
+// Staging is COMPACT: an item takes exactly the row slots it needs (FUSE: deg + nsel, else 2 nsel; on average 26 / 14 of the
+// 64 a fixed layout reserves) from the warp's slot pool.  Two items are alive at a time (A = being summed, B = in flight):
+// B goes behind A when it fits there, else to the front of the pool when it fits before A, and otherwise waits until A
+// is done (that item loses its prefetch, nothing else).  The pool is `slots` rows (launcher: 64 -> 8 KB per warp at C = 32,
+// 24+ warps per SM where the fixed two-stage layout allowed 12).
 template <int G, bool FUSE, bool CHUNK>
 __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_source_staged_kernel(const EdgeBwdArgs a) {
     constexpr int C = 4 * G;
     constexpr int RB = 16 * G;                  // no lane-per-row reads here: no padding needed
     constexpr int EPW = 32 / G;
-    constexpr int SB = 64 * RB;                 // 32 g rows, 32 h rows
-    constexpr uint32_t HOFF = 32u * RB;
     extern __shared__ __align__(128) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t sbase = smem_u32(smraw) + (uint32_t)warp * 2u * SB;
+    const int slots = a.slots;
+    const uint32_t sbase = smem_u32(smraw) + (uint32_t)(warp * slots * RB);
     const int q = lane % G, grp = lane / G;
     const bool cq_ok = q * 4 < a.c;
     const int ch = lane % C;
@@ -1092,7 +1101,8 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_source_staged_kernel(c
     const char* gq = reinterpret_cast<const char*>(a.g + q * 4);
     const int64_t ldhb = (int64_t)a.ld * 4, ldgb = (int64_t)a.ldg * 4;
     const int egrp = cq_ok ? grp : 64;
-    const uint32_t cp_off = (uint32_t)(grp * RB + q * 16), ch_off = (uint32_t)(ch * 4);
+    const uint32_t cp_off = (uint32_t)(q * 16), ch_off = (uint32_t)(ch * 4);
+    const unsigned lt_grp = (1u << grp) - 1u;   // edges below this lane's edge inside a copy step
     const float beta = FUSE ? __ldg(a.beta) : 0.f;
     const int stride = gridDim.x * kStWarps;
     const int row0 = blockIdx.x * kStWarps + warp;
@@ -1113,22 +1123,29 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_source_staged_kernel(c
         il = 0; cf = make_float2(0.f, 0.f);
         if ((unsigned)deg <= 32u && lane < deg) { il = __ldg(a.col_out + beg + lane); cf = __ldg(a.coef + beg + lane); }
     };
+    auto need_of = [&](int deg, unsigned selm) { return (unsigned)deg <= 32u ? (FUSE ? deg : __popc(selm)) + __popc(selm) : 0; };
+    // g rows at slots [0, ng) of the item (FUSE: slot = edge, else slot = rank among the selected), h rows of the selected behind them
     auto issue = [&](uint32_t st0, int deg, int il, unsigned selm) {
         if ((unsigned)deg <= 32u) {
             const uint32_t dst = st0 + cp_off;
+            const uint32_t hoff = (uint32_t)((FUSE ? deg : __popc(selm)) * RB);
 #pragma unroll
             for (int st = 0; st < G; ++st) {
                 if (st * EPW < deg) {                                                    // warp-uniform
                     const int i = __shfl_sync(kFull, il, st * EPW + grp);
                     const int e = st * EPW + egrp;
                     const bool sel = e < 32 && ((selm >> e) & 1u);
-                    if (FUSE ? e < deg : sel) cp_async16(dst + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(gq + i * ldgb));
-                    if (sel) cp_async16(dst + HOFF + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(hq + i * ldhb));
+                    const uint32_t rk = (uint32_t)(__popc(selm & ((1u << (st * EPW)) - 1u)) + __popc((selm >> (st * EPW)) & lt_grp));   // selected edges before e
+                    const uint32_t gs = FUSE ? (uint32_t)(st * EPW + grp) : rk;
+                    if (FUSE ? e < deg : sel) cp_async16(dst + gs * RB, reinterpret_cast<const float*>(gq + i * ldgb));
+                    if (sel) cp_async16(dst + hoff + rk * RB, reinterpret_cast<const float*>(hq + i * ldhb));
                 }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // where item B may be staged while item A (slots [bA, bA + nA)) is alive: behind A, in front of A, or nowhere (-1)
+    auto place = [&](int bA, int nA, int nB) { return bA + nA + nB <= slots ? bA + nA : (nB <= bA ? 0 : -1); };
 
     int begA, degA, begB, degB, begC, degC, begD, degD;
     load_rp(row0, begA, degA);
@@ -1138,6 +1155,7 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_source_staged_kernel(c
     load_edges(begA, degA, ilA, cfA);
     load_edges(begB, degB, ilB, cfB);
     unsigned smA = __ballot_sync(kFull, cfA.x != 0.f || cfA.y != 0.f);                   // an unselected edge has both coefficients 0
+    int bA = 0, nA = need_of(degA, smA);
     issue(sbase, degA, ilA, smA);
     // finish operands of row A (non-chunk items): h_j, dnT_j, 1/r_j -- lane = channel, requested one item ahead like the rows
     float hjA = 0.f, dnA = 0.f, irA = 0.f;
@@ -1145,32 +1163,45 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_source_staged_kernel(c
         irA = __ldg(a.inv_r + row0);
         if (ch_ok) { hjA = __ldg(a.h + (int64_t)row0 * a.ld + ch); dnA = __ldg(a.dnT + (int64_t)row0 * a.ld + ch); }
     }
-    uint32_t stA = sbase, stB = sbase + SB;
     for (int row = row0; row < n_items; row += stride) {
         load_rp(row + 3 * stride, begD, degD);
         int ilC; float2 cfC;
         load_edges(begC, degC, ilC, cfC);
         const unsigned smB = __ballot_sync(kFull, cfB.x != 0.f || cfB.y != 0.f);
-        issue(stB, degB, ilB, smB);
+        const int nB = need_of(degB, smB);
+        int bB = place(bA, nA, nB);
+        const bool ahead = bB >= 0;                                                      // warp-uniform
+        if (ahead) issue(sbase + (uint32_t)(bB * RB), degB, ilB, smB);
         float hjB = 0.f, dnB = 0.f, irB = 0.f;
         if (!CHUNK && degB >= 0 && degB <= 32) {
             irB = __ldg(a.inv_r + row + stride);
             if (ch_ok) { hjB = __ldg(a.h + (int64_t)(row + stride) * a.ld + ch); dnB = __ldg(a.dnT + (int64_t)(row + stride) * a.ld + ch); }
         }
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (ahead) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         if (degA <= 32) {                                                                // (degA >= 0 here; longer rows go through the chunk pass)
-            const uint32_t rd = stA + ch_off;
+            const uint32_t rd = sbase + (uint32_t)(bA * RB) + ch_off;
+            const uint32_t rh = rd + (uint32_t)((FUSE ? degA : __popc(smA)) * RB);
             float dval = 0.f, dnj = 0.f, dw = 0.f;
-            for (int e = 0; e < degA; ++e) {
-                const bool sel = (smA >> e) & 1u;                                        // warp-uniform
-                if (FUSE || sel) {
+            if (FUSE) {
+                uint32_t hs = rh;
+                for (int e = 0; e < degA; ++e) {
                     const float gv = lds32(rd + (uint32_t)(e * RB));
-                    if (FUSE) dw += gv;
-                    if (sel) {
+                    dw += gv;
+                    if ((smA >> e) & 1u) {                                               // warp-uniform
                         dval = fmaf(__shfl_sync(kFull, cfA.x, e), gv, dval);
-                        dnj = fmaf(__shfl_sync(kFull, cfA.y, e), lds32(rd + HOFF + (uint32_t)(e * RB)), dnj);
+                        dnj = fmaf(__shfl_sync(kFull, cfA.y, e), lds32(hs), dnj);
+                        hs += RB;
                     }
+                }
+            } else {
+                uint32_t gs = rd, hs = rh;
+                for (unsigned m = smA; m; m &= m - 1u) {                                 // selected edges only, ascending position
+                    const int e = __ffs(m) - 1;
+                    dval = fmaf(__shfl_sync(kFull, cfA.x, e), lds32(gs), dval);
+                    dnj = fmaf(__shfl_sync(kFull, cfA.y, e), lds32(hs), dnj);
+                    gs += RB; hs += RB;
                 }
             }
             if (CHUNK) {
@@ -1190,11 +1221,11 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_source_staged_kernel(c
                 }
             }
         }
-        __syncwarp();
-        begA = begB; degA = degB; ilA = ilB; cfA = cfB; smA = smB; hjA = hjB; dnA = dnB; irA = irB;
+        __syncwarp();                                                                    // A's slots are free from here
+        if (!ahead) { bB = 0; issue(sbase, degB, ilB, smB); }                            // B did not fit next to A: staged now, waited for in full next iteration
+        begA = begB; degA = degB; ilA = ilB; cfA = cfB; smA = smB; hjA = hjB; dnA = dnB; irA = irB; bA = bB; nA = nB;
         begB = begC; degB = degC; ilB = ilC; cfB = cfC;
         begC = begD; degC = degD;
-        const uint32_t t = stA; stA = stB; stB = t;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -1559,17 +1590,24 @@ extern "C" int sng_edge_fwd(const float* h, int64_t n_total, int64_t n, int64_t 
 }
 
 namespace sng {
+// row slots per warp of the staged source pass (see edge_bwd_source_staged_kernel); >= 64 so that any single item fits
+static int source_slots(bool fuse) {
+    const int o = debug_env_int("SNG_K2B_SLOTS", 64, 128);
+    (void)fuse;
+    return o ? o : 64;                      // measured (pokec shape, C = 32): 64 / 72 equal, 80+ slower in both modes (occupancy)
+}
 template <int G>
 static int launch_bwd_target_staged(const EdgeBwdArgs& a, cudaStream_t st) {
-    const size_t ss = (size_t)kStWarps * 2 * 34 * staged_row_bytes<G>();
+    const size_t ss = (size_t)kStWarps * 2 * (size_t)((a.top_k < 32 ? a.top_k : 32) + 2) * staged_row_bytes<G>();
     cudaFuncSetAttribute(edge_bwd_target_staged_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
     const int grid = grid_resident(edge_bwd_target_staged_kernel<G>, a.n, kStWarps, ss, kStWarps * 32);
     edge_bwd_target_staged_kernel<G><<<grid, kStWarps * 32, ss, st>>>(a);
     return grid;
 }
 template <int G, bool FUSE>
-static void launch_bwd_source_staged(const EdgeBwdArgs& a, cudaStream_t st) {
-    const size_t ss = (size_t)kStWarps * 2 * 64 * 16 * G;
+static void launch_bwd_source_staged(EdgeBwdArgs a, cudaStream_t st) {
+    a.slots = source_slots(FUSE);
+    const size_t ss = (size_t)kStWarps * a.slots * 16 * G;
     cudaFuncSetAttribute(edge_bwd_source_staged_kernel<G, FUSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
     edge_bwd_source_staged_kernel<G, FUSE, false><<<grid_resident(edge_bwd_source_staged_kernel<G, FUSE, false>, a.n_total, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
     if (a.n_chunks > 0) {

@@ -1065,6 +1065,10 @@ static int env_int(const char* name, int lo, int hi) {
     return (v >= lo && v <= hi) ? v : 0;
 }
 static bool env_flag(const char* name) { return g_debug_env && getenv(name) != nullptr; }
+}  // namespace knn
+// the same switch for the other translation units (0 = not set / overrides off)
+int debug_env_int(const char* name, int lo, int hi) { return knn::env_int(name, lo, hi); }
+namespace knn {
 
 // Candidate slots per row list.  The list keeps the row's best `cand` FP16 scores; stage 2 proves a row only if its k-th
 // exact score clears the list's drop bound by the FP16 error, so cand - top_k is the number of near-cut columns a row may

@@ -64,6 +64,7 @@ def test_training_trajectory_matches_the_oracle(model):
     data, C = T.load_data("small", 0, "cuda")
     n, fd = data.x.shape
     m = T.build_model(cfg, fd, C, n)
+    m.dropout.p = 0.0                                     # the SNGNN factory call passes no dropout (R: train.py:304): default 0.5
     sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
     m = m.to("cuda")
     opt = torch.optim.Adam(m.parameters(), lr=cfg["lr"], weight_decay=cfg["weight_decay"])
