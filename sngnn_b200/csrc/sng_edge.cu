@@ -96,6 +96,7 @@ struct EdgeFwdArgs {
     float* out; int ldo;
     int* sel_src; float* sel_w; int* sel_q; int* sel_cnt;      // saved for backward; all nullptr in inference
     const float* wt; int ldw; const float* b_w; const float* beta; const float* bias; float* diff;   // fused SNGNN++ epilogue
+    int slots;                               // staged kernel: row slots per warp (>= 33, fused >= 65: any single item fits)
 };
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -142,6 +143,16 @@ __device__ __forceinline__ void write_row(const EdgeFwdArgs& a, int row, int c4,
 // coalesced store.  This kernel is bound by instruction issue, not by memory (ncu: profiles/): every phase is written to
 // keep the per-row instruction count down.
 constexpr int kStWarps = 4;
+// resident CTAs per SM the staged kernels are compiled for (register caps): they are latency / issue bound with few warps
+#ifndef SNG_FWD_MINB
+#define SNG_FWD_MINB 8
+#endif
+#ifndef SNG_BWDT_MINB
+#define SNG_BWDT_MINB 8
+#endif
+#ifndef SNG_BWDS_MINB
+#define SNG_BWDS_MINB 8
+#endif
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -162,15 +173,19 @@ template <int G, bool FUSE>
 constexpr int staged_stage_bytes() { return (FUSE ? 65 : 33) * staged_row_bytes<G>(); }   // 32 source rows + the target row (+ 32 Wt rows)
 
 template <int G, bool FUSE, bool SELECT_ALL, bool CHUNK>
-__global__ void __launch_bounds__(kStWarps * 32) edge_fwd_staged_kernel(const EdgeFwdArgs a) {
+__global__ void __launch_bounds__(kStWarps * 32, SNG_FWD_MINB) edge_fwd_staged_kernel(const EdgeFwdArgs a) {
     constexpr int C = 4 * G;                    // channels of a padded row
     constexpr int RB = staged_row_bytes<G>();
     constexpr int EPW = 32 / G;                 // rows copied per cp.async instruction
-    constexpr int SB = staged_stage_bytes<G, FUSE>();
-    constexpr uint32_t WOFF = 33u * RB;         // Wt rows behind the target row
+    // Compact staging: an item takes deg source rows, the target row (slot deg) and, fused, deg Wt rows behind it from the
+    // warp's pool of `slots` row slots; two items are alive at a time (A = being scored, B = in flight).  B goes behind A
+    // when it fits there, else in front of A when it fits there, else it is staged after A is done (that item loses its
+    // prefetch).  A fixed two-stage layout reserves 2 x 33 (65) slots per warp where an average row needs 20 (39): the pool
+    // is what lets 28-32 warps share an SM instead of 20 (12), and this kernel is latency / issue bound.
     extern __shared__ __align__(128) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t sbase = smem_u32(smraw) + (uint32_t)warp * 2u * SB;
+    const int slots = a.slots;
+    const uint32_t sbase = smem_u32(smraw) + (uint32_t)(warp * slots * RB);
     const int q = lane % G, grp = lane / G;     // copy role: chunk q of the row of edge st * EPW + grp
     const bool cq_ok = q * 4 < a.c;
     const int nch = (a.c + 3) >> 2;             // 16-byte chunks per row that hold data
@@ -181,7 +196,6 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_fwd_staged_kernel(const Ed
     const int64_t ldhb = (int64_t)a.ldh * 4, ldwb = (int64_t)a.ldw * 4;
     const int egrp = cq_ok ? grp : 64;                          // lanes of a chunk beyond the channel count never copy
     const uint32_t cp_off = (uint32_t)(grp * RB + q * 16);      // this lane's copy destination inside a step's EPW slots
-    const uint32_t own_off = (uint32_t)(lane * RB);             // this lane's own row slot (lane = edge)
     const uint32_t ch_off = (uint32_t)(ch * 4);
     float beta = 0.f, bw = 0.f, bb = 0.f;
     if (FUSE) { beta = __ldg(a.beta); if (ch_ok) { bw = __ldg(a.b_w + ch); if (a.bias) bb = __ldg(a.bias + ch); } }
@@ -202,26 +216,29 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_fwd_staged_kernel(const Ed
         }
     };
     auto load_col = [&](int beg, int deg) { return ((unsigned)deg <= 32u && lane < deg) ? __ldg(a.col + beg + lane) : 0; };
-    auto copy_steps = [&](uint32_t dst, int deg, int jl, auto lo, auto hi) {            // steps [lo, hi): per-lane predicates only, no branches
+    auto copy_steps = [&](uint32_t dst, uint32_t woff, int deg, int jl, auto lo, auto hi) {   // steps [lo, hi): per-lane predicates only, no branches
 #pragma unroll
         for (int st = decltype(lo)::value; st < decltype(hi)::value; ++st) {
             const int j = __shfl_sync(kFull, jl, st * EPW + grp);
             if (st * EPW + egrp < deg) {
                 cp_async16(dst + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(hq + j * ldhb));
-                if (FUSE) cp_async16(dst + WOFF + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(wq + j * ldwb));
+                if (FUSE) cp_async16(dst + woff + (uint32_t)(st * EPW * RB), reinterpret_cast<const float*>(wq + j * ldwb));
             }
         }
     };
     auto issue = [&](uint32_t st0, int row, int deg, int jl) {                           // gathers of one item -> one cp.async group (row = target row)
         if ((unsigned)deg <= 32u) {
             const uint32_t dst = st0 + cp_off;
+            const uint32_t woff = (uint32_t)((deg + 1) * RB);                            // Wt rows behind the target row
             constexpr int H = G > 1 ? G / 2 : 1;
-            copy_steps(dst, deg, jl, std::integral_constant<int, 0>{}, std::integral_constant<int, H>{});
-            if (G > 1 && deg > 16) copy_steps(dst, deg, jl, std::integral_constant<int, H>{}, std::integral_constant<int, G>{});
-            if (lane < nch) cp_async16(st0 + 32u * RB + (uint32_t)lane * 16u, a.h + (int64_t)(a.row_offset + row) * a.ldh + lane * 4);
+            copy_steps(dst, woff, deg, jl, std::integral_constant<int, 0>{}, std::integral_constant<int, H>{});
+            if (G > 1 && deg > 16) copy_steps(dst, woff, deg, jl, std::integral_constant<int, H>{}, std::integral_constant<int, G>{});
+            if (lane < nch) cp_async16(st0 + (uint32_t)(deg * RB) + (uint32_t)lane * 16u, a.h + (int64_t)(a.row_offset + row) * a.ldh + lane * 4);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto need_of = [&](int deg) { return (unsigned)deg <= 32u ? (FUSE ? 2 * deg + 1 : deg + 1) : 0; };
+    auto place = [&](int bA, int nA, int nB) { return bA + nA + nB <= slots ? bA + nA : (nB <= bA ? 0 : -1); };
 
     // pipeline registers: item A = being computed, B = gathers in flight, C = source ids in flight, D = rowptr in flight
     int begA, degA, trA, begB, degB, trB, begC, degC, trC, begD, degD, trD;
@@ -230,31 +247,38 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_fwd_staged_kernel(const Ed
     load_rp(row0 + 2 * stride, begC, degC, trC);
     int jlA = load_col(begA, degA), jlB = load_col(begB, degB);
     issue(sbase, trA, degA, jlA);
+    int bA = 0, nA = need_of(degA);
     float irlA = 0.f, iriA = 0.f; int tqA = 0;
     if ((unsigned)degA <= 32u) {
         irlA = lane < degA ? __ldg(a.inv_r + jlA) : 0.f;
         iriA = __ldg(a.inv_r + a.row_offset + trA);
         if (want_q && lane < degA) tqA = __ldg(a.tpos + begA + lane);
     }
-    uint32_t stA = sbase, stB = sbase + SB;
     for (int row = row0; row < n_items; row += stride) {
         // ---- look ahead: rowptr of item + 3 strides, source ids of item + 2, gathers (+ scalars) of item + 1
         load_rp(row + 3 * stride, begD, degD, trD);
         const int jlC = load_col(begC, degC);
-        issue(stB, trB, degB, jlB);
+        const int nB = need_of(degB);
+        int bB = place(bA, nA, nB);
+        const bool ahead = bB >= 0;                                                      // warp-uniform
+        if (ahead) issue(sbase + (uint32_t)(bB * RB), trB, degB, jlB);
+        const uint32_t stA = sbase + (uint32_t)(bA * RB);
         float irlB = 0.f, iriB = 0.f; int tqB = 0;
         if ((unsigned)degB <= 32u) {
             irlB = lane < degB ? __ldg(a.inv_r + jlB) : 0.f;
             iriB = __ldg(a.inv_r + a.row_offset + trB);
             if (want_q && lane < degB) tqB = __ldg(a.tpos + begB + lane);
         }
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (ahead) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         // ---- row A
         if (degA <= 32) {                                                                // (degA >= 0 here)
             const int deg = degA;
             const bool has = lane < deg;
-            const uint32_t own = stA + own_off, tgt = stA + 32u * RB;
+            // lane = edge: its own row slot; lanes without an edge read the target row's slot (inside the item, value unused)
+            const uint32_t tgt = stA + (uint32_t)(deg * RB), own = stA + (uint32_t)(min(lane, deg) * RB);
+            const uint32_t WOFF = (uint32_t)((deg + 1) * RB);
             float d = 0.f;
 #pragma unroll
             for (int i = 0; i < G; ++i) {
@@ -323,11 +347,11 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_fwd_staged_kernel(const Ed
                 }
             }
         }
-        __syncwarp();                                                                    // the stage is overwritten two iterations from now
-        begA = begB; degA = degB; trA = trB; jlA = jlB; irlA = irlB; iriA = iriB; tqA = tqB;
+        __syncwarp();                                                                    // A's slots are free from here
+        if (!ahead) { bB = 0; issue(sbase, trB, degB, jlB); }                            // B did not fit next to A: staged now, waited for in full next iteration
+        begA = begB; degA = degB; trA = trB; jlA = jlB; irlA = irlB; iriA = iriB; tqA = tqB; bA = bB; nA = nB;
         begB = begC; degB = degC; trB = trC; jlB = jlC;
         begC = begD; degC = degD; trC = trD;
-        const uint32_t t = stA; stA = stB; stB = t;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -959,7 +983,7 @@ __global__ void __launch_bounds__(kThreads) edge_bwd_source_kernel(const EdgeBwd
 // Pass T, item = target row: stage = its <= top_k selected source rows (lane = edge for ds_e = <h_j, g_i>, lane = channel for
 // dn_i = sum ds_e n_j), plus h_i and g_i.
 template <int G>
-__global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(const EdgeBwdArgs a) {
+__global__ void __launch_bounds__(kStWarps * 32, SNG_BWDT_MINB) edge_bwd_target_staged_kernel(const EdgeBwdArgs a) {
     constexpr int C = 4 * G;
     constexpr int RB = staged_row_bytes<G>();
     constexpr int EPW = 32 / G;
@@ -1085,7 +1109,7 @@ __global__ void __launch_bounds__(kStWarps * 32) edge_bwd_target_staged_kernel(c
 // is done (that item loses its prefetch, nothing else).  The pool is `slots` rows (launcher: 64 -> 8 KB per warp at C = 32,
 // 24+ warps per SM where the fixed two-stage layout allowed 12).
 template <int G, bool FUSE, bool CHUNK>
-__global__ void __launch_bounds__(kStWarps * 32) edge_bwd_source_staged_kernel(const EdgeBwdArgs a) {
+__global__ void __launch_bounds__(kStWarps * 32, SNG_BWDS_MINB) edge_bwd_source_staged_kernel(const EdgeBwdArgs a) {
     constexpr int C = 4 * G;
     constexpr int RB = 16 * G;                  // no lane-per-row reads here: no padding needed
     constexpr int EPW = 32 / G;
@@ -1498,6 +1522,13 @@ static size_t hub_smem(int top_k) {
     return ((size_t)kWarpsPerBlock * 2 * k1 + 2 * k1 + kWarpsPerBlock + (size_t)kWarpsPerBlock * 2 * 128) * sizeof(float);
 }
 
+// row slots per warp of the staged forward kernel (see there); any single item (33 / fused 65 slots) must fit
+static int forward_slots(bool fuse, int g) {
+    const int o = debug_env_int("SNG_K2_SLOTS", 33, 160);
+    if (o) return o < (fuse ? 65 : 33) ? (fuse ? 65 : 33) : o;
+    (void)g;
+    return fuse ? 66 : 40;                  // measured (pokec shape, C = 32): smaller pools win -- occupancy beats prefetch depth
+}
 template <int G, bool FUSE, bool SELECT_ALL>
 static void launch_edge_fwd(EdgeFwdArgs a, const int32_t* rows_hub, int64_t n_hub, cudaStream_t st) {
     const size_t ls = long_smem(a.top_k), hs = hub_smem(a.top_k);
@@ -1505,7 +1536,8 @@ static void launch_edge_fwd(EdgeFwdArgs a, const int32_t* rows_hub, int64_t n_hu
         if (a.n_chunks >= 0) {
             // degree lists known, rows of <= 128 bytes: staged kernel over the short rows, then over the <= 32-edge chunks of the
             // long rows, then the per-row merge of the chunk candidates
-            const size_t ss = (size_t)kStWarps * 2 * staged_stage_bytes<G, FUSE>();
+            a.slots = forward_slots(FUSE, G);
+            const size_t ss = (size_t)kStWarps * a.slots * staged_row_bytes<G>();
             cudaFuncSetAttribute(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
             edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false><<<grid_resident(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false>, a.n, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
             if (a.n_chunks > 0) {
