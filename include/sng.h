@@ -190,6 +190,16 @@ SNG_API int sng_lin_norm_supported(int64_t f, int64_t c);
 SNG_API int sng_lin_norm_fwd(const float* x, int64_t n, int64_t f, int64_t ldx, const float* w, int64_t c, int64_t ldw, const float* bias,
                      float* h, float* inv_norm, void* stream);
 
+/* Weight / bias gradient of the same layer: dw [c, lddw] = g^T x, db [c] (or NULL) = column sums of g, for g [n, ldg] (the first c
+ * columns are used), x [n, ldx].  One streaming pass over g and x, per-CTA partials summed in a fixed order (bit-reproducible).
+ * replaces the autograd GEMMs of `self.lin` (R: models/models.py:121).  workspace >= sng_lin_bwd_workspace_bytes(n, f, c).
+ * Supported for f <= 128 and ceil(f/4) * ceil(c/4) <= 256 (sng_lin_bwd_supported); wider layers keep the library GEMM. */
+SNG_API int sng_lin_bwd_supported(int64_t f, int64_t c);
+SNG_API size_t sng_lin_bwd_workspace_bytes(int64_t n, int64_t f, int64_t c);
+SNG_API int sng_lin_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, int64_t n, int64_t f, int64_t c, float* dw, int64_t lddw,
+                float* db, void* workspace, size_t workspace_bytes, void* stream);
+
+
 /* ------------------------------------------------------------------------------------------------
  * Data formats either side of the path.
  * sng_knn_to_csr: fixed-width neighbour lists (idx / sim [nq, top_k], cnt [nq], the outputs of sng_simknn_build or the saved

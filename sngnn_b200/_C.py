@@ -24,6 +24,9 @@ SIGNATURES = {
                             _P, _P, _P, _P, _P, _I32, _P, _I64, _P, _P, _P, _P, _P]),
     "sng_lin_norm_supported": (_I32, [_I64, _I64]),
     "sng_lin_norm_fwd": (_I32, [_P, _I64, _I64, _I64, _P, _I64, _I64, _P, _P, _P, _P]),
+    "sng_lin_bwd_supported": (_I32, [_I64, _I64]),
+    "sng_lin_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "sng_lin_bwd": (_I32, [_P, _I64, _P, _I64, _I64, _I64, _I64, _P, _I64, _P, _P, _SZ, _P]),
     "sng_edge_bwd": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _P,
                             _P, _P, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _I64, _P, _P]),
     "sng_edge_agg_bwd": (_I32, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),

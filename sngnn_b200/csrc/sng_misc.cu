@@ -120,6 +120,10 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src, bool ok)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
 }
 
+__device__ __forceinline__ void cp_async16z(float* dst, const float* src, bool ok) {     // 16-byte async copy; !ok writes zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
+
 template <int CG>                                   // CG = cp / 4 channel groups per row (power of two <= 32)
 __global__ void __launch_bounds__(256) lin_norm_kernel(const float* __restrict__ x, int64_t n, int f, int64_t ldx, const float* __restrict__ w, int c,
                                                       int64_t ldw, const float* __restrict__ bias, float* __restrict__ h, float* __restrict__ inv) {
@@ -213,6 +217,255 @@ __global__ void __launch_bounds__(256) lin_norm_kernel(const float* __restrict__
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 }  // namespace sng
+
+// ------------------------------------------------------------------------------------------ lin backward: dW = g^T x, db = sum g
+// The weight gradient of `x = self.lin(x)` (R: models/models.py:121): dW [c, f] = sum_n g[n, :]^T x[n, :], db [c] = sum_n g[n, :].
+// A reduction over N (10^6) rows with a tiny output: the library GEMM runs it as one skinny split-K kernel at 10-20 % of the
+// bandwidth this takes (0.86 ms at the pokec shape, c = 32, f = 65, where reading g and x once costs 0.1 ms).  Here every CTA
+// streams a contiguous range of rows through shared memory (cp.async, two tiles in flight).  A thread owns 4 channels
+// (consecutive) x 4 columns (ft, ft + FT, ft + 2 FT, ft + 3 FT: consecutive lanes read consecutive words, so the tile needs no
+// 16-byte row alignment) of the output in registers; RG row groups of FT x CT threads split the rows of a tile and are
+// summed in shared memory at the end; the CTA writes one partial [c4, 4 FT], and a second kernel adds the partials of all
+// row chunks in a fixed order: deterministic, no float atomics.
+// FLAT staging (x contiguous, ldx == f): a tile of 32 rows is one contiguous, 16-byte aligned block of memory whatever f is
+// (32 f floats), so it is copied with 16-byte cp.async in the layout it has (row stride f) -- a few instructions per tile where
+// element-wise 4-byte copies of rows that start at odd addresses (f = 65) cost more than the arithmetic.
+namespace sng {
+constexpr int kLbRows = 32;                         // rows per shared-memory tile (small tiles: 6-8 CTAs per SM hide the barriers)
+constexpr int kLbMaxF = 128;                        // widest x this kernel takes (one slab of 4 x 32 columns)
+
+struct LinBwdPlan { int ft, ct, rg, threads, nchunk; bool flat; size_t smem; };
+
+template <int RG, bool FLAT>
+__global__ void lin_bwd_partial_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx, int64_t n, int f, int c,
+                                       int FT, int CT, int64_t rows_per_chunk, float* __restrict__ part, float* __restrict__ part_b) {
+    const int fslab = FT * 4, cslab = CT * 4;
+    const int XS = FLAT ? f : fslab, GS = cslab + 4;
+    const int xtile = FLAT ? ((kLbRows * f + 3) & ~3) + 4 * FT : kLbRows * XS;      // FLAT: columns >= f of the last row read (unused) words behind the tile
+    extern __shared__ __align__(16) float lsm[];
+    float* xs = lsm;                                // 2 x xtile
+    float* gs = lsm + 2 * xtile;                    // 2 x [kLbRows][GS]
+    const int tpg = FT * CT;                        // threads per row group
+    const int t = threadIdx.x;
+    const bool active = t < tpg * RG;
+    const int rgi = t / tpg, tt = t % tpg, ft = tt % FT, ct = tt / FT;
+    const int64_t r_beg = (int64_t)blockIdx.x * rows_per_chunk, r_end = min(n, r_beg + rows_per_chunk);
+    const int ntile = r_beg < r_end ? (int)((r_end - r_beg + kLbRows - 1) / kLbRows) : 0;
+    const int c4u = (c + 3) & ~3;
+    const bool g16 = (ldg & 3) == 0 && ldg >= c4u && ((uintptr_t)g & 15) == 0;
+
+    auto stage = [&](int it) {
+        if (it < ntile) {
+            const int64_t r0 = r_beg + (int64_t)it * kLbRows;
+            float* xb = xs + (it & 1) * xtile;
+            float* gb = gs + (it & 1) * kLbRows * GS;
+            const int warp = t >> 5, lane = t & 31, nwarp = blockDim.x >> 5;
+            if (FLAT) {
+                // floats [r0 f, min(r0 + 32, r_end) f) of x: 16-byte chunks, the last one possibly partial (zero filled)
+                const float* src = x + r0 * (int64_t)f;
+                const int64_t valid = (min(r0 + kLbRows, r_end) - r0) * (int64_t)f;   // floats
+                for (int q = t; q * 4 < kLbRows * f; q += blockDim.x) {
+                    const int64_t left = valid - (int64_t)q * 4;
+                    const int bytes = left >= 4 ? 16 : (left > 0 ? (int)left * 4 : 0);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(xb + q * 4)),
+                                 "l"(bytes ? src + q * 4 : x), "r"(bytes) : "memory");
+                }
+            } else {
+                for (int rr = warp; rr < kLbRows; rr += nwarp) {                    // warp per tile row, lanes across the columns
+                    const bool rok = r0 + rr < r_end;
+                    const float* xr = x + (r0 + rr) * ldx;
+                    for (int ff = lane; ff < fslab; ff += 32) {
+                        const bool ok = rok && ff < f;
+                        cp_async4(xb + rr * XS + ff, ok ? xr + ff : x, ok);
+                    }
+                }
+            }
+            for (int rr = warp; rr < kLbRows; rr += nwarp) {
+                const bool rok = r0 + rr < r_end;
+                const float* gr = g + (r0 + rr) * ldg;
+                if (g16) {
+                    for (int q = lane; q < CT; q += 32) {
+                        const bool ok = rok && q * 4 < c4u;
+                        cp_async16z(gb + rr * GS + q * 4, ok ? gr + q * 4 : g, ok);
+                    }
+                } else {
+                    for (int cc = lane; cc < cslab; cc += 32) {
+                        const bool ok = rok && cc < c;
+                        cp_async4(gb + rr * GS + cc, ok ? gr + cc : g, ok);
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[4][4], accb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { accb[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f; }
+    stage(0);
+    for (int it = 0; it < ntile; ++it) {
+        stage(it + 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        if (active) {
+            const float* xb = xs + (it & 1) * xtile + ft;
+            const float* gb = gs + (it & 1) * kLbRows * GS + ct * 4;
+#pragma unroll
+            for (int u = 0; u < kLbRows / RG; ++u) {                               // rows beyond r_end: g was staged as zeros
+                const int rr = rgi + u * RG;
+                const float4 gv = *reinterpret_cast<const float4*>(gb + rr * GS);
+                const float* xr = xb + rr * XS;
+                const float x0 = xr[0], x1 = xr[FT], x2 = xr[2 * FT], x3 = xr[3 * FT];
+                const float gr[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = fmaf(gr[i], x0, acc[i][0]); acc[i][1] = fmaf(gr[i], x1, acc[i][1]);
+                    acc[i][2] = fmaf(gr[i], x2, acc[i][2]); acc[i][3] = fmaf(gr[i], x3, acc[i][3]);
+                }
+            }
+        }
+        if (t < 32) {                                                              // db: warp 0 sums the columns of the g tile (lane = channel)
+            const float* gb = gs + (it & 1) * kLbRows * GS;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int ch = t + 32 * k;
+                if (ch < cslab) {
+#pragma unroll 8
+                    for (int rr = 0; rr < kLbRows; ++rr) accb[k] += gb[rr * GS + ch];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (t < 32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (t + 32 * k < cslab) part_b[(size_t)blockIdx.x * cslab + t + 32 * k] = accb[k];
+    }
+    // sum over the row groups in a fixed order, through shared memory (the tiles are dead): red[rg][tt][16]
+    float* red = lsm;
+    if (active) {
+        float* o = red + ((size_t)rgi * tpg + tt) * 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[i * 4 + j] = acc[i][j];
+    }
+    __syncthreads();
+    for (int i = t; i < tpg * 16; i += blockDim.x) {
+        const int tt2 = i >> 4, e = i & 15;
+        float sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < RG; ++r) sum += red[((size_t)r * tpg + tt2) * 16 + e];
+        const int ft2 = tt2 % FT, ct2 = tt2 / FT;
+        part[((size_t)blockIdx.x * cslab + ct2 * 4 + (e >> 2)) * fslab + ft2 + (e & 3) * FT] = sum;
+    }
+}
+
+// one warp per output element: lanes stride over the row chunks, then a fixed shuffle tree (deterministic).  A thread per
+// output walking ~1000 partials serially took longer than the streaming pass itself.
+__global__ void __launch_bounds__(256) lin_bwd_finish_kernel(const float* __restrict__ part, const float* __restrict__ part_b, int nchunk, int cslab, int fslab,
+                                                            int c, int f, float* __restrict__ dw, int64_t lddw, float* __restrict__ db) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int fe = db ? f + 1 : f;
+    if (i >= c * fe) return;
+    const int cc = i / fe, ff = i % fe;
+    const float* p0 = ff < f ? part + (size_t)cc * fslab + ff : part_b + cc;
+    const size_t stride = ff < f ? (size_t)cslab * fslab : (size_t)cslab;
+    float s = 0.f;
+    for (int k = lane; k < nchunk; k += 32) s += __ldg(p0 + (size_t)k * stride);
+    s = group_sum<32>(s);
+    if (lane == 0) {
+        if (ff < f) dw[(int64_t)cc * lddw + ff] = s;
+        else db[cc] = s;
+    }
+}
+
+template <int RG, bool FLAT>
+static void lin_bwd_launch(const LinBwdPlan& p, int* occ, bool launch, const float* g, int64_t ldg, const float* x, int64_t ldx, int64_t n, int f, int c,
+                           int64_t rows_per_chunk, float* part, float* part_b, cudaStream_t st) {
+    cudaFuncSetAttribute(lin_bwd_partial_kernel<RG, FLAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, lin_bwd_partial_kernel<RG, FLAT>, p.threads, p.smem) != cudaSuccess || *occ < 1)) {
+        cudaGetLastError(); *occ = 1;
+    }
+    if (launch)
+        lin_bwd_partial_kernel<RG, FLAT><<<(unsigned)p.nchunk, p.threads, p.smem, st>>>(g, ldg, x, ldx, n, f, c, p.ft, p.ct, rows_per_chunk, part, part_b);
+}
+#define SNG_LB_DISPATCH(p, ...)                                                                  \
+    switch ((p).rg) {                                                                            \
+        case 1: if ((p).flat) lin_bwd_launch<1, true>(__VA_ARGS__); else lin_bwd_launch<1, false>(__VA_ARGS__); break;    \
+        case 2: if ((p).flat) lin_bwd_launch<2, true>(__VA_ARGS__); else lin_bwd_launch<2, false>(__VA_ARGS__); break;    \
+        case 4: if ((p).flat) lin_bwd_launch<4, true>(__VA_ARGS__); else lin_bwd_launch<4, false>(__VA_ARGS__); break;    \
+        case 8: if ((p).flat) lin_bwd_launch<8, true>(__VA_ARGS__); else lin_bwd_launch<8, false>(__VA_ARGS__); break;    \
+        case 16: if ((p).flat) lin_bwd_launch<16, true>(__VA_ARGS__); else lin_bwd_launch<16, false>(__VA_ARGS__); break; \
+        default: if ((p).flat) lin_bwd_launch<32, true>(__VA_ARGS__); else lin_bwd_launch<32, false>(__VA_ARGS__); break; \
+    }
+
+static LinBwdPlan lin_bwd_plan(int64_t n, int64_t f, int64_t c, bool flat) {
+    LinBwdPlan p;
+    p.flat = flat;
+    p.ft = (int)((f + 3) / 4);                                                     // <= 32
+    p.ct = (int)((c + 3) / 4);                                                     // <= 32
+    int rg = 1;
+    while (rg < 32 && p.ft * p.ct * rg * 2 <= 256) rg *= 2;                        // power of two: the row loop is unrolled at compile time
+    p.rg = rg;
+    p.threads = (p.ft * p.ct * p.rg + 31) / 32 * 32;
+    if (p.threads > 1024) p.threads = 1024;
+    const size_t xtile = flat ? (size_t)((kLbRows * f + 3) & ~(int64_t)3) + 4 * p.ft : (size_t)kLbRows * p.ft * 4;
+    const size_t tiles = (2 * xtile + (size_t)2 * kLbRows * (p.ct * 4 + 4)) * sizeof(float);
+    const size_t red = (size_t)p.ft * p.ct * p.rg * 16 * sizeof(float);
+    p.smem = tiles > red ? tiles : red;
+    int occ = 1;
+    SNG_LB_DISPATCH(p, p, &occ, false, nullptr, 0, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr)
+    const int64_t sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t want = sms * occ;                                                      // one resident wave of CTAs
+    const int64_t max_chunks = (n + 4 * kLbRows - 1) / (4 * kLbRows);              // at least 4 tiles per CTA
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    p.nchunk = (int)want;
+    return p;
+}
+}  // namespace sng
+
+// one row group must fit 256 threads (f x c <= 4096 outputs): beyond that the SIMT FMA rate, not memory, bounds the kernel and the
+// library GEMM is as fast (measured at f = c = 128)
+extern "C" int sng_lin_bwd_supported(int64_t f, int64_t c) { return f > 0 && c > 0 && f <= sng::kLbMaxF && c <= 128 && ((f + 3) / 4) * ((c + 3) / 4) <= 256 ? 1 : 0; }
+
+extern "C" size_t sng_lin_bwd_workspace_bytes(int64_t n, int64_t f, int64_t c) {
+    if (n <= 0 || !sng_lin_bwd_supported(f, c)) return 256;
+    // chunk count bound that does not depend on the staging mode: one resident wave is at most 32 CTAs per SM
+    const int64_t sms = sng::sm_count() > 0 ? sng::sm_count() : 148;
+    const size_t f4 = (size_t)(f + 3) / 4 * 4, c4 = (size_t)(c + 3) / 4 * 4;
+    return (size_t)(sms * 32) * c4 * (f4 + 1) * sizeof(float) + 256;
+}
+
+extern "C" int sng_lin_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, int64_t n, int64_t f, int64_t c, float* dw, int64_t lddw,
+                           float* db, void* workspace, size_t workspace_bytes, void* stream) {
+    SNG_REQUIRE(dw && n >= 0 && f > 0 && c > 0 && ldg >= c && ldx >= f && lddw >= f, "sng_lin_bwd: bad arguments");
+    SNG_REQUIRE(sng_lin_bwd_supported(f, c), "sng_lin_bwd: unsupported shape (f=%lld c=%lld): f <= 128, c <= 128", (long long)f, (long long)c);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        for (int64_t r = 0; r < c; ++r) if (cudaMemsetAsync(dw + r * lddw, 0, (size_t)f * sizeof(float), st) != cudaSuccess) return check_launch("sng_lin_bwd memset");
+        if (db && cudaMemsetAsync(db, 0, (size_t)c * sizeof(float), st) != cudaSuccess) return check_launch("sng_lin_bwd memset");
+        return SNG_OK;
+    }
+    SNG_REQUIRE(g && x, "sng_lin_bwd: null input");
+    SNG_REQUIRE(workspace && workspace_bytes >= sng_lin_bwd_workspace_bytes(n, f, c), "sng_lin_bwd: workspace too small (%zu < %zu)",
+                workspace_bytes, sng_lin_bwd_workspace_bytes(n, f, c));
+    const bool flat = ldx == f && ((uintptr_t)x & 15) == 0;
+    const LinBwdPlan p = lin_bwd_plan(n, f, c, flat);
+    const int cslab = p.ct * 4, fslab = p.ft * 4;
+    float* part = reinterpret_cast<float*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    float* part_b = part + (size_t)p.nchunk * cslab * fslab;
+    const int64_t rows_per_chunk = ((n + p.nchunk - 1) / p.nchunk + kLbRows - 1) / kLbRows * kLbRows;
+    SNG_LB_DISPATCH(p, p, nullptr, true, g, ldg, x, ldx, n, (int)f, (int)c, rows_per_chunk, part, part_b, st)
+    const int64_t outs = c * (f + (db ? 1 : 0));
+    lin_bwd_finish_kernel<<<(unsigned)((outs + 7) / 8), 256, 0, st>>>(part, part_b, p.nchunk, cslab, fslab, (int)c, (int)f, dw, lddw, db);
+    return check_launch("sng_lin_bwd");
+}
 
 extern "C" int sng_lin_norm_supported(int64_t f, int64_t c) {
     if (f <= 0 || c <= 0) return 0;

@@ -41,11 +41,33 @@ class LinNorm(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gh, _ginv):
         x, w = ctx.saved_tensors
-        g = gh[:, :ctx.c]
-        dx = g @ w if ctx.needs_input_grad[0] else None
-        dw = g.t() @ x if ctx.needs_input_grad[1] else None
-        db = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        dx = gh[:, :ctx.c] @ w if ctx.needs_input_grad[0] else None
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] and _C.lib().sng_lin_bwd_supported(x.size(1), ctx.c):
+            dw, db = lin_bwd(gh, x, ctx.c, want_b)
+        else:
+            g = gh[:, :ctx.c]
+            dw = g.t() @ x if ctx.needs_input_grad[1] else None
+            db = g.sum(0) if want_b else None
         return dx, dw, db, None
+
+
+def lin_bwd(gh, x, c, want_bias=True):
+    """(dW [c, f], db [c] | None) = (gh[:, :c]^T x, column sums of gh[:, :c]) in one streaming pass (sng_lin_bwd): the weight
+    gradient of `self.lin` (R: models/models.py:121).  The library GEMM runs this N-long reduction with a [c, f] output as one
+    skinny kernel at a fraction of the memory bandwidth; fixed-order partial sums make the result bit-reproducible."""
+    _C.require_cuda(gh, x)
+    if gh.stride(1) != 1:
+        gh = gh.contiguous()
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    n, f = x.shape
+    dw = torch.empty(c, f, dtype=torch.float32, device=x.device)
+    db = torch.empty(c, dtype=torch.float32, device=x.device) if want_bias else None
+    nb = _C.lib().sng_lin_bwd_workspace_bytes(n, f, c)
+    ws = torch.empty(nb, dtype=torch.uint8, device=x.device)
+    _C.call("sng_lin_bwd", x, _C.ptr(gh), gh.stride(0), _C.ptr(x), x.stride(0), n, f, c, _C.ptr(dw), f, _C.ptr(db), _C.ptr(ws), nb)
+    return dw, db
 
 
 def lin_norm(x, weight, bias, cp):

@@ -177,6 +177,8 @@ def main(argv=None, log=print):
     if not torch.cuda.is_available():
         raise RuntimeError("sngnn_b200.train needs a CUDA device (there is no CPU path)")
     device = torch.device(cfg["device"])
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     torch.cuda.set_device(device)
     set_random_seed(cfg["seed"])
     log(f"Config:\n{cfg}")

@@ -314,3 +314,41 @@ def test_lin_norm_matches_linear_and_normalize(n, f, c):
     torch.testing.assert_close(gx, x.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(gw, lin.weight.grad, rtol=1e-4, atol=1e-3)
     torch.testing.assert_close(gb, lin.bias.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,f,c", [(1000, 65, 32), (5000, 128, 5), (777, 32, 2), (300, 100, 7), (2000, 128, 32), (64, 7, 1),
+                                   (70001, 65, 32), (33, 66, 3), (0, 16, 4)])
+def test_lin_bwd_weight_gradient(n, f, c):
+    """dW = g^T x and db = sum g (sng_lin_bwd) against FP64; bit-reproducible."""
+    from sngnn_b200 import functional as SF
+    torch.manual_seed(n + f + c)
+    cp = SF.padded_channels(c)
+    gh = torch.randn(n, cp, device=DEV)
+    x = torch.randn(n, f, device=DEV)
+    dw, db = SF.lin_bwd(gh, x, c)
+    ref_w = gh[:, :c].double().t() @ x.double()
+    ref_b = gh[:, :c].double().sum(0)
+    scale = ref_w.abs().max().item() + 1e-12
+    assert (dw.double() - ref_w).abs().max().item() / scale < 1e-5
+    assert (db.double() - ref_b).abs().max().item() / (ref_b.abs().max().item() + 1e-12) < 1e-5
+    dw2, db2 = SF.lin_bwd(gh, x, c)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    # strided views (a column slice of a wider matrix) go through the leading dimensions
+    wide = torch.randn(n, f + 3, device=DEV)
+    dw3, _ = SF.lin_bwd(gh, wide[:, :f], c, want_bias=False)
+    assert (dw3.double() - gh[:, :c].double().t() @ wide[:, :f].double()).abs().max().item() / scale < 1e-5 or n == 0
+
+
+def test_lin_bwd_wide_layers_keep_the_library_gemm():
+    """f > 128 is outside sng_lin_bwd (loud error from the C ABI); LinNorm.backward routes such layers to the library GEMM."""
+    from sngnn_b200 import functional as SF, _C
+    assert not _C.lib().sng_lin_bwd_supported(269, 32) and _C.lib().sng_lin_bwd_supported(128, 32)
+    with pytest.raises(RuntimeError):
+        SF.lin_bwd(torch.randn(10, 32, device=DEV), torch.randn(10, 269, device=DEV), 32)
+    x = torch.randn(500, 269, device=DEV)
+    w = torch.randn(32, 269, device=DEV, requires_grad=True)
+    b = torch.randn(32, device=DEV, requires_grad=True)
+    h, _ = SF.lin_norm(x, w, b, 32)
+    h.square().sum().backward()
+    ref = (2 * (x @ w.t() + b)).t() @ x
+    assert (w.grad - ref).abs().max() / ref.abs().max() < 1e-5
