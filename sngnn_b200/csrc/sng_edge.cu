@@ -356,6 +356,144 @@ __global__ void __launch_bounds__(kStWarps * 32, SNG_FWD_MINB) edge_fwd_staged_k
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- narrow rows (C <= 4: a row is one float4), rows with <= 32 in-edges ---------------------------------------------------
+// With 16-byte rows nothing is bound by bytes: the staged kernel spends ~400 warp instructions per row on copy issue,
+// shared-memory row slots and lane = channel loops in which 4 of 32 lanes do useful work (1.3 ms per forward at the pokec
+// shape for a layer whose rows total 26 MB).  Here lane = edge and the whole row lives in registers: each lane loads its
+// source id, its source row (one LDG.128), 1/norm and (fused) its Wt row one item ahead of their use -- registers are the
+// stage --, scores it against the target row, the top_k rounds run on the keys, and the weighted rows are summed ACROSS
+// lanes with a recursive-halving reduction (K values over 32 lanes in ~4K instructions instead of 10 K).
+// After lane_reduce_scatter<K> lane l holds the warp total of value index (l >> (5 - log2 K)) -- bit 4 of the lane is the
+// most significant index bit.
+template <int K>
+__device__ __forceinline__ float lane_reduce_scatter(float (&v)[K], int lane) {
+#pragma unroll
+    for (int n = K; n > 1; n >>= 1) {
+        const int m = 16 * n / K;                                                    // compile time after unrolling: 16, 8, ...
+        const bool hi = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = hi ? v[i] : v[i + n / 2];
+            const float keep = hi ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, m);
+        }
+    }
+    float r = v[0];
+#pragma unroll
+    for (int m = 16 / K; m > 0; m >>= 1) r += __shfl_xor_sync(kFull, r, m);
+    return r;
+}
+
+struct NarrowGather { float4 hj, wj, hi; float irl, iri; int tq; };
+
+template <bool FUSE, bool SELECT_ALL>
+__global__ void __launch_bounds__(kThreads) edge_fwd_narrow_kernel(const EdgeFwdArgs a) {
+    constexpr int K = FUSE ? 8 : 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = gridDim.x * kWarpsPerBlock;
+    const int row0 = blockIdx.x * kWarpsPerBlock + warp;
+    const bool train = !SELECT_ALL && a.sel_cnt != nullptr;
+    const bool want_q = train && a.sel_q != nullptr;
+    // the lane that holds (and writes) channel wc of out_1 after the reduction; fused: the Wt total of the channel sits in lane ^ 16
+    const int wc = FUSE ? (lane >> 2) & 3 : (lane >> 3) & 3;
+    const bool writer = (FUSE ? (lane & 0x13) == 0 : (lane & 7) == 0) && wc < a.c;
+    float beta = 0.f, bw = 0.f, bb = 0.f;
+    if (FUSE) { beta = __ldg(a.beta); if (wc < a.c) { bw = __ldg(a.b_w + wc); if (a.bias) bb = __ldg(a.bias + wc); } }
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto load_rp = [&](int row, int& beg, int& deg) {
+        beg = 0; deg = -1;
+        if (row < a.n) { beg = __ldg(a.rowptr + row); deg = __ldg(a.rowptr + row + 1) - beg; }
+    };
+    auto load_col = [&](int beg, int deg) { return ((unsigned)deg <= 32u && lane < deg) ? __ldg(a.col + beg + lane) : -1; };
+    auto gather = [&](int row, int beg, int deg, int j, NarrowGather& g) {
+        g.hj = z4; g.wj = z4; g.hi = z4; g.irl = 0.f; g.iri = 0.f; g.tq = 0;
+        if ((unsigned)deg <= 32u) {
+            g.hi = ldg4(a.h + (int64_t)(a.row_offset + row) * a.ldh);
+            g.iri = __ldg(a.inv_r + a.row_offset + row);
+            if (j >= 0) {
+                g.hj = ldg4(a.h + (int64_t)j * a.ldh);
+                g.irl = __ldg(a.inv_r + j);
+                if (FUSE) g.wj = ldg4(a.wt + (int64_t)j * a.ldw);
+                if (want_q) g.tq = __ldg(a.tpos + beg + lane);
+            }
+        }
+    };
+
+    // pipeline registers: A = being computed, B = gathers in flight, C = source ids in flight, D = rowptr in flight
+    int begA, degA, begB, degB, begC, degC, begD, degD;
+    load_rp(row0, begA, degA);
+    load_rp(row0 + stride, begB, degB);
+    load_rp(row0 + 2 * stride, begC, degC);
+    int jA = load_col(begA, degA), jB = load_col(begB, degB);
+    NarrowGather gA, gB;
+    gather(row0, begA, degA, jA, gA);
+    for (int row = row0; row < a.n; row += stride) {
+        load_rp(row + 3 * stride, begD, degD);
+        const int jC = load_col(begC, degC);
+        gather(row + stride, begB, degB, jB, gB);
+        if ((unsigned)degA <= 32u) {
+            const int deg = degA;
+            const bool has = lane < deg;
+            // same operation order as the staged kernel (and its chunk pass): the scores are bit-identical to theirs
+            const float d = fmaf(gA.hj.x, gA.hi.x, fmaf(gA.hj.y, gA.hi.y, fmaf(gA.hj.z, gA.hi.z, fmaf(gA.hj.w, gA.hi.w, 0.f))));
+            const float my_s = (d * gA.iri) * gA.irl + 0.0f;
+            int cnt = 0, myrank = -1;
+            float wgt;
+            if (SELECT_ALL) {
+                wgt = has ? my_s : 0.f;
+            } else {
+                const bool cand = has && my_s >= a.thr;
+                unsigned key = cand ? okey(my_s) : 0u;
+                const int ncand = __popc(__ballot_sync(kFull, cand));
+                const int rounds = min(a.top_k, ncand);
+                if (!train && ncand <= a.top_k) {                                    // inference: every candidate is selected, no order needed
+                    myrank = cand ? 0 : -1; cnt = ncand;
+                } else {
+#pragma unroll 2
+                    for (; cnt < rounds; ++cnt) {
+                        const unsigned mx = __reduce_max_sync(kFull, key);
+                        const int w = __ffs(__ballot_sync(kFull, key == mx)) - 1;    // lowest lane = lowest edge position wins ties
+                        if (lane == w) { key = 0u; myrank = cnt; }
+                    }
+                }
+                wgt = myrank >= 0 ? my_s : 0.f;
+            }
+            float v[K];
+            v[0] = wgt * gA.hj.x; v[1] = wgt * gA.hj.y; v[2] = wgt * gA.hj.z; v[3] = wgt * gA.hj.w;
+            if (FUSE) { v[4] = gA.wj.x; v[5] = gA.wj.y; v[6] = gA.wj.z; v[7] = gA.wj.w; }       // zero for lanes without an edge
+            const float tot = lane_reduce_scatter<K>(v, lane);
+            const float a0 = FUSE ? __shfl_xor_sync(kFull, tot, 16) : 0.f;
+            if (writer) {
+                const float o1 = __fdividef(tot, (float)max(deg, 1));                // PyG aggr='mean': the full in-degree
+                const int64_t o = (int64_t)row * a.ldo + wc;
+                if (FUSE) {
+                    const float o0 = a0 + bw;
+                    a.out[o] = beta * o0 + (1.f - beta) * o1 + bb;
+                    if (a.diff) a.diff[o] = o0 - o1;
+                } else {
+                    a.out[o] = o1;
+                }
+            }
+            if (train) {
+                const int64_t lo = (int64_t)row * a.top_k;
+                if (myrank >= 0) {
+                    a.sel_src[lo + myrank] = jA; a.sel_w[lo + myrank] = my_s;
+                    if (want_q) a.sel_q[lo + myrank] = gA.tq;
+                }
+                for (int t = cnt + lane; t < a.top_k; t += 32) {                     // -1 padding behind the list
+                    a.sel_src[lo + t] = -1; a.sel_w[lo + t] = 0.f;
+                    if (want_q) a.sel_q[lo + t] = 0;
+                }
+                if (lane == 0) a.sel_cnt[row] = cnt;
+            }
+        }
+        begA = begB; degA = degB; jA = jB; gA = gB;
+        begB = begC; degB = degC; jB = jC;
+        begC = begD; degC = degD;
+    }
+}
+
 // Sorted (score desc, position asc) candidate list of one warp, in shared memory.
 struct TopList {
     float* s;
@@ -1538,8 +1676,13 @@ static void launch_edge_fwd(EdgeFwdArgs a, const int32_t* rows_hub, int64_t n_hu
             // long rows, then the per-row merge of the chunk candidates
             a.slots = forward_slots(FUSE, G);
             const size_t ss = (size_t)kStWarps * a.slots * staged_row_bytes<G>();
-            cudaFuncSetAttribute(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
-            edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false><<<grid_resident(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false>, a.n, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
+            if constexpr (G == 1) {
+                // 16-byte rows: everything in registers (edge_fwd_narrow_kernel); the chunk pass of the long rows stays staged
+                edge_fwd_narrow_kernel<FUSE, SELECT_ALL><<<grid_resident(edge_fwd_narrow_kernel<FUSE, SELECT_ALL>, a.n, kWarpsPerBlock), kThreads, 0, st>>>(a);
+            } else {
+                cudaFuncSetAttribute(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
+                edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false><<<grid_resident(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, false>, a.n, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
+            }
             if (a.n_chunks > 0) {
                 cudaFuncSetAttribute(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
                 edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, true><<<grid_resident(edge_fwd_staged_kernel<G, FUSE, SELECT_ALL, true>, a.n_chunks, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);

@@ -61,7 +61,10 @@ def test_models_match_reference_golden(fname):
 
 @pytest.mark.parametrize("n,e,c,k,thr,rsl", [(5000, 60000, 32, 10, 0.0, True), (5000, 60000, 5, 3, 0.3, False),
                                               (20000, 400000, 64, 10, -0.5, True), (3000, 30000, 2, 64, -1.0, True),
-                                              (4000, 50000, 128, 7, 0.2, True)])
+                                              (4000, 50000, 128, 7, 0.2, True),
+                                              # narrow rows (C <= 4): the register kernels
+                                              (5000, 60000, 2, 10, 0.0, True), (5000, 60000, 4, 3, -0.5, False), (8000, 100000, 3, 10, 0.1, True),
+                                              (3000, 20000, 1, 64, -1.0, True)])
 def test_edge_selection_and_aggregate_vs_oracle(n, e, c, k, thr, rsl):
     """sel lists exact vs the oracle's rank rule; out_1 within 1e-5; dh via K2b vs autograd of the oracle."""
     from oracle import sn_ref
@@ -202,7 +205,8 @@ def _hub_graph(n, e, seed, symmetric, hubs=(3, 17), hub_deg=(1500, 200)):
     return torch.stack([key // n, key % n])
 
 
-@pytest.mark.parametrize("c,k,thr,sym", [(32, 10, 0.0, True), (32, 10, 0.0, False), (5, 3, 0.2, True), (64, 40, -0.3, True), (8, 1, 0.99, True)])
+@pytest.mark.parametrize("c,k,thr,sym", [(32, 10, 0.0, True), (32, 10, 0.0, False), (5, 3, 0.2, True), (64, 40, -0.3, True), (8, 1, 0.99, True),
+                                          (2, 10, 0.0, True), (2, 10, 0.0, False), (4, 5, 0.1, True), (1, 3, -1.0, True), (3, 40, -0.3, True)])
 def test_snconv_plus_plus_fused_and_unfused_vs_oracle(c, k, thr, sym):
     """One SNConv_plus_plus layer on a graph with short, long (> 32) and hub (> 1024) rows: the fused single pass (symmetric
     graph) and the two-kernel form (asymmetric) against the FP64 oracle -- output, every parameter gradient and dL/dx at
