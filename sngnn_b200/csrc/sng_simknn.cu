@@ -36,6 +36,7 @@ constexpr int kTileBytes = 128 * BK * 2;// 16 KiB: one K block of 128 rows (A bl
 constexpr int kUmmaK = 16;
 constexpr int kNonEpiThreads = 128;
 constexpr int kMaxStages = 10;
+constexpr int kMaxD = 4096;             // feature width limit (d > ~640 streams the query block, see Stage1Params::stream_a)
 constexpr int kMaxCandTotal = 192;      // lists per row * cand <= this; stage 2 expands every candidate into 3 columns
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 // Instrumented builds (make EXTRA=-DSNG_KNN_INSTRUMENT): the SNG_KNN_DEBUG work-skipping modes and the SNG_KNN_TRACE
@@ -180,6 +181,7 @@ struct Stage1Params {
     int nq, n, q_offset;          // query rows in this call, database rows, global id of query row 0
     int kblocks, ksteps_last;     // K tiling: kblocks tiles of 64, the last one has ksteps_last MMA steps of 16
     int stages;                   // B ring depth (K blocks)
+    int stream_a;                 // 1 = the query block does not stay resident (large d): every ring stage holds an A K block AND a B K block
     int cand;                     // candidate slots per row list (L)
     int qcap;                     // hit queue entries (power of two)
     int nsplit, tiles_total;      // 256-column tiles are split across gridDim.y cluster columns
@@ -278,9 +280,13 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();                      // 0 = leader (issues the MMAs)
     const uint32_t a_off = 0;
-    const uint32_t b_off = a_off + (uint32_t)p.kblocks * kTileBytes;
+    // resident A: all K blocks of the CTA's 128 query rows, then the B ring.  Streamed A (d too large for that, p.stream_a):
+    // no resident block; a ring stage is 32 KiB = the A K block followed by the B K block, both reloaded for every tile
+    // (the query block of a CTA is 128 x d FP16 -- 0.6 MB at d = 2,325 --, it stays in L2 between tiles)
+    const uint32_t b_off = a_off + (p.stream_a ? 0u : (uint32_t)p.kblocks * kTileBytes);
+    const uint32_t stage_bytes = p.stream_a ? 2u * kTileBytes : (uint32_t)kTileBytes;
     // per-ROW candidate lists (slot-major: slot s of row r at [s * BM + r]), their bookkeeping, and the hit queue
-    const uint32_t list_off = b_off + (uint32_t)p.stages * kTileBytes;
+    const uint32_t list_off = b_off + (uint32_t)p.stages * stage_bytes;
     const uint32_t thr_off = list_off + (uint32_t)p.cand * BM * 6u;
     const uint32_t q_off = (thr_off + BM * 12u + 15u) & ~15u;         // row_thr, list_cnt, list_minpos; then the 16-byte aligned queue
     const uint32_t qcap = (uint32_t)p.qcap;
@@ -382,7 +388,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // ------------------------------------------------------------------ TMA producer (both CTAs, whole warp, one lane issues)
         const bool issuer = elect_one();
         const uint32_t bar_a_leader = bar_a & kPeerMask;
-        if (issuer) {
+        if (issuer && !p.stream_a) {
             for (int kb = 0; kb < p.kblocks; ++kb)
                 tma_load_2d_pair(base + a_off + (uint32_t)kb * kTileBytes, &map_q, bar_a_leader, kb * BK, row0);
             if (rank == 0) mbar_expect_tx(bar_a, 2u * (uint32_t)p.kblocks * kTileBytes);
@@ -413,8 +419,10 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 if (issuer) {
                     if (!(dbg & 4)) {
-                        tma_load_2d_pair(base + b_off + (uint32_t)stage * kTileBytes, &map_db, (bar_full + 8 * stage) & kPeerMask, kb * BK, brow);
-                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * kTileBytes);
+                        const uint32_t sdst = base + b_off + (uint32_t)stage * stage_bytes;
+                        if (p.stream_a) tma_load_2d_pair(sdst, &map_q, (bar_full + 8 * stage) & kPeerMask, kb * BK, row0);
+                        tma_load_2d_pair(sdst + (p.stream_a ? (uint32_t)kTileBytes : 0u), &map_db, (bar_full + 8 * stage) & kPeerMask, kb * BK, brow);
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2u * stage_bytes);
                         else mbar_arrive_cluster(bar_full + 8 * stage, 0);
                     } else {                                        // profiling: no B traffic at all, the MMAs read stale shared memory
                         mbar_arrive_cluster(bar_full + 8 * stage, 0);
@@ -434,7 +442,7 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int w = warp - 1;
         if (rank == 0 && w < p.issuers) {
             const bool issuer = elect_one();
-            mbar_wait(bar_a, 0);
+            if (!p.stream_a) mbar_wait(bar_a, 0);
             tc_fence_after();
             const uint64_t adesc0 = make_smem_desc(base + a_off);
             const uint64_t bdesc0 = make_smem_desc(base + b_off);
@@ -458,8 +466,8 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                     tc_fence_after();
                     const int ksteps = (kb == p.kblocks - 1) ? p.ksteps_last : (BK / kUmmaK);
                     // descriptors count 16-byte units: one 16 KiB tile = 1024 units, one K step (32 B) = 2 units
-                    const uint64_t adesc = adesc0 + (uint64_t)(kb * (kTileBytes >> 4));
-                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage * (kTileBytes >> 4));
+                    const uint64_t adesc = p.stream_a ? bdesc0 + (uint64_t)(stage * 2 * (kTileBytes >> 4)) : adesc0 + (uint64_t)(kb * (kTileBytes >> 4));
+                    const uint64_t bdesc = p.stream_a ? adesc + (uint64_t)(kTileBytes >> 4) : bdesc0 + (uint64_t)(stage * (kTileBytes >> 4));
                     if (issuer) {
                         for (int ks = 0; ks < ksteps; ++ks)
                             umma_f16_pair(tmem_d, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), kIdesc, (kb | ks) != 0 ? 1u : 0u);
@@ -1027,7 +1035,7 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
 }
 
 struct Plan {
-    int ew, stages, cand, qcap, nsplit, kblocks, ksteps_last, tiles;
+    int ew, stages, cand, qcap, nsplit, kblocks, ksteps_last, tiles, stream_a;
     int seed_stride, seed_q;      // 0 = no seed pass
     size_t smem;
     int lists() const { return nsplit; }          // one candidate list per (row, column split)
@@ -1047,10 +1055,10 @@ static int seed_quantile(int top_k, int stride, double tol) {
     return top_k + 1;
 }
 
-static size_t smem_bytes(int ew, int kblocks, int stages, int cand, int qcap) {
+static size_t smem_bytes(int ew, int kblocks, int stages, int cand, int qcap, bool stream_a = false) {
     (void)ew;
-    return 1024 + (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes + (size_t)cand * BM * 6 + BM * 12 + 16 + (size_t)qcap * 68 + 16 +
-           8 * (2 * kMaxStages + 9) + 16;
+    return 1024 + (stream_a ? (size_t)stages * 2 * kTileBytes : (size_t)kblocks * kTileBytes + (size_t)stages * kTileBytes) + (size_t)cand * BM * 6 + BM * 12 +
+           16 + (size_t)qcap * 68 + 16 + 8 * (2 * kMaxStages + 9) + 16;
 }
 
 // Tuning / debugging overrides through environment variables are OFF unless a test or experiment switches them on with
@@ -1088,6 +1096,7 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     pl->ksteps_last = (d16 - (pl->kblocks - 1) * BK) / kUmmaK;
     pl->tiles = (int)((n + BN - 1) / BN);
     pl->ew = 0;
+    pl->stream_a = 0;
     // small K: the epilogue (TMEM reads) paces the kernel -> 16 epilogue warps; large K: the MMAs do -> fewer, deeper B ring
     const int ew_pref = d16 <= 128 ? 4 : (d16 <= 320 ? 2 : 1);
     if (force_ew == 4 && pl->kblocks > 2) force_ew = 2;        // EW = 4 is the split-N mode, built for at most two K blocks
@@ -1112,6 +1121,20 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
                 }
             }
             if (force_ew) break;
+        }
+    }
+    if (!pl->ew && force_ew != 4) {
+        // the query block cannot stay resident (d > ~640): stream it through the ring with B, K block by K block.  One epilogue
+        // warp per lane quarter (the MMAs of a large-K tile take far longer than its epilogue), the deepest ring that fits.
+        static const int kMarginsS[] = {22, 14, 8, 4};
+        for (int mi = 0; mi < (top_k > 0 ? 4 : 1) && !pl->ew; ++mi) {
+            const int c = top_k > 0 ? cand_for(top_k, kMarginsS[mi]) : cand;
+            if (c > kMaxCandTotal) continue;
+            for (int qc = kQueue; qc >= 64 && !pl->ew; qc /= 4)
+                for (int st = 5; st >= 2; --st) {
+                    const size_t sz = smem_bytes(1, pl->kblocks, st, c, qc, true);
+                    if (sz <= kMaxSmem) { pl->ew = 1; pl->stages = st; pl->smem = sz; pl->cand = c; pl->qcap = qc; pl->stream_a = 1; break; }
+                }
         }
     }
     if (!pl->ew) { set_error("simknn: d=%lld top_k=%d does not fit in shared memory", (long long)d, top_k); return SNG_ERR_UNSUPPORTED; }
@@ -1166,10 +1189,11 @@ static int launch_stage1(const Plan& pl, const uint16_t* xq, const uint16_t* xal
     if (int rc = make_map(&mdb, xall, n_db, ldb, seed_pass ? pl.seed_stride : 1)) return rc;
     Stage1Params p;
     p.nq = (int)nq; p.n = (int)n_db; p.q_offset = (int)q_offset;
-    p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.cand = seed_pass ? 0 : pl.cand; p.qcap = pl.qcap;
+    p.kblocks = pl.kblocks; p.ksteps_last = pl.ksteps_last; p.stages = pl.stages; p.stream_a = pl.stream_a; p.cand = seed_pass ? 0 : pl.cand; p.qcap = pl.qcap;
     p.nsplit = seed_pass ? 1 : pl.nsplit; p.tiles_total = (int)((n_db + BN - 1) / BN); p.thr_lo = thr_lo; p.remove_self = remove_self;
     p.debug = env_int("SNG_KNN_DEBUG", 1, 63);
     p.issuers = env_int("SNG_KNN_ISSUERS", 1, 2) ? env_int("SNG_KNN_ISSUERS", 1, 2) : (pl.kblocks <= 3 ? 2 : 1);
+    if (pl.stream_a) p.issuers = 1;
     p.cand_val = cand_val; p.cand_idx = cand_idx; p.cand_min = cand_min;
     p.phase = seed_pass ? nullptr : phase;
     p.nq_dev = nq_dev; p.row_ids = row_ids;
@@ -1213,12 +1237,16 @@ static int check_common(const char* fn, const void* xq, const void* xall, int64_
     if (nq <= 0 || n <= 0 || d <= 0 || q_offset < 0 || n >= (1ll << 31) || nq >= (1ll << 31)) { set_error("%s: bad nq/n/d/q_offset", fn); return SNG_ERR_ARG; }
     if (ldb % 8 != 0 || ldb < (d + 15) / 16 * 16) { set_error("%s: ldb=%lld must be a multiple of 8 and >= d rounded up to 16", fn, (long long)ldb); return SNG_ERR_ARG; }
     if (((uintptr_t)xq | (uintptr_t)xall) & 15) { set_error("%s: FP16 operands must be 16-byte aligned", fn); return SNG_ERR_ARG; }
-    if (d > 1024) { set_error("%s: d=%lld > 1024 not supported", fn, (long long)d); return SNG_ERR_UNSUPPORTED; }
+    if (d > kMaxD) { set_error("%s: d=%lld > %d not supported", fn, (long long)d, kMaxD); return SNG_ERR_UNSUPPORTED; }
     return SNG_OK;
 }
 
 // worst-case |fp16-tensor-core score - exact FP32 score| for unit rows: 2 * 2^-11 (operand rounding) + accumulation slack
+// The accumulation slack grows with the contraction length (the tensor cores add into their FP32 accumulators with truncation):
+// 1.2e-4 covers K <= 640, longer contractions scale it.
 constexpr float kScoreEps = 0.0009765625f + 1.2e-4f;
+static float score_eps(int64_t d) { return 0.0009765625f + 1.2e-4f * (d > 640 ? (float)d / 640.0f : 1.0f); }
+static int64_t retry_ld(int64_t d) { const int64_t d16 = (d + 15) / 16 * 16; return d16 + 64 > 1024 ? d16 + 64 : 1024; }   // widest ldb of the retry query matrix
 
 }  // namespace knn
 }  // namespace sng
@@ -1238,7 +1266,7 @@ extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, i
     const size_t part = (size_t)kFbWaveRows * ((n + kChunk - 1) / kChunk) * top_k;
     return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + 2 * align256(part * 4) +
            align256((size_t)nq * kSeedGroups * 4) + 256 +
-           align256((size_t)kRetryRows * 1024 * 2) + 2 * align256((size_t)kRetryRows * kMaxCandTotal * 4) + align256((size_t)kRetryRows * 8 * 4) +
+           align256((size_t)kRetryRows * retry_ld(d) * 2) + 2 * align256((size_t)kRetryRows * kMaxCandTotal * 4) + align256((size_t)kRetryRows * 8 * 4) +
            align256((size_t)nq * 4) + 256 + 1024;
 }
 
@@ -1291,7 +1319,8 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     SNG_REQUIRE(xq32 && xall32 && ld32 % 4 == 0 && ld32 >= d, "sng_simknn_build: FP32 rows must be padded to a multiple of 4 floats (ld32=%lld)", (long long)ld32);
     SNG_REQUIRE(top_k >= 1 && top_k <= SNG_KNN_MAX_TOPK, "sng_simknn_build: top_k=%d out of [1,%d]", top_k, SNG_KNN_MAX_TOPK);
     SNG_REQUIRE(idx && sim && cnt && n_fallback && workspace, "sng_simknn_build: null output / workspace");
-    SNG_REQUIRE(ldb <= 1024, "sng_simknn_build: ldb > 1024");
+    SNG_REQUIRE(ldb <= retry_ld(d), "sng_simknn_build: ldb=%lld > %lld (rows padded far beyond d)", (long long)ldb, (long long)retry_ld(d));
+    const float eps = score_eps(d);
     if (workspace_bytes < sng_simknn_workspace_bytes(nq, n, d, top_k)) { set_error("sng_simknn_build: workspace too small (%zu < %zu)", workspace_bytes, sng_simknn_workspace_bytes(nq, n, d, top_k)); return SNG_ERR_WORKSPACE; }
     Plan pl;
     if (int rc = make_plan(&pl, nq, n, d, top_k, 0, 0)) return rc;
@@ -1309,7 +1338,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     float* seeds = reinterpret_cast<float*>(w); w += align256((size_t)nq * kSeedGroups * 4);
     int* phase = reinterpret_cast<int*>(w); w += 256;
     // retry pass buffers
-    uint16_t* xq_retry = reinterpret_cast<uint16_t*>(w); w += align256((size_t)kRetryRows * 1024 * 2);
+    uint16_t* xq_retry = reinterpret_cast<uint16_t*>(w); w += align256((size_t)kRetryRows * retry_ld(d) * 2);
     float* rcand_val = reinterpret_cast<float*>(w); w += align256((size_t)kRetryRows * kMaxCandTotal * 4);
     int* rcand_idx = reinterpret_cast<int*>(w); w += align256((size_t)kRetryRows * kMaxCandTotal * 4);
     float* rcand_min = reinterpret_cast<float*>(w); w += align256((size_t)kRetryRows * 8 * 4);
@@ -1332,7 +1361,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     if (cudaMemsetAsync(n_fb1, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
     if (cudaMemsetAsync(n_fallback, 0, sizeof(int), st) != cudaSuccess) return check_launch("sng_simknn_build memset");
     // approximate scores below thr - eps can never reach thr exactly
-    const float thr_lo = thr - 1.01f * kScoreEps;
+    const float thr_lo = thr - 1.01f * eps;
     if (pl.seed_stride > 0)
         if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, nullptr, nullptr, nullptr, nullptr, seeds, nullptr, st)) return rc;
     if (int rc = launch_stage1(pl, xq, xall, ldb, nq, q_offset, n, thr_lo, remove_self, cand_val, cand_idx, cand_min,
@@ -1344,7 +1373,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     {
         const int blocks = (int)((nq + 7) / 8 < (int64_t)sm_count() * 8 ? (nq + 7) / 8 : (int64_t)sm_count() * 8);
         simknn_rescore_kernel<<<blocks > 0 ? blocks : 1, 256, (size_t)8 * 2 * 3 * m_total * 4, st>>>(
-            xq32, xall32, ld32, d4, (int)nq, (int)n, (int)q_offset, remove_self, m_total, pl.lists(), top_k, thr, kScoreEps, cand_val, cand_idx, cand_min,
+            xq32, xall32, ld32, d4, (int)nq, (int)n, (int)q_offset, remove_self, m_total, pl.lists(), top_k, thr, eps, cand_val, cand_idx, cand_min,
             idx, sim, cnt, flag_rows, flag_cnt, nullptr, nullptr);
         if (int rc = check_launch("simknn stage 2")) return rc;
     }
@@ -1360,7 +1389,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
                                    pl.seed_stride > 0 ? seeds : nullptr, nullptr, nullptr, st, n_fb1, fb_rows)) return rc;
         const int mr = pr.lists() * pr.cand;
         simknn_rescore_kernel<<<kRetryRows / 8, 256, (size_t)8 * 2 * 3 * mr * 4, st>>>(
-            xq32, xall32, ld32, d4, kRetryRows, (int)n, (int)q_offset, remove_self, mr, pr.lists(), top_k, thr, kScoreEps, rcand_val, rcand_idx, rcand_min,
+            xq32, xall32, ld32, d4, kRetryRows, (int)n, (int)q_offset, remove_self, mr, pr.lists(), top_k, thr, eps, rcand_val, rcand_idx, rcand_min,
             idx, sim, cnt, fb2_rows, n_fallback, n_fb1, fb_rows);
         if (int rc = check_launch("simknn retry pass")) return rc;
     }

@@ -35,7 +35,9 @@ def _score64(x):
 
 
 @pytest.mark.parametrize("n,d,ew,ns", [(1000, 64, 1, 1), (1000, 64, 2, 1), (3000, 65, 4, 3), (2500, 128, 4, 2), (1500, 269, 0, 0),
-                                       (1300, 512, 0, 0), (700, 16, 2, 1), (900, 40, 0, 0), (5000, 65, 0, 0), (257, 65, 4, 1), (900, 24, 0, 0), (800, 90, 4, 1), (600, 200, 0, 0)])
+                                       (1300, 512, 0, 0), (700, 16, 2, 1), (900, 40, 0, 0), (5000, 65, 0, 0), (257, 65, 4, 1), (900, 24, 0, 0), (800, 90, 4, 1), (600, 200, 0, 0),
+                                       # d > ~640: the query block is streamed through the ring with B (Stage1Params::stream_a)
+                                       (1500, 768, 0, 0), (1200, 1024, 0, 0), (900, 2325, 0, 0)])
 def test_stage1_candidates_contain_true_topk(n, d, ew, ns):
     """Tensor-core stage.  A candidate is a column TRIPLE {c, c+1, c+2} (two columns when c % 32 == 30) scored with the
     maximum FP16 score of its columns.  Every true top-10 neighbour must lie inside a kept triple or under the reported
@@ -75,7 +77,10 @@ def test_stage1_candidates_contain_true_topk(n, d, ew, ns):
 @pytest.mark.parametrize("n,d,k,thr,rs,kind", [(2000, 65, 10, -1.0, True, "normal"), (2000, 65, 10, 0.9, True, "clustered"),
                                                 (3000, 128, 10, 0.0, False, "clustered"), (1200, 48, 50, -1.0, True, "clustered"),
                                                 (2277, 2325 // 8, 10, 0.3, True, "binary"), (1000, 269, 5, 0.5, True, "clustered"),
-                                                (600, 8, 64, -1.0, False, "normal"), (130, 33, 10, -1.0, True, "normal")])
+                                                (600, 8, 64, -1.0, False, "normal"), (130, 33, 10, -1.0, True, "normal"),
+                                                # wide features (streamed query block): the Chameleon shape with its raw 2,325 features
+                                                (2277, 2325, 10, 0.3, True, "binary"), (1500, 800, 10, -1.0, True, "normal"),
+                                                (1000, 1500, 5, 0.0, False, "clustered")])
 def test_build_matches_oracle(n, d, k, thr, rs, kind):
     from sngnn_b200 import simknn
     x = _features(n, d, kind, seed=7 * n + d)
@@ -88,7 +93,8 @@ def test_build_matches_oracle(n, d, k, thr, rs, kind):
     assert check_tie_order(idx, sim, cnt)
     keep = torch.arange(k)[None, :] < cnt.cpu()[:, None]
     same = (idx.cpu().long() == idx_ref) & keep
-    assert (sim.cpu().double()[same] - sim_ref[same]).abs().max() < 2e-6 if same.any() else True
+    tol = 2e-6 if d <= 512 else 1e-5                      # FP32 summation error of a d-term dot product (the contract is 1e-5)
+    assert (sim.cpu().double()[same] - sim_ref[same]).abs().max() < tol if same.any() else True
 
 
 @pytest.mark.parametrize("n,d", [(1500, 40), (20000, 24)])
