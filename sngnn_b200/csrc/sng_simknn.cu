@@ -506,21 +506,31 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                 }
                 __threadfence_block();
                 const bool mine = lane < nr;
-                float m[12]; int row = -1 - lane, col0 = 0;                          // distinct sentinel rows for idle lanes
+                // Usually one or two of an entry's 11 triples beat the row threshold (bit i of `mleft`, computed here, lane =
+                // entry).  Round j applies the j-th such triple of EVERY entry of the batch at once: the insert
+                // below -- a divergent detour with a 32-slot minimum scan when the list is full -- runs once per round for up to
+                // 32 values, not once per triple index per batch (11 x), which made this warp the pacer of the whole CTA on small
+                // databases, where hits are dense (arxiv shape: 38 % of all warp-chunks hit).
+                int row = 0, col0 = 0; unsigned mleft = 0u;
+                const float* qf = reinterpret_cast<const float*>(q_ent + 4 * s);
                 if (mine) {
-                    const float4 e0 = q_ent[4 * s], e1 = q_ent[4 * s + 1], e2 = q_ent[4 * s + 2], e3 = q_ent[4 * s + 3];
-                    m[0] = e0.x; m[1] = e0.y; m[2] = e0.z; m[3] = e0.w; m[4] = e1.x; m[5] = e1.y; m[6] = e1.z; m[7] = e1.w;
-                    m[8] = e2.x; m[9] = e2.y; m[10] = e2.z; col0 = __float_as_int(e2.w); row = __float_as_int(e3.x);
-                }
-                unsigned pending = __ballot_sync(0xffffffffu, mine);
-                while (pending) {                                                   // entries of one row are applied one at a time
-                    const unsigned same = __match_any_sync(0xffffffffu, row) & pending;
-                    const bool go = mine && ((pending >> lane) & 1u) && (__ffs(same) - 1 == lane);
-                    if (go) {
-                        float thr = row_thr[row];
+                    col0 = __float_as_int(qf[11]); row = __float_as_int(qf[12]);
+                    const float thr0 = row_thr[row];
 #pragma unroll
-                        for (int i = 0; i < 11; ++i) {
-                            const float val = m[i];
+                    for (int i = 0; i < 11; ++i) mleft |= (qf[i] > thr0 ? 1u : 0u) << i;
+                }
+                while (__any_sync(0xffffffffu, mleft != 0u)) {
+                    const bool has = mleft != 0u;
+                    const int i = has ? __ffs(mleft) - 1 : 0;
+                    mleft &= mleft - 1u;                                             // (0 stays 0)
+                    const float val = has ? qf[i] : 0.f;
+                    const int rowk = has ? row : -1 - lane;                          // distinct sentinel rows for idle lanes
+                    unsigned pending = __ballot_sync(0xffffffffu, has);
+                    while (pending) {                                               // values of one row are applied one at a time
+                        const unsigned same = __match_any_sync(0xffffffffu, rowk) & pending;
+                        const bool go = has && ((pending >> lane) & 1u) && (__ffs(same) - 1 == lane);
+                        if (go) {
+                            const float thr = row_thr[row];
                             if (val > thr) {
                                 int c = list_cnt[row], slot;
                                 if (c < L) { slot = c; list_cnt[row] = ++c; }
@@ -533,13 +543,13 @@ simknn_stage1_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                                     for (int s2 = 1; s2 < L; ++s2) { const unsigned y = list_val[s2 * BM + row]; if (y < mn) { mn = y; mp = s2; } }
                                     list_minpos[row] = mp;
                                     const float tn = q_upper(mn);                    // nothing in the minimum's bin can be told from it
-                                    if (tn > thr) { thr = tn; row_thr[row] = tn; }
+                                    if (tn > thr) row_thr[row] = tn;
                                 }
                             }
                         }
+                        __syncwarp();
+                        pending &= ~__ballot_sync(0xffffffffu, go);
                     }
-                    __syncwarp();
-                    pending &= ~__ballot_sync(0xffffffffu, go);
                 }
                 if (mine) q_flag[s] = 0;
                 __threadfence_block();
