@@ -1392,6 +1392,155 @@ __global__ void __launch_bounds__(kStWarps * 32, SNG_BWDS_MINB) edge_bwd_source_
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- narrow rows (C <= 4) of the two passes: lane = edge, rows in registers, cross-lane sums by recursive halving (see
+// edge_fwd_narrow_kernel).  Pass T covers every row (a saved list has <= top_k <= 32 entries); pass S the source rows with
+// <= 32 out-edges (longer ones go through the staged chunk pass + merge).
+__global__ void __launch_bounds__(kThreads) edge_bwd_target_narrow_kernel(const EdgeBwdArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = gridDim.x * kWarpsPerBlock;
+    const int row0 = blockIdx.x * kWarpsPerBlock + warp;
+    const float gscale = a.beta ? 1.0f - __ldg(a.beta) : 1.0f;
+    const int wc = (lane >> 3) & 3;                                                  // lane_reduce_scatter<4>: lane 8 c holds channel c
+    const bool writer = (lane & 7) == 0 && wc < a.c;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float bpart = 0.f;
+    struct Gt { float4 hj, hi, gi; float irj, iri, df, gc; };
+    auto load_meta = [&](int row, int& cnt, int& deg) {
+        cnt = -1; deg = 1;
+        if (row < a.n) { cnt = __ldg(a.sel_cnt + row); deg = __ldg(a.rowptr + row + 1) - __ldg(a.rowptr + row); }
+    };
+    auto load_list = [&](int row, int cnt, int& j, float& w, int& qp) {
+        j = -1; w = 0.f; qp = 0;
+        if (lane < cnt) { const int64_t o = (int64_t)row * a.top_k + lane; j = __ldg(a.sel_src + o); w = __ldg(a.sel_w + o); qp = __ldg(a.sel_q + o); }
+    };
+    auto gather = [&](int row, int cnt, int j, Gt& g) {
+        g.hj = z4; g.hi = z4; g.gi = z4; g.irj = 0.f; g.iri = 0.f; g.df = 0.f; g.gc = 0.f;
+        if (cnt >= 0) {
+            g.gi = ldg4(a.g + (int64_t)row * a.ldg);
+            g.iri = __ldg(a.inv_r + a.row_offset + row);
+            if (j >= 0) { g.hj = ldg4(a.h + (int64_t)j * a.ld); g.irj = __ldg(a.inv_r + j); }
+            if (a.diff && writer) { g.df = __ldg(a.diff + (int64_t)row * a.lddiff + wc); g.gc = __ldg(a.g + (int64_t)row * a.ldg + wc); }
+        }
+    };
+    int cntA, degA, cntB, degB, cntC, degC, cntD, degD;
+    load_meta(row0, cntA, degA);
+    load_meta(row0 + stride, cntB, degB);
+    load_meta(row0 + 2 * stride, cntC, degC);
+    int jA, qA, jB, qB; float wA, wB;
+    load_list(row0, cntA, jA, wA, qA);
+    load_list(row0 + stride, cntB, jB, wB, qB);
+    Gt gA, gB;
+    gather(row0, cntA, jA, gA);
+    for (int row = row0; row < a.n; row += stride) {
+        load_meta(row + 3 * stride, cntD, degD);
+        int jC, qC; float wC;
+        load_list(row + 2 * stride, cntC, jC, wC, qC);
+        gather(row + stride, cntB, jB, gB);
+        {
+            const float invd = __fdividef(1.0f, (float)max(degA, 1)) * gscale;           // g1_i / deg_i = g_i * invd
+            const float d = fmaf(gA.hj.x, gA.gi.x, fmaf(gA.hj.y, gA.gi.y, fmaf(gA.hj.z, gA.gi.z, fmaf(gA.hj.w, gA.gi.w, 0.f))));
+            const float ds = d * invd;                                                   // dL/ds_e (lane = selected edge)
+            if (lane < cntA) a.coef[qA] = make_float2(wA * invd, ds * gA.iri);
+            const float wdn = lane < cntA ? ds * gA.irj : 0.f;                           // ds_e / r_j: dn_i += wdn h_j
+            float v[4] = {wdn * gA.hj.x, wdn * gA.hj.y, wdn * gA.hj.z, wdn * gA.hj.w};
+            const float tot = lane_reduce_scatter<4>(v, lane);
+            if (writer) {
+                a.dnT[(int64_t)(a.row_offset + row) * a.ld + wc] = tot;
+                bpart = fmaf(gA.df, gA.gc, bpart);                                       // dL/dbeta: diff . g (raw g); df = 0 without diff
+            }
+        }
+        cntA = cntB; degA = degB; jA = jB; wA = wB; qA = qB; gA = gB;
+        cntB = cntC; degB = degC; jB = jC; wB = wC; qB = qC;
+        cntC = cntD; degC = degD;
+    }
+    if (a.dbeta_part) {                                                                  // fixed-order block sum -> one partial per block
+        bpart = group_sum<32>(bpart);
+        __shared__ float red[kWarpsPerBlock];
+        if (lane == 0) red[warp] = bpart;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < kWarpsPerBlock; ++w) t += red[w];
+            a.dbeta_part[blockIdx.x] = t;
+        }
+    }
+}
+
+template <bool FUSE>
+__global__ void __launch_bounds__(kThreads) edge_bwd_source_narrow_kernel(const EdgeBwdArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = gridDim.x * kWarpsPerBlock;
+    const int row0 = blockIdx.x * kWarpsPerBlock + warp;
+    const float beta = FUSE ? __ldg(a.beta) : 0.f;
+    // after lane_reduce_scatter<8> of (dval, dn_source): lanes with bit 4 clear hold dval[c], lanes with bit 4 set dn_source[c],
+    // c = bits 3:2.  The lanes 16 + 4 c finish channel c; after lane_reduce_scatter<4> of dw lane 8 c holds channel c.
+    const int fc = (lane >> 2) & 3;
+    const bool fin = (lane & 0x13) == 0x10;
+    const bool fin_ok = fin && fc < a.c;
+    const int wc = (lane >> 3) & 3;
+    const bool wwriter = (lane & 7) == 0 && wc < a.c;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    struct Gs { float4 gv, hv; float hj, dn, ir; };
+    auto load_rp = [&](int item, int& beg, int& deg) {
+        beg = 0; deg = -1;
+        if (item < a.n_total) {
+            const int jr = item - a.shift;                                   // rows of the by-source CSR are shifted source ids
+            deg = 0;
+            if (jr >= 0) { beg = __ldg(a.rowptr_out + jr); deg = __ldg(a.rowptr_out + jr + 1) - beg; }
+        }
+    };
+    auto load_edges = [&](int beg, int deg, int& il, float2& cf) {
+        il = -1; cf = make_float2(0.f, 0.f);
+        if ((unsigned)deg <= 32u && lane < deg) { il = __ldg(a.col_out + beg + lane); cf = __ldg(a.coef + beg + lane); }
+    };
+    auto gather = [&](int item, int deg, int il, const float2& cf, Gs& g) {
+        g.gv = z4; g.hv = z4; g.hj = 0.f; g.dn = 0.f; g.ir = 0.f;
+        if ((unsigned)deg <= 32u) {
+            const bool sel = cf.x != 0.f || cf.y != 0.f;                     // an unselected edge has both coefficients 0
+            if (il >= 0 && (FUSE || sel)) g.gv = ldg4(a.g + (int64_t)il * a.ldg);
+            if (sel) g.hv = ldg4(a.h + (int64_t)il * a.ld);
+            g.ir = __ldg(a.inv_r + item);
+            if (fin_ok) { g.hj = __ldg(a.h + (int64_t)item * a.ld + fc); g.dn = __ldg(a.dnT + (int64_t)item * a.ld + fc); }
+        }
+    };
+    int begA, degA, begB, degB, begC, degC, begD, degD;
+    load_rp(row0, begA, degA);
+    load_rp(row0 + stride, begB, degB);
+    load_rp(row0 + 2 * stride, begC, degC);
+    int ilA, ilB; float2 cfA, cfB;
+    load_edges(begA, degA, ilA, cfA);
+    load_edges(begB, degB, ilB, cfB);
+    Gs gA, gB;
+    gather(row0, degA, ilA, cfA, gA);
+    for (int row = row0; row < a.n_total; row += stride) {
+        load_rp(row + 3 * stride, begD, degD);
+        int ilC; float2 cfC;
+        load_edges(begC, degC, ilC, cfC);
+        gather(row + stride, degB, ilB, cfB, gB);
+        if ((unsigned)degA <= 32u) {
+            float v[8] = {cfA.x * gA.gv.x, cfA.x * gA.gv.y, cfA.x * gA.gv.z, cfA.x * gA.gv.w,
+                          cfA.y * gA.hv.x, cfA.y * gA.hv.y, cfA.y * gA.hv.z, cfA.y * gA.hv.w};
+            const float tot = lane_reduce_scatter<8>(v, lane);
+            const float dval = __shfl_xor_sync(kFull, tot, 16);              // for the finishing lanes: dval of their channel
+            // dh_j = dval + (dn - n_j (n_j . dn)) / r_j with dn = the target-side part (dnT) + the source-side part
+            const float nj = gA.hj * gA.ir;
+            const float dn = gA.dn + tot;
+            float proj = fin_ok ? nj * dn : 0.f;
+            proj += __shfl_xor_sync(kFull, proj, 4);
+            proj += __shfl_xor_sync(kFull, proj, 8);
+            if (fin_ok) a.dh[(int64_t)row * a.ld + fc] = dval + (dn - nj * proj) * gA.ir;
+            if (FUSE) {
+                float u[4] = {gA.gv.x, gA.gv.y, gA.gv.z, gA.gv.w};
+                const float dw = lane_reduce_scatter<4>(u, lane);
+                if (wwriter) a.dwt[(int64_t)row * a.lddw + wc] = dw * beta;
+            }
+        }
+        begA = begB; degA = degB; ilA = ilB; cfA = cfB; gA = gB;
+        begB = begC; degB = degC; ilB = ilC; cfB = cfC;
+        begC = begD; degC = degD;
+    }
+}
+
 // long source rows: sum of the chunk partials + the same finish (warp per row, lane = channel)
 template <int G, bool FUSE>
 __global__ void __launch_bounds__(kThreads) edge_bwd_source_merge_kernel(const EdgeBwdArgs a) {
@@ -1783,8 +1932,12 @@ template <int G, bool FUSE>
 static void launch_bwd_source_staged(EdgeBwdArgs a, cudaStream_t st) {
     a.slots = source_slots(FUSE);
     const size_t ss = (size_t)kStWarps * a.slots * 16 * G;
-    cudaFuncSetAttribute(edge_bwd_source_staged_kernel<G, FUSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
-    edge_bwd_source_staged_kernel<G, FUSE, false><<<grid_resident(edge_bwd_source_staged_kernel<G, FUSE, false>, a.n_total, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
+    if constexpr (G == 1) {
+        edge_bwd_source_narrow_kernel<FUSE><<<grid_resident(edge_bwd_source_narrow_kernel<FUSE>, a.n_total, kWarpsPerBlock), kThreads, 0, st>>>(a);
+    } else {
+        cudaFuncSetAttribute(edge_bwd_source_staged_kernel<G, FUSE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
+        edge_bwd_source_staged_kernel<G, FUSE, false><<<grid_resident(edge_bwd_source_staged_kernel<G, FUSE, false>, a.n_total, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
+    }
     if (a.n_chunks > 0) {
         cudaFuncSetAttribute(edge_bwd_source_staged_kernel<G, FUSE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss);
         edge_bwd_source_staged_kernel<G, FUSE, true><<<grid_resident(edge_bwd_source_staged_kernel<G, FUSE, true>, a.n_chunks, kStWarps, ss, kStWarps * 32), kStWarps * 32, ss, st>>>(a);
@@ -1828,7 +1981,12 @@ extern "C" int sng_edge_bwd(const float* h, const float* inv_norm, const float* 
     const bool staged_s = c <= 32 && n_chunks_out >= 0;              // pass S with the by-source chunk tables
     int grid_t = 1;
     SNG_DISPATCH_G(c,
-        if constexpr (G <= 8) {
+        if constexpr (G == 1) {
+            if (staged_t) {
+                grid_t = grid_resident(edge_bwd_target_narrow_kernel, n, kWarpsPerBlock);
+                edge_bwd_target_narrow_kernel<<<grid_t, kThreads, 0, st>>>(a);
+            }
+        } else if constexpr (G <= 8) {
             if (staged_t) grid_t = launch_bwd_target_staged<G>(a, st);
         }
         if (!staged_t || G > 8) {
