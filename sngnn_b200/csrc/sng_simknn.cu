@@ -762,6 +762,25 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
         const int row = row_map ? __ldg(row_map + f) : f;
         const float* a = xq + (int64_t)row * ld32;
         const int self_col = remove_self ? q_offset + row : -1;
+        // An all-zero query row (F.normalize maps a zero feature row to zero) scores exactly 0 against every column: its list is
+        // the lowest top_k column ids (minus itself) when 0 >= thr, else empty -- by the rule itself, no scan.  (No tensor-core
+        // list can prove such a row: every score ties; it used to cost an exact scan of all n columns.)
+        {
+            bool nz = false;
+            for (int k4 = lane; k4 < d4; k4 += 32) { const float4 v = ldg4(a + 4 * k4); nz = nz || v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f; }
+            if (!__any_sync(0xffffffffu, nz)) {
+                const int avail = n - ((self_col >= 0 && self_col < n) ? 1 : 0);
+                const int cnt0 = 0.0f >= thr ? min(top_k, avail) : 0;
+                for (int t = lane; t < top_k; t += 32) {
+                    const int j = (self_col >= 0 && t >= self_col) ? t + 1 : t;
+                    idx_out[(size_t)row * top_k + t] = t < cnt0 ? j : -1;
+                    sim_out[(size_t)row * top_k + t] = 0.f;
+                }
+                if (lane == 0) cnt_out[row] = cnt0;
+                __syncwarp();
+                continue;
+            }
+        }
         // Triples that cannot matter are not rescored.  Let t_k be the top_k-th largest triple maximum (FP16 scores).  The
         // top_k largest triples each hold a column whose exact score is >= t_k - eps, so the top_k-th best exact score is
         // too; every column of a triple whose maximum is < t_k - 2 eps scores < t_k - eps exactly: strictly below the cut.
@@ -1364,6 +1383,16 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
             pr.seed_stride = pr.seed_q = 0;
             pr.nsplit = kMaxCandTotal / rcand < pr.tiles ? kMaxCandTotal / rcand : pr.tiles;
             if (pr.nsplit < 1) pr.nsplit = 1;
+            // The retry pass is a handful of CTA pairs sweeping all n columns, so its latency is one pair's sweep.  The same total
+            // list capacity per row (splits x slots <= 192) cut into the maximum of 8 column splits with shorter lists sweeps 8/3
+            // as fast; a list still keeps top_k + 14 triples of ITS column range.
+            if (pr.tiles >= 64) {
+                const int rc8 = ((top_k + 14 > kMaxCandTotal / 8 ? top_k + 14 : kMaxCandTotal / 8) + 1) / 2 * 2;
+                Plan p8;
+                if (rc8 < rcand && 8 * rc8 <= kMaxCandTotal && make_plan(&p8, kRetryRows, n, d, 0, rc8, pl.ew) == SNG_OK && p8.ew == pl.ew) {
+                    pr = p8; pr.seed_stride = pr.seed_q = 0; pr.nsplit = 8;
+                }
+            }
             retry = true;
         }
     }

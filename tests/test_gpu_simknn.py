@@ -99,11 +99,14 @@ def test_build_matches_oracle(n, d, k, thr, rs, kind):
 
 @pytest.mark.parametrize("n,d", [(1500, 40), (20000, 24)])
 def test_massive_ties_go_through_exact_fallback(n, d):
-    """Sparse 0/1 features: most scores tie (many at exactly 0), so stage 2 cannot prove most rows and the exact
-    stage-3 scans (parallel waves + serial remainder) must reproduce the index tie-break."""
+    """A handful of distinct feature rows, each repeated hundreds of times: every row ties at cosine 1 with far more columns than
+    any candidate list holds, so stage 2 cannot prove it and the exact stage-3 scans (parallel waves + serial remainder) must
+    reproduce the index tie-break.  All-zero rows (a fifth of them) tie at 0 everywhere and are resolved by rule in stage 2."""
     from sngnn_b200 import simknn
     g = torch.Generator().manual_seed(n)
-    x = (torch.rand(n, d, generator=g) < 0.03).float()       # ~half the rows are all-zero: every score ties at 0
+    pats = torch.randn(5, d, generator=g)
+    pats[0] = 0
+    x = pats[torch.randint(0, 5, (n,), generator=g)]
     k, thr = 10, -1.0
     idx, sim, cnt, nfb = simknn.build_knn(x.to(DEV), k, thr, True, return_fallback=True)
     torch.cuda.synchronize()
@@ -112,6 +115,21 @@ def test_massive_ties_go_through_exact_fallback(n, d):
     print(f"ties n={n}: {res} fallback_rows={int(nfb[0])} retry_rows={int(nfb[1])}")
     assert int(nfb[0]) > n // 4
     assert res["out_of_band"] == 0, res
+    assert check_tie_order(idx, sim, cnt)
+    zero = (x.abs().sum(1) == 0)
+    assert torch.equal(idx.cpu().long()[zero], idx_ref[zero]) and bool((sim.cpu()[zero] == 0).all())
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.5])
+def test_sparse_binary_rows_with_zero_rows(thr):
+    """Sparse 0/1 features (a third of the rows all-zero, most scores exactly 0): lists identical to the oracle's."""
+    from sngnn_b200 import simknn
+    n, d, k = 1500, 40, 10
+    x = (torch.rand(n, d, generator=torch.Generator().manual_seed(n)) < 0.03).float()
+    idx, sim, cnt, nfb = simknn.build_knn(x.to(DEV), k, thr, True, return_fallback=True)
+    idx_ref, sim_ref, cnt_ref = _oracle(x, k, thr, True)
+    res = compare_lists(idx, cnt, idx_ref, cnt_ref, _score64(x), thr)
+    assert res["out_of_band"] == 0 and res["exact"] == n, res
     assert check_tie_order(idx, sim, cnt)
 
 
@@ -212,9 +230,10 @@ def test_build_without_retry_pass_matches_oracle(monkeypatch, debug_env):
     """SNG_KNN_NORETRY: unproven rows go straight to the exact scan (the path every row took before the retry pass existed)."""
     from sngnn_b200 import simknn
     monkeypatch.setenv("SNG_KNN_NORETRY", "1")
-    monkeypatch.setenv("SNG_KNN_CAND", "12")                     # two spare slots only: many rows cannot be proven
+    monkeypatch.setenv("SNG_KNN_CAND", "10")                     # no spare slot: many rows cannot be proven
     n, d, k = 6000, 65, 10
     x = _features(n, d, "clustered", seed=11)
+    x[100:140] = x[100]                                          # 40 identical rows: 39 ties at cosine 1 against a 10-slot list
     idx, sim, cnt, nfb = simknn.build_knn(x.to(DEV), k, 0.0, True, return_fallback=True)
     torch.cuda.synchronize()
     idx_ref, sim_ref, cnt_ref = _oracle(x, k, 0.0, True)
