@@ -1179,9 +1179,11 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
     pl->nsplit = ns;
     // threshold seeding: only for full builds (top_k known) that sweep many tiles with one list set per row
     pl->seed_stride = pl->seed_q = 0;
-    // (the seed pass is never column-split, so with many splits it would cost as much as the main pass)
+    // (the seed pass is never column-split: with ns splits it costs ns / stride of the main pass.  It still pays at every ns --
+    // a rank's share of a sharded build of a small database gets 3 splits, and measured there (arxiv shape, 1/8 of the rows)
+    // the unseeded lists cost 9.4 ms against 2.3 ms seeded: without a threshold every list starts with its warm-up inserts.)
     const bool forced = env_int("SNG_KNN_SEED_S", 2, 256) != 0;
-    if (top_k > 0 && (ns <= 2 || forced) && !env_flag("SNG_KNN_NOSEED")) {
+    if (top_k > 0 && !env_flag("SNG_KNN_NOSEED")) {
         if (forced) {
             const int stride = env_int("SNG_KNN_SEED_S", 2, 256);
             int q = env_int("SNG_KNN_SEED_Q", 1, kSeedGroups - 2);
