@@ -275,7 +275,8 @@ SNG_API int sng_graph_prepare(const int64_t* edge_index, int64_t num_edges, int6
 
 /* ------------------------------------------------------------------------------------------------
  * K1  all-pairs similarity-kNN builder (tcgen05 / TMA / TMEM), never materialising the N x N matrix.
- *   xq_f16  [nq , ldh]  normalised query rows  (FP16, zero padded, ldh % 8 == 0, ldh >= 16*ceil(d/16), 16-byte aligned)
+ *   xq_f16  [nq , ldh]  normalised query rows  (FP16, zero padded, ldh % 8 == 0, 16*ceil(d/16) <= ldh <= 16*ceil(d/16) + 64,
+ *                       16-byte aligned; d <= 4096 -- beyond d ~ 640 the query block is streamed instead of resident)
  *   xall_f16[n  , ldh]  normalised database rows
  *   query row r is global node q_offset + r (used for remove_self and for sharding by query rows)
  * Stage 1 (tensor cores; a seed pass over a column sample first sets every row's starting threshold) keeps, per query
@@ -285,6 +286,9 @@ SNG_API int sng_graph_prepare(const int64_t* edge_index, int64_t num_edges, int6
  * of the best possible score of any dropped column is flagged.
  * Flagged rows first get a RETRY pass (a second tensor-core pass over just those rows, with long candidate lists and a
  * much lower starting threshold); only rows that fail that proof too are recomputed by an exact FP32 scan (stage 3).
+ * The retry pass is sized from the number of flagged rows: the call reads that 4-byte count back and synchronises `stream`
+ * once, after stage 2 (nothing else in the library synchronises); on a stream that is being captured it launches one retry
+ * round of at most 16 K rows with the count on the device instead.  All-zero query rows are answered by rule in stage 2.
  * Outputs: idx [nq, top_k] int32 (-1 padded), sim [nq, top_k], cnt [nq]; n_fallback (device int32) counts
  * rows that needed stage 3, n_retry (device int32, may be NULL) rows that needed the retry pass.
  * Replaces (as "the reference rule on the complete graph") the selection of

@@ -850,20 +850,35 @@ __global__ void __launch_bounds__(256) simknn_rescore_kernel(
 
 // Retry pass, step 1: compact the FP16 rows of the first kRetryRows flagged query rows into one matrix (the TMA operand of
 // the second tensor-core pass); flagged rows beyond that go straight to the exact-scan list.
-constexpr int kRetryRows = 16384;          // capacity of the retry pass; flagged rows beyond it go to the exact scan
-__global__ void __launch_bounds__(256) simknn_retry_gather_kernel(const uint16_t* __restrict__ xq, int64_t ldb, const int* __restrict__ fb_rows,
-                                                                 const int* __restrict__ n_fb, uint16_t* __restrict__ xq_retry,
-                                                                 int* __restrict__ fb2_rows, int* __restrict__ n_fb2) {
+// Capacity of the retry pass (flagged rows beyond it go to the exact scan): every query row of small calls, a quarter of a
+// million for large ones.  It used to be 16 K: inputs whose rows sit closer together than the FP16 scoring error (dense
+// clusters at large d with a large top_k) flag most rows, and the exact scan re-reads the whole database per row.
+constexpr int kRetryRowsMin = 16384, kRetryRowsMax = 262144;
+static int retry_rows(int64_t nq) {
+    int64_t c = (nq + 255) / 256 * 256;
+    if (c < kRetryRowsMin) c = kRetryRowsMin;
+    if (c > kRetryRowsMax) c = kRetryRowsMax;
+    return (int)c;
+}
+constexpr int kRetryRounds = 48;           // the retry pass runs in rounds of retry_rows(nq) flagged rows (fixed buffers, counts on the device)
+// round_cnt[r] = flagged rows of round r; flagged rows beyond the last round go straight to the exact-scan list
+__global__ void __launch_bounds__(256) simknn_retry_rounds_kernel(const int* __restrict__ fb_rows, const int* __restrict__ n_fb, int cap, int rounds,
+                                                                 int* __restrict__ round_cnt, int* __restrict__ fb2_rows, int* __restrict__ n_fb2) {
     const int nfb = *n_fb;
+    for (int r = threadIdx.x; r < rounds; r += blockDim.x) round_cnt[r] = max(0, min(cap, nfb - r * cap));
+    for (long long f = (long long)rounds * cap + threadIdx.x; f < nfb; f += blockDim.x) fb2_rows[atomicAdd(n_fb2, 1)] = fb_rows[f];
+}
+__global__ void __launch_bounds__(256) simknn_retry_gather_kernel(const uint16_t* __restrict__ xq, int64_t ldb, const int* __restrict__ fb_rows,
+                                                                 const int* __restrict__ n_round, uint16_t* __restrict__ xq_retry) {
+    const int nr = *n_round;
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
     const int64_t vec = ldb / 8;                                             // 16-byte chunks per row (ldb % 8 == 0)
-    for (int f = w; f < min(nfb, kRetryRows); f += nw) {
+    for (int f = w; f < nr; f += nw) {
         const uint4* src = reinterpret_cast<const uint4*>(xq + (int64_t)fb_rows[f] * ldb);
         uint4* dst = reinterpret_cast<uint4*>(xq_retry + (int64_t)f * ldb);
         for (int64_t i = lane; i < vec; i += 32) dst[i] = src[i];
     }
-    for (int f = kRetryRows + w * 32 + lane; f < nfb; f += nw * 32) fb2_rows[atomicAdd(n_fb2, 1)] = fb_rows[f];
 }
 
 // Stage 3 (parallel form): work item = (flagged row f, chunk of kChunk columns).  Scan: exact scores of the chunk in
@@ -1277,7 +1292,7 @@ static int check_common(const char* fn, const void* xq, const void* xall, int64_
 // 1.2e-4 covers K <= 640, longer contractions scale it.
 constexpr float kScoreEps = 0.0009765625f + 1.2e-4f;
 static float score_eps(int64_t d) { return 0.0009765625f + 1.2e-4f * (d > 640 ? (float)d / 640.0f : 1.0f); }
-static int64_t retry_ld(int64_t d) { const int64_t d16 = (d + 15) / 16 * 16; return d16 + 64 > 1024 ? d16 + 64 : 1024; }   // widest ldb of the retry query matrix
+static int64_t retry_ld(int64_t d) { return (d + 15) / 16 * 16 + 64; }   // widest ldb (FP16 row pitch) the build accepts: the retry query matrix is sized for it
 
 }  // namespace knn
 }  // namespace sng
@@ -1297,7 +1312,7 @@ extern "C" size_t sng_simknn_workspace_bytes(int64_t nq, int64_t n, int64_t d, i
     const size_t part = (size_t)kFbWaveRows * ((n + kChunk - 1) / kChunk) * top_k;
     return align256(slots * 4) * 2 + align256((size_t)nq * pl.lists() * 4) + align256((size_t)nq * 4) + 2 * align256(part * 4) +
            align256((size_t)nq * kSeedGroups * 4) + 256 +
-           align256((size_t)kRetryRows * retry_ld(d) * 2) + 2 * align256((size_t)kRetryRows * kMaxCandTotal * 4) + align256((size_t)kRetryRows * 8 * 4) +
+           align256((size_t)retry_rows(nq) * retry_ld(d) * 2) + 2 * align256((size_t)retry_rows(nq) * kMaxCandTotal * 4) + align256((size_t)retry_rows(nq) * 8 * 4) +
            align256((size_t)nq * 4) + 256 + 1024;
 }
 
@@ -1369,6 +1384,7 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
     float* seeds = reinterpret_cast<float*>(w); w += align256((size_t)nq * kSeedGroups * 4);
     int* phase = reinterpret_cast<int*>(w); w += 256;
     // retry pass buffers
+    const int kRetryRows = retry_rows(nq);
     uint16_t* xq_retry = reinterpret_cast<uint16_t*>(w); w += align256((size_t)kRetryRows * retry_ld(d) * 2);
     float* rcand_val = reinterpret_cast<float*>(w); w += align256((size_t)kRetryRows * kMaxCandTotal * 4);
     int* rcand_idx = reinterpret_cast<int*>(w); w += align256((size_t)kRetryRows * kMaxCandTotal * 4);
@@ -1422,16 +1438,43 @@ extern "C" int sng_simknn_build(const uint16_t* xq, const uint16_t* xall, int64_
         // Retry pass: the (few) unproven rows -- a seed threshold that hid a neighbour, or more near-cut columns than the list
         // has slots -- go through the tensor cores once more as their own small query matrix, unseeded, with long lists and
         // the column range split over many CTAs; only rows that fail this proof too reach the exact FP32 scan.
-        simknn_retry_gather_kernel<<<64, 256, 0, st>>>(xq, ldb, fb_rows, n_fb1, xq_retry, fb2_rows, n_fallback);
         // seeded like the main pass but from a much lower quantile (10th..12th of the 16 group maxima instead of the 6th): it
         // cannot hide a neighbour (that would take top_k of top_k in a 1/stride sample) and spares the lists the warm-up
         if (pl.seed_stride > 0) { pr.seed_stride = pl.seed_stride; pr.seed_q = pl.seed_q + 4 < kSeedGroups - 4 ? pl.seed_q + 4 : kSeedGroups - 4; }
-        if (int rc = launch_stage1(pr, xq_retry, xall, ldb, kRetryRows, q_offset, n, thr_lo, remove_self, rcand_val, rcand_idx, rcand_min,
-                                   pl.seed_stride > 0 ? seeds : nullptr, nullptr, nullptr, st, n_fb1, fb_rows)) return rc;
+        // How many rows were flagged decides how many launches follow and how large they are, and a launch sized for the worst
+        // case costs its CTAs' scheduling even when they leave at once (16 K idle CTAs of this kernel: 0.9 ms).  So the call
+        // reads the 4-byte count back -- its one host synchronisation -- and sizes the rounds exactly: none at all for an input
+        // whose rows were all proven, rounds of kRetryRows rows through the same buffers otherwise.  On a capturing stream
+        // (no synchronisation allowed) one round of at most 16 K rows is launched with the count on the device; the rest
+        // of the flagged rows then go to the exact scan.
+        cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap_status) != cudaSuccess) { cudaGetLastError(); cap_status = cudaStreamCaptureStatusNone; }
+        const bool capturing = cap_status != cudaStreamCaptureStatusNone;
+        int flagged = 0, rounds = 1, cap = kRetryRows;
+        if (capturing) {
+            cap = kRetryRowsMin < kRetryRows ? kRetryRowsMin : kRetryRows;
+        } else {
+            if (cudaMemcpyAsync(&flagged, n_fb1, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+                return check_launch("sng_simknn_build flagged-row count");
+            rounds = (flagged + cap - 1) / cap;
+            if (rounds > kRetryRounds) rounds = kRetryRounds;
+        }
+        int* round_cnt = phase + 16;                                  // (the 256-byte phase block: ints 0..7 = sweep phases)
+        if (rounds > 0) simknn_retry_rounds_kernel<<<1, 256, 0, st>>>(fb_rows, n_fb1, cap, rounds, round_cnt, fb2_rows, n_fallback);
         const int mr = pr.lists() * pr.cand;
-        simknn_rescore_kernel<<<kRetryRows / 8, 256, (size_t)8 * 2 * 3 * mr * 4, st>>>(
-            xq32, xall32, ld32, d4, kRetryRows, (int)n, (int)q_offset, remove_self, mr, pr.lists(), top_k, thr, eps, rcand_val, rcand_idx, rcand_min,
-            idx, sim, cnt, fb2_rows, n_fallback, n_fb1, fb_rows);
+        for (int r = 0; r < rounds; ++r) {
+            const int* rows_r = fb_rows + (size_t)r * cap;
+            // rows of this round: exact on the host unless capturing (then the grid covers `cap` rows and the device count trims it)
+            const int n_r = capturing ? cap : (flagged - r * cap < cap ? flagged - r * cap : cap);
+            const int n_launch = (n_r + 2 * BM - 1) / (2 * BM) * (2 * BM);
+            simknn_retry_gather_kernel<<<(sm_count() > 0 ? sm_count() : 148) * 2, 256, 0, st>>>(xq, ldb, rows_r, round_cnt + r, xq_retry);
+            if (int rc = launch_stage1(pr, xq_retry, xall, ldb, n_launch, q_offset, n, thr_lo, remove_self, rcand_val, rcand_idx, rcand_min,
+                                       pl.seed_stride > 0 ? seeds : nullptr, nullptr, nullptr, st, round_cnt + r, rows_r)) return rc;
+            const int rblocks = (n_launch + 7) / 8 < 4096 ? (n_launch + 7) / 8 : 4096;
+            simknn_rescore_kernel<<<rblocks, 256, (size_t)8 * 2 * 3 * mr * 4, st>>>(
+                xq32, xall32, ld32, d4, n_launch, (int)n, (int)q_offset, remove_self, mr, pr.lists(), top_k, thr, eps, rcand_val, rcand_idx, rcand_min,
+                idx, sim, cnt, fb2_rows, n_fallback, round_cnt + r, rows_r);
+        }
         if (int rc = check_launch("simknn retry pass")) return rc;
     }
     if (n_retry) {
