@@ -242,3 +242,28 @@ def test_build_without_retry_pass_matches_oracle(monkeypatch, debug_env):
     assert res["out_of_band"] == 0, res
     assert int(nfb[0]) > 0 and int(nfb[0]) == int(nfb[1])
     assert check_tie_order(idx, sim, cnt)
+
+
+def test_build_inside_a_cuda_graph_capture():
+    """The build reads the flagged-row count back (one host synchronisation) to size its retry rounds; on a capturing stream it
+    must not synchronise: one fixed retry round with the count on the device.  Captured + replayed lists == eager lists."""
+    from sngnn_b200 import simknn
+    n, d, k = 4000, 65, 10
+    x = _features(n, d, "clustered", seed=5)
+    x[200:500] = x[200]                                           # 300 identical rows: more ties than a main-pass list holds -> flagged
+    xf, xh = simknn.normalize_operands(x.to(DEV))
+    eager = simknn.build_knn_normalized(xf, xh, d, k, 0.0, True, return_fallback=True)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        simknn.build_knn_normalized(xf, xh, d, k, 0.0, True)      # warm-up on the side stream (allocations, function attributes)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        captured = simknn.build_knn_normalized(xf, xh, d, k, 0.0, True, return_fallback=True)
+    g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eager[:3], captured[:3]):
+        assert torch.equal(a, b)
+    assert int(captured[3][1]) == int(eager[3][1]) > 0            # the same rows were flagged for the retry pass
