@@ -1205,9 +1205,11 @@ static int make_plan(Plan* pl, int64_t nq, int64_t n, int64_t d, int top_k, int 
             if (!q) q = seed_quantile(top_k, stride, 2e-5);
             if (pl->tiles / stride >= 8 && q <= kSeedGroups - 4) { pl->seed_stride = stride; pl->seed_q = q; }
         } else {
-            // sample 1/16 of the columns when there are plenty, more of them for small databases; a large top_k needs a
+            // sample 1/32 (1/16) of the columns when there are plenty, more of them for small databases; a large top_k needs a
             // sparser sample for the quantile to stay inside the 16 groups
-            for (int stride = pl->tiles >= 512 ? 16 : (pl->tiles / 32 > 4 ? pl->tiles / 32 : 4); stride <= 64 && !pl->seed_stride; stride *= 2) {
+            // (pokec shape, 6,379 tiles: stride 16 / 24 / 32 / 48 / 64 -> 397.1 / 392.5 / 389.1 / 389.7 / 390.5 ms per build: the
+            // seed pass costs 1/stride of a sweep, a looser threshold a few more inserts)
+            for (int stride = pl->tiles >= 2048 ? 32 : (pl->tiles >= 512 ? 16 : (pl->tiles / 32 > 4 ? pl->tiles / 32 : 4)); stride <= 64 && !pl->seed_stride; stride *= 2) {
                 const int q = seed_quantile(top_k, stride, 2e-5);
                 if (pl->tiles / stride >= 8 && q <= kSeedGroups - 4) { pl->seed_stride = stride; pl->seed_q = q; }
             }

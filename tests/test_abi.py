@@ -95,13 +95,19 @@ def test_module_surface_matches_reference_signatures():
 def test_simknn_plan_is_host_logic():
     """sng_simknn_plan needs no GPU: the launch plan of the build for the named shapes."""
     from sngnn_b200 import simknn
-    p = simknn.build_plan(1632803, 1632803, 65, 10)                      # pokec: split mode, seeded 1/16 with the 6th of 16 group maxima
-    assert (p["ew"], p["kblocks"], p["nsplit"], p["seed_stride"], p["seed_q"], p["cand"]) == (4, 2, 1, 16, 6, 32), p
+    p = simknn.build_plan(1632803, 1632803, 65, 10)                      # pokec: split mode, seeded 1/32 with the 5th of 16 group maxima
+    assert (p["ew"], p["kblocks"], p["nsplit"], p["seed_stride"], p["seed_q"], p["cand"]) == (4, 2, 1, 32, 5, 32), p
     assert p["stages"] % p["kblocks"] == 0
     p = simknn.build_plan(204101, 1632803, 65, 10)                       # one rank of an 8-GPU build: same plan
-    assert (p["ew"], p["nsplit"], p["seed_stride"]) == (4, 1, 16), p
+    assert (p["ew"], p["nsplit"], p["seed_stride"]) == (4, 1, 32), p
+    p = simknn.build_plan(169343, 169343, 128, 10)                       # arxiv-year shape: 662 tiles -> 1/16 sample
+    assert (p["ew"], p["nsplit"], p["seed_stride"], p["seed_q"]) == (4, 1, 16, 6), p
+    p = simknn.build_plan(21168, 169343, 128, 10)                        # one rank of 8 on it: column splits, still seeded
+    assert p["nsplit"] == 3 and p["seed_stride"] == 16, p
     p = simknn.build_plan(2923922, 2923922, 269, 10)                     # snap-patents: K = 272 -> two 256-column stages
-    assert (p["ew"], p["kblocks"], p["seed_stride"]) == (2, 5, 16), p
+    assert (p["ew"], p["kblocks"], p["seed_stride"]) == (2, 5, 32), p
+    p = simknn.build_plan(2277, 2277, 2325, 10)                          # Chameleon's raw features: streamed query block, one epilogue warp per quarter
+    assert p["ew"] == 1 and p["kblocks"] == 37, p
     p = simknn.build_plan(100000, 100000, 512, 50)                       # sweep corner: A alone is 128 KB -> thinner margin, 2 stages
     assert p["ew"] == 1 and 64 <= p["cand"] <= 72 and p["stages"] >= 2 and p["seed_q"] <= 12, p      # margin >= 14 before a third ring stage
     p = simknn.build_plan(2277, 2277, 2325 // 8, 10)                     # tiny database: column-split, unseeded
