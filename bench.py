@@ -125,7 +125,7 @@ def run_reference(args):
                        "features": args.features, "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- our arm
@@ -699,13 +699,31 @@ def run_ours(args):
                                      "simknn_rescore_kernel (retry)", "4 x (simknn_fb_scan_kernel, simknn_fb_merge_kernel)", "simknn_fb_stream_kernel"],
                 "roofline": roofline, "cpu_baseline": head.get("cpu"), "clocks": clocks, "parity": head["parity"], "configs": configs}
         line.update(extras)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         cx.dist.barrier()
         cx.dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the real stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
+    # Libraries print to file descriptor 1 behind Python's back (NCCL announces its version there when a communicator is
+    # created): keep the real stdout for the result line only and send everything else to stderr.
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
