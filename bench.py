@@ -693,9 +693,9 @@ def run_ours(args):
                            "parallelism": f"row-shard x{world}" + (" + one NCCL all-gather of FP32 x-hat (FP16 operand converted locally)" if world > 1 else "")},
                 "e2e": {"value": pairs / (ms_e2e * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes"],
                         "d2h_bytes_per_step": head["d2h_bytes"], "ms_per_step": ms_e2e, "copy_ms_rank0": head["e2e_copy_ms"]},
-                "gpu_launches": (15 + (1 if plan["seed_stride"] > 0 else 0)) * args.steps,
+                "gpu_launches": (16 + (1 if plan["seed_stride"] > 0 else 0)) * args.steps,
                 "kernels_per_step": ["rownorm_kernel"] + (["simknn_stage1_kernel<seed>"] if plan["seed_stride"] > 0 else []) +
-                                    ["simknn_stage1_kernel", "simknn_rescore_kernel", "simknn_retry_gather_kernel", "simknn_stage1_kernel (retry)",
+                                    ["simknn_stage1_kernel", "simknn_rescore_kernel", "simknn_retry_rounds_kernel", "simknn_retry_gather_kernel", "simknn_stage1_kernel (retry)",
                                      "simknn_rescore_kernel (retry)", "4 x (simknn_fb_scan_kernel, simknn_fb_merge_kernel)", "simknn_fb_stream_kernel"],
                 "roofline": roofline, "cpu_baseline": head.get("cpu"), "clocks": clocks, "parity": head["parity"], "configs": configs}
         line.update(extras)
