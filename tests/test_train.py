@@ -100,3 +100,23 @@ def test_main_runs_the_readme_configuration():
     assert len(hist) == 4 and all(torch.isfinite(torch.tensor(h[0])) for h in hist)
     assert hist[-1][0] < hist[0][0]                       # the training loss goes down
     assert any(l.startswith("Epoch: 3 | Train_loss") for l in lines) and lines[-1].startswith("Part 0 final test acc")
+
+
+def test_load_data_from_a_graph_file(tmp_path):
+    """`--dataset path.pt`: tensors, ten split columns selected by part_id (both layouts), class count."""
+    n = 50
+    g = torch.Generator().manual_seed(0)
+    masks = torch.rand(n, 10, generator=g) < 0.5
+    blob = {"x": torch.randn(n, 6, generator=g).double(), "edge_index": torch.randint(0, n, (2, 120), generator=g).int(),
+            "y": torch.randint(0, 3, (n,), generator=g), "train_mask": masks, "val_mask": masks.t().contiguous(), "test_mask": masks[:, 0]}
+    path = str(tmp_path / "graph.pt")
+    torch.save(blob, path)
+    data, c = T.load_data(path, part_id=4, device="cpu")
+    assert c == 3 and data.x.dtype == torch.float32 and data.edge_index.dtype == torch.int64
+    assert torch.equal(data.train_mask, masks[:, 4]) and torch.equal(data.val_mask, masks[:, 4]) and torch.equal(data.test_mask, masks[:, 0])
+    del blob["train_mask"], blob["val_mask"], blob["test_mask"]
+    torch.save(blob, path)
+    data, _ = T.load_data(path, part_id=1, device="cpu")             # no masks in the file: the seeded 48/32/20 split
+    assert int(data.train_mask.sum()) == 24 and int(data.val_mask.sum()) == 16 and int(data.test_mask.sum()) == 10
+    with pytest.raises(ValueError):
+        T.load_data("no-such-shape-or-file", 0, "cpu")
