@@ -199,11 +199,37 @@ class _ShardedPPFuse(torch.autograd.Function):
         return g - g0, dw, g0.sum(0)[:c], dbeta, dbias, None, None, None
 
 
-def _complete_dw(g0, shard, n, nl, c, cp):
+def _gather_row_blocks_async(local, n):
+    """Start the all-gather of row blocks without waiting for it: returns (work | None, result [n, ld], buffers the caller keeps
+    alive until it has waited).  The collective runs on the backend's own stream; `work.wait()` makes the current stream
+    wait for it.  (NCCL only; other backends gather at once.)"""
+    ws, _ = world()
+    local = local.contiguous()
+    if ws == 1:
+        return None, local, None
+    if dist.get_backend() != "nccl":
+        return None, all_gather_rows(local, n), None
+    r = rows_per_rank(n, ws)
+    ld = local.size(1)
+    pad = local if local.size(0) == r else torch.zeros(r, ld, dtype=local.dtype, device=local.device)
+    if pad is not local:
+        pad[: local.size(0)].copy_(local)
+    out = torch.empty(ws * r, ld, dtype=local.dtype, device=local.device)
+    work = dist.all_gather_into_tensor(out, pad, async_op=True)
+    return work, out[:n], (pad, out)
+
+
+def _complete_dw(g0, shard, n, nl, c, cp, pending=None):
     """dL/dw.weight [C, N] (complete, identical on every rank) from this shard's g0 = beta * dL/dout rows: row t of dL/dW^T
-    gathers g0 over the (shifted) sources of t's in-edges -- any row of g0, hence the all-gather."""
+    gathers g0 over the (shifted) sources of t's in-edges -- any row of g0, hence the all-gather.  `pending` = an all-gather of
+    g0 the caller already started (`_gather_row_blocks_async`), so that it overlaps the caller's kernels."""
     from . import functional as SF
-    g0_all = _gather_row_blocks(g0, n)
+    if pending is None:
+        g0_all = _gather_row_blocks(g0, n)
+    else:
+        work, g0_all, _keep = pending
+        if work is not None:
+            work.wait()
     if nl:
         dwt_local = SF.spmm(g0_all.contiguous(), shard.rowptr_in, shard.col_in_shift, nl)
     else:
@@ -241,13 +267,14 @@ class _ShardedFusedAgg(torch.autograd.Function):
         nl = shard.n
         g = g.contiguous()
         g0 = g * beta
+        pending = _gather_row_blocks_async(g0, n)                 # needed only for dL/dW^T below: overlaps the aggregation backward
         g1 = (g - g0).contiguous()
         dval, dnrm, dh = torch.zeros_like(h_all), torch.zeros_like(h_all), torch.empty_like(h_all)
         _C.call("sng_edge_agg_bwd", h_all, _C.ptr(h_all), _C.ptr(inv_norm), _C.ptr(g1), n_total, nl, ctx.lo, cp, cp,
                 _C.ptr(shard.rowptr_in), _C.ptr(shard.col_in), k, _C.ptr(sel_src), _C.ptr(sel_w), _C.ptr(sel_cnt),
                 _C.ptr(shard.inv_deg), _C.ptr(dval), _C.ptr(dnrm), _C.ptr(dh))
         dbeta = (diff * g).sum().reshape(1)
-        dw = _complete_dw(g0, shard, n, nl, c, cp)
+        dw = _complete_dw(g0, shard, n, nl, c, cp, pending)
         dbias = g.sum(0)[:c] if ctx.has_bias else None
         return dh, dw, g0.sum(0)[:c], dbeta, dbias, None, None, None, None, None
 
