@@ -35,6 +35,10 @@ def _worker(rank, ws, port, n, ret):
     # --- padded all-gather reproduces the full matrix on every rank
     full = D.all_gather_rows(x[lo:hi].clone(), n)
     assert torch.equal(full, x)
+    work, full2, keep = D._gather_row_blocks_async(x[lo:hi].clone(), n)   # the started-early form (NCCL: async handle; gloo: done at once)
+    if work is not None:
+        work.wait()
+    assert torch.equal(full2, x)
 
     # --- sharded kNN build == rows [lo,hi) of the unsharded build
     def normalize(xs):
